@@ -1,0 +1,103 @@
+"""Pins oracle/cvae_oracle.py against the fixtures frozen from the reference's own classes
+(oracle/make_golden.py).  CPU only; no /root/reference needed."""
+import os
+from collections import OrderedDict
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import cvae_oracle as O
+
+CASES = {
+    "real48_z10": O.CVAEConfig(z_dim=10),
+    "synth64_labelled_z10": O.CVAEConfig(z_dim=10, num_classes=4),
+    "synth24_z32": O.CVAEConfig(z_dim=32),
+    "uni_wave24_z10": O.CVAEConfig(z_dim=10, multimodal=False, output_size_wave=50),
+    "uni_isi24_z10": O.CVAEConfig(z_dim=10, multimodal=False, output_size_wave=100),
+}
+
+
+def _load(golden_dir, tag):
+    return np.load(os.path.join(golden_dir, tag + ".npz"))
+
+
+def _heads(d, names, n=6):
+    return np.stack([np.pad(d[k].detach().double().flatten()[:n].numpy(), (0, max(0, n - d[k].numel()))) for k in names])
+
+
+@pytest.mark.parametrize("tag", list(CASES))
+def test_init_bit_exact(golden_dir, tag):
+    cfg, fx = CASES[tag], _load(golden_dir, tag)
+    st = O.init_state(cfg, seed=42)
+    names = [str(s) for s in fx["param_names"]]
+    assert names == O.param_names(cfg)
+    assert np.array_equal(_heads(st, names), fx["init_head"])
+    assert np.array_equal(np.array([st[n].double().sum().item() for n in names]), fx["init_sum"])
+    assert np.array_equal(np.array([st[n].double().abs().sum().item() for n in names]), fx["init_abs"])
+
+
+@pytest.mark.parametrize("tag", list(CASES))
+@pytest.mark.parametrize("dt", ["f32", "f64"])
+def test_train_step_and_eval_match_reference(golden_dir, tag, dt):
+    cfg, fx = CASES[tag], _load(golden_dir, tag)
+    dtype = torch.float32 if dt == "f32" else torch.float64
+    lr, wd, beta, w1, w2, clip = [float(v) for v in fx["hyper"]]
+    x1 = torch.tensor(fx["x1"]).to(dtype)
+    x2 = torch.tensor(fx["x2"]).to(dtype) if "x2" in fx else None
+    labels = torch.tensor(fx["labels"])
+    cls, src = (labels.unbind(1) if labels.dim() == 2 else (None, labels))
+    st = O.init_state(cfg, seed=42)
+    st = OrderedDict((k, v.to(dtype) if v.is_floating_point() else v) for k, v in st.items())
+    opt = O.new_opt_state(st, cfg)
+    keys = ["enc", "mu", "logvar", "dec1"] + (["dec2"] if cfg.multimodal else [])
+    tight = dt == "f64"
+    torch.manual_seed(int(fx["eps_seeds"][0]))
+    eps = torch.randn(x1.shape[0], cfg.z_dim).to(dtype)
+    with torch.no_grad():
+        o0, _, _ = O.forward(st, cfg, x1, x2, src, cls, eps, train=True)
+    for k in keys:
+        r = torch.tensor(fx[f"{dt}_fwd0_{k}"])
+        tol = (1e-10 if tight else 2e-5) * max(1.0, r.abs().max().item())
+        assert (o0[k] - r).abs().max().item() <= tol, k
+    # first optimisation step (later steps are chaotic in fp32; fp64 stays tight)
+    nsteps = len(fx["eps_seeds"]) if tight else 1
+    for s in range(nsteps):
+        torch.manual_seed(int(fx["eps_seeds"][s]))
+        eps = torch.randn(x1.shape[0], cfg.z_dim).to(dtype)
+        st, opt, info = O.train_step(st, opt, cfg, x1, x2, labels, eps, lr=lr, weight_decay=wd, beta=beta,
+                                     w1=w1, w2=w2, max_norm=clip)
+        ref_loss = fx[f"{dt}_s{s}_loss"]
+        got = np.array([info["loss"].item(), info["mse1"].item(), info["mse2"].item(), info["kl"].item()])
+        np.testing.assert_allclose(got, ref_loss, rtol=1e-11 if tight else 2e-6, atol=1e-12)
+        np.testing.assert_allclose(info["grad_norm"].item(), float(fx[f"{dt}_s{s}_grad_norm"]),
+                                   rtol=1e-10 if tight else 2e-3)
+        gn = [str(n) for n in fx[f"s{s}_grad_names"]]
+        assert sorted(gn) == sorted(info["grads_raw"].keys())
+        if tight:
+            l2 = np.array([info["grads_raw"][n].double().norm().item() for n in gn])
+            np.testing.assert_allclose(l2, fx[f"f64_s{s}_grad_l2"], rtol=1e-8, atol=1e-14)
+            np.testing.assert_allclose(_heads(info["grads_raw"], gn), fx[f"f64_s{s}_grad_head"], rtol=1e-7, atol=1e-13)
+            names = [str(n) for n in fx["param_names"]]
+            np.testing.assert_allclose(_heads(st, names), fx[f"f64_s{s}_param_head"], rtol=1e-9, atol=1e-12)
+            rn = [str(n) for n in fx["running_names"]]
+            np.testing.assert_allclose(_heads(st, rn), fx[f"f64_s{s}_running_head"], rtol=1e-10, atol=1e-13)
+        else:
+            names = [str(n) for n in fx["param_names"]]
+            d = np.abs(_heads(st, names) - fx[f"f32_s{s}_param_head"]).max()
+            assert d <= 2 * lr + 1e-7  # Adam's first step is ~lr*sign(g): noise-level grads may flip
+
+
+def test_dataset_transform_fixture(golden_dir):
+    fx = np.load(os.path.join(golden_dir, "cellexplorer_raw48.npz"))
+    for i in range(fx["wf"].shape[0]):
+        a, b = O.dataset_item(fx["wf"][i], fx["isi"][i])
+        assert np.array_equal(a.numpy(), fx["x1"][i]) and np.array_equal(b.numpy(), fx["x2"][i])
+
+
+def test_zscore_variants():
+    e = torch.randn(7, 10, dtype=torch.float64)
+    np.testing.assert_allclose(O.zscore_rows(e, 0).numpy(),
+                               (e.numpy() - e.numpy().mean(1, keepdims=True)) / e.numpy().std(1, keepdims=True))
+    np.testing.assert_allclose(O.zscore_rows(e, 1).numpy(),
+                               ((e - e.mean(1)[:, None]) / e.std(1)[:, None]).numpy())
