@@ -1,0 +1,872 @@
+// libhippie_b200.so -- C ABI (include/hippie_b200.h) and the layer program of the HIPPIE cVAE.
+//
+// The engine owns no tensor memory: parameters, gradients, AdamW state and BatchNorm buffers are
+// flat device buffers handed over by hippie_bind(); activations live in a caller-provided workspace.
+// The network structure below restates, as launch sequences over channels-last padded tensors,
+//   ResNet18Enc / BasicBlockEnc      reference hippie/backbones.py:19-41, 73-103
+//   ResNet18Dec / BasicBlockDec      reference hippie/backbones.py:44-70, 106-141
+//   MultiModalCVAE / unimodal twin   reference hippie/model.py:350-432, 12-72
+//   training_step loss               reference hippie/model.py:454-482
+// and their backward passes (autograd in the reference).
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/hippie_b200.h"
+#include "kernels.cuh"
+
+using namespace hp;
+
+namespace {
+
+struct Param {
+  std::string name;
+  int ndim = 0;
+  int64_t shape[3] = {0, 0, 0};
+  int64_t off = 0, numel = 0;
+  int layout = HIPPIE_LAYOUT_NATIVE;
+};
+struct BNInfo {
+  std::string name;
+  int C = 0;
+  int gamma = -1, beta = -1;  // param indices
+  int64_t run_off = 0;        // offset into bn_mean / bn_var
+  int64_t coef_off = 0;       // workspace offset of the 8*C coefficient block
+};
+struct Act {
+  std::string name;
+  int L = 0, C = 0;
+  int64_t off = 0;  // workspace float offset of padded row 0
+};
+struct Conv {
+  int w = -1, b = -1;
+  int cin = 0, cout = 0, k = 3, stride = 1;
+  int64_t wt_off = -1;
+};
+struct EncBlock {
+  Conv c1, c2, cs;
+  int bn1 = -1, bn2 = -1, bns = -1;
+  bool down = false;
+  int x = -1, c1o = -1, a1 = -1, c2o = -1, cso = -1, out = -1;
+  int g_a1 = -1, dc1 = -1, dc2 = -1, dcs = -1;
+};
+struct Encoder {
+  std::string prefix;
+  int stem_w = -1, bn0 = -1, Lin = 0, L0 = 0;
+  int c0 = -1, a0 = -1, dc0 = -1;
+  EncBlock blk[8];
+  int lin_w = -1, lin_b = -1;
+  int64_t pooled = 0, h = 0, dh = 0;  // workspace offsets
+};
+struct DecBlock {
+  Conv c2, c1, cs;
+  int bn2 = -1, bn1 = -1, bns = -1;
+  bool up = false;
+  int x = -1, x_up = -1, c2o = -1, a2 = -1, a2_up = -1, c1o = -1, cso = -1, out = -1, out_up = -1;
+  int dc2 = -1, dc1 = -1, dcs = -1, g_a2 = -1, g_a2_up = -1, g_x_up = -1;
+};
+struct Decoder {
+  std::string prefix;
+  int lin_w = -1, lin_b = -1, t0 = -1;
+  DecBlock blk[8];
+  int wc = -1, bc = -1, lo_w = -1, lo_b = -1, Lo = 0;
+  int64_t d = 0, dd = 0, gx0 = 0, y = 0, ddec = 0, dy = 0, dec = 0, part = 0;  // workspace offsets
+};
+struct Branch {
+  cudaStream_t st = nullptr;
+  float* part = nullptr;   // BatchNorm statistics / stem / tail partials
+  float* bpart = nullptr;  // BatchNorm backward partials
+};
+
+}  // namespace
+
+struct hippie_engine {
+  hippie_cfg cfg{};
+  std::string err;
+  int sm_count = 148;
+  std::vector<Param> params;
+  std::map<std::string, int> pidx;
+  std::vector<BNInfo> bns;
+  std::map<std::string, int> bidx;
+  std::vector<Act> acts;
+  std::map<int, int> gact;  // activation index -> gradient tensor index
+  int64_t param_floats = 0, bn_floats = 0, ws_floats = 0;
+  int n_enc = 0, n_dec = 0;
+  Encoder enc[2];
+  Decoder dec[2];
+  HeadParams headp{};
+  int64_t head_scratch = 0, scal_off = 0, part_off[2] = {0, 0}, bpart_off[2] = {0, 0}, adam_part = 0;
+  int64_t part_floats = 0, bpart_floats = 0;
+  int64_t wt_table_off = 0, bn_table_off = 0;
+  std::vector<WtEntry> wt_table;
+  std::vector<BnEvalEntry> bn_table;
+  int cls_emb = -1;
+  // bound buffers
+  float *P = nullptr, *G = nullptr, *M1 = nullptr, *M2 = nullptr, *bn_mean = nullptr, *bn_var = nullptr;
+  int64_t* bn_count = nullptr;
+  float* ws = nullptr;
+  bool bound = false;
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  int launches = 0;
+
+  // ---- construction -------------------------------------------------------------------------
+  int64_t take(int64_t floats) {
+    int64_t r = ws_floats;
+    ws_floats += (floats + 63) & ~(int64_t)63;
+    return r;
+  }
+  int add_param(const std::string& name, int ndim, int64_t s0, int64_t s1, int64_t s2, int layout) {
+    Param p;
+    p.name = name, p.ndim = ndim, p.shape[0] = s0, p.shape[1] = s1, p.shape[2] = s2, p.layout = layout;
+    p.numel = s0 * (ndim > 1 ? s1 : 1) * (ndim > 2 ? s2 : 1);
+    p.off = param_floats;
+    param_floats += (p.numel + 3) & ~(int64_t)3;
+    pidx[name] = (int)params.size();
+    params.push_back(p);
+    return (int)params.size() - 1;
+  }
+  void spec_conv(const std::string& n, int cout, int cin, int k, bool bias) {
+    add_param(n + ".weight", 3, cout, cin, k, HIPPIE_LAYOUT_CONV_OKI);
+    if (bias) add_param(n + ".bias", 1, cout, 0, 0, HIPPIE_LAYOUT_NATIVE);
+  }
+  void spec_bn(const std::string& n, int c) {
+    BNInfo b;
+    b.name = n, b.C = c;
+    b.gamma = add_param(n + ".weight", 1, c, 0, 0, HIPPIE_LAYOUT_NATIVE);
+    b.beta = add_param(n + ".bias", 1, c, 0, 0, HIPPIE_LAYOUT_NATIVE);
+    b.run_off = bn_floats;
+    bn_floats += (c + 3) & ~3;
+    bidx[n] = (int)bns.size();
+    bns.push_back(b);
+  }
+  void spec_linear(const std::string& n, int nout, int nin) {
+    add_param(n + ".weight", 2, nout, nin, 0, HIPPIE_LAYOUT_NATIVE);
+    add_param(n + ".bias", 1, nout, 0, 0, HIPPIE_LAYOUT_NATIVE);
+  }
+  // ResNet18Enc.__init__ (hippie/backbones.py:74-84); BasicBlockEnc.__init__ (:20-34)
+  void spec_encoder(const std::string& p, int z) {
+    spec_conv(p + ".conv1", 64, 1, 3, false);
+    spec_bn(p + ".bn1", 64);
+    int in_planes = 64;
+    const int planes[4] = {64, 128, 256, 512}, strides[4] = {1, 2, 2, 2};
+    for (int li = 0; li < 4; ++li)
+      for (int bi = 0; bi < 2; ++bi) {
+        const int s = bi == 0 ? strides[li] : 1, out = in_planes * s;
+        const std::string q = p + ".layer" + std::to_string(li + 1) + "." + std::to_string(bi);
+        spec_conv(q + ".conv1", out, in_planes, 3, false);
+        spec_bn(q + ".bn1", out);
+        spec_conv(q + ".conv2", out, out, 3, false);
+        spec_bn(q + ".bn2", out);
+        if (s != 1) {
+          spec_conv(q + ".shortcut.0", out, in_planes, 1, false);
+          spec_bn(q + ".shortcut.1", out);
+        }
+        in_planes = planes[li];
+      }
+    spec_linear(p + ".linear", 2 * z, 512);
+  }
+  // ResNet18Dec.__init__ (hippie/backbones.py:107-126): _make_layer reverses the strides
+  void spec_decoder(const std::string& p, int z, int output_size) {
+    spec_linear(p + ".linear", 512, 2 * z);
+    int in_planes = 512;
+    const int lis[4] = {4, 3, 2, 1}, planes[4] = {256, 128, 64, 64}, strides[4] = {2, 2, 2, 1};
+    for (int i = 0; i < 4; ++i) {
+      for (int bi = 0; bi < 2; ++bi) {
+        const int s = bi == 0 ? 1 : strides[i], out = in_planes / s;
+        const std::string q = p + ".layer" + std::to_string(lis[i]) + "." + std::to_string(bi);
+        spec_conv(q + ".conv2", in_planes, in_planes, 3, false);
+        spec_bn(q + ".bn2", in_planes);
+        if (s == 1) {
+          spec_conv(q + ".conv1", out, in_planes, 3, false);
+          spec_bn(q + ".bn1", out);
+        } else {
+          spec_conv(q + ".conv1.conv", out, in_planes, 3, true);
+          spec_bn(q + ".bn1", out);
+          spec_conv(q + ".shortcut.0.conv", out, in_planes, 3, true);
+          spec_bn(q + ".shortcut.1", out);
+        }
+      }
+      in_planes = planes[i];
+    }
+    spec_conv(p + ".conv1.conv", 1, 64, 3, true);
+    spec_linear(p + ".linear_out", output_size, 64);
+  }
+  void build_spec() {
+    const int z = cfg.z_dim, h = cfg.class_hidden_dim;
+    if (cfg.multimodal) {  // MultiModalCVAE.__init__ (hippie/model.py:352-395)
+      spec_encoder("encoder_mod1", z);
+      spec_encoder("encoder_mod2", z);
+      spec_linear("fusion_encoder.0", 2 * z, 4 * z + 2 * h);
+      spec_bn("fusion_encoder.1", 2 * z);
+      spec_linear("fusion_encoder.3", z, 2 * z);
+      add_param("source_embedding.weight", 2, cfg.num_sources, h, 0, HIPPIE_LAYOUT_NATIVE);
+      cls_emb = add_param("class_embedding.weight", 2, cfg.num_classes, h, 0, HIPPIE_LAYOUT_NATIVE);
+      spec_linear("z_mean", z, z);
+      spec_linear("z_log_var", z, z);
+      for (const char* m : {"decoder_fc_mod1", "decoder_fc_mod2"}) {
+        spec_linear(std::string(m) + ".0", 2 * z, z + 2 * h);
+        spec_linear(std::string(m) + ".2", 2 * z, 2 * z);
+        spec_bn(std::string(m) + ".3", 2 * z);
+      }
+      spec_decoder("decoder_mod1", z, cfg.len_wave);
+      spec_decoder("decoder_mod2", z, cfg.len_isi);
+    } else {  // hippieUnimodalCVAE.__init__ (hippie/model.py:13-44)
+      spec_encoder("encoder", z);
+      spec_linear("encoder_fc.0", 2 * z, 2 * z + 2 * h);
+      spec_bn("encoder_fc.1", 2 * z);
+      spec_linear("encoder_fc.3", z, 2 * z);
+      spec_bn("encoder_fc.4", z);
+      add_param("source_embedding.weight", 2, cfg.num_sources, h, 0, HIPPIE_LAYOUT_NATIVE);
+      cls_emb = add_param("class_embedding.weight", 2, cfg.num_classes, h, 0, HIPPIE_LAYOUT_NATIVE);
+      spec_linear("z_mean", z, z);
+      spec_linear("z_log_var", z, z);
+      spec_linear("decoder_fc.0", 2 * z, z + 2 * h);
+      spec_linear("decoder_fc.2", 2 * z, 2 * z);
+      spec_bn("decoder_fc.3", 2 * z);
+      spec_decoder("decoder", z, cfg.len_wave);
+    }
+    param_floats = (param_floats + 63) & ~(int64_t)63;
+  }
+
+  int act(const std::string& name, int L, int C) {
+    Act a;
+    a.name = name, a.L = L, a.C = C;
+    const int64_t rows = (int64_t)cfg.max_batch * (L + 2) + 2;  // + one finite guard row on either side
+    a.off = take(rows * C) + C;
+    acts.push_back(a);
+    return (int)acts.size() - 1;
+  }
+  int grad_of(int a) {
+    if (cfg.inference_only) return -1;
+    auto it = gact.find(a);
+    if (it != gact.end()) return it->second;
+    int g = act("g:" + acts[a].name, acts[a].L, acts[a].C);
+    gact[a] = g;
+    return g;
+  }
+  int gact_or(int a) { return cfg.inference_only ? -1 : act("d:" + acts[a].name, acts[a].L, acts[a].C); }
+  Conv mkconv(const std::string& n, int cout, int cin, int k, int stride, bool bias, bool need_wt) {
+    Conv c;
+    c.w = pidx.at(n + ".weight");
+    c.b = bias ? pidx.at(n + ".bias") : -1;
+    c.cin = cin, c.cout = cout, c.k = k, c.stride = stride;
+    if (need_wt && !cfg.inference_only) {
+      c.wt_off = take((int64_t)cout * cin * k);
+      WtEntry e;
+      e.w_off = params[c.w].off, e.wt_off = c.wt_off, e.cout = cout, e.cin = cin, e.k = k;
+      wt_table.push_back(e);
+    }
+    return c;
+  }
+  static int conv_len(int L, int k, int s, int p) { return (L + 2 * p - k) / s + 1; }
+
+  void build_encoder(Encoder& E, const std::string& p, int Lin, bool train_tensors) {
+    const int z = cfg.z_dim;
+    E.prefix = p, E.Lin = Lin, E.L0 = conv_len(Lin, 3, 2, 1);
+    E.stem_w = pidx.at(p + ".conv1.weight");
+    E.bn0 = bidx.at(p + ".bn1");
+    E.c0 = act(p + ".conv1", E.L0, 64);
+    E.a0 = act(p + ".stem", E.L0, 64);
+    if (train_tensors) E.dc0 = gact_or(E.c0);
+    int x = E.a0, L = E.L0, in_planes = 64;
+    const int planes[4] = {64, 128, 256, 512}, strides[4] = {1, 2, 2, 2};
+    for (int li = 0; li < 4; ++li)
+      for (int bi = 0; bi < 2; ++bi) {
+        EncBlock& b = E.blk[li * 2 + bi];
+        const int s = bi == 0 ? strides[li] : 1, out = in_planes * s;
+        const std::string q = p + ".layer" + std::to_string(li + 1) + "." + std::to_string(bi);
+        const int Lout = conv_len(L, 3, s, 1);
+        b.down = s != 1;
+        b.c1 = mkconv(q + ".conv1", out, in_planes, 3, s, false, true);
+        b.c2 = mkconv(q + ".conv2", out, out, 3, 1, false, true);
+        b.bn1 = bidx.at(q + ".bn1"), b.bn2 = bidx.at(q + ".bn2");
+        b.x = x;
+        b.c1o = act(q + ".conv1", Lout, out);
+        b.a1 = act(q + ".a1", Lout, out);
+        b.c2o = act(q + ".conv2", Lout, out);
+        if (b.down) {
+          b.cs = mkconv(q + ".shortcut.0", out, in_planes, 1, s, false, true);
+          b.bns = bidx.at(q + ".shortcut.1");
+          b.cso = act(q + ".shortcut", Lout, out);
+        }
+        b.out = act(q, Lout, out);
+        if (train_tensors) {
+          grad_of(b.x), grad_of(b.out);
+          b.g_a1 = act("g:" + q + ".a1", Lout, out);
+          b.dc2 = act("d:" + q + ".conv2", Lout, out);
+          // gradients of stride-2 convs are stored zero-dilated at the INPUT resolution, so their
+          // dgrad / wgrad run as stride-1 problems (DESIGN.md "Backward of strided convs")
+          b.dc1 = act("d:" + q + ".conv1", b.down ? L : Lout, out);
+          if (b.down) b.dcs = act("d:" + q + ".shortcut", L, out);
+        }
+        x = b.out, L = Lout, in_planes = planes[li];
+      }
+    E.lin_w = pidx.at(p + ".linear.weight"), E.lin_b = pidx.at(p + ".linear.bias");
+    E.pooled = take((int64_t)cfg.max_batch * 512);
+    E.h = take((int64_t)cfg.max_batch * 2 * z);
+    E.dh = take((int64_t)cfg.max_batch * 2 * z);
+  }
+
+  void build_decoder(Decoder& D, const std::string& p, int Lo, bool train_tensors) {
+    const int z = cfg.z_dim;
+    D.prefix = p, D.Lo = Lo;
+    D.lin_w = pidx.at(p + ".linear.weight"), D.lin_b = pidx.at(p + ".linear.bias");
+    D.t0 = act(p + ".linear", 4, 512);
+    int x = D.t0, L = 4, in_planes = 512;
+    const int lis[4] = {4, 3, 2, 1}, planes[4] = {256, 128, 64, 64}, strides[4] = {2, 2, 2, 1};
+    for (int i = 0; i < 4; ++i) {
+      for (int bi = 0; bi < 2; ++bi) {
+        DecBlock& b = D.blk[i * 2 + bi];
+        const int s = bi == 0 ? 1 : strides[i], out = in_planes / s;
+        const std::string q = p + ".layer" + std::to_string(lis[i]) + "." + std::to_string(bi);
+        b.up = s != 1;
+        const int Lout = L * s;
+        b.x = x;
+        b.c2 = mkconv(q + ".conv2", in_planes, in_planes, 3, 1, false, true);
+        b.bn2 = bidx.at(q + ".bn2"), b.bn1 = bidx.at(q + ".bn1");
+        b.c2o = act(q + ".conv2", L, in_planes);
+        b.a2 = act(q + ".a2", L, in_planes);
+        if (b.up) {
+          b.c1 = mkconv(q + ".conv1.conv", out, in_planes, 3, 1, true, true);
+          b.cs = mkconv(q + ".shortcut.0.conv", out, in_planes, 3, 1, true, true);
+          b.bns = bidx.at(q + ".shortcut.1");
+          b.a2_up = act(q + ".a2_up", Lout, in_planes);
+          b.x_up = act(q + ".x_up", Lout, in_planes);
+          b.cso = act(q + ".shortcut", Lout, out);
+        } else {
+          b.c1 = mkconv(q + ".conv1", out, in_planes, 3, 1, false, true);
+        }
+        b.c1o = act(q + ".conv1", Lout, out);
+        b.out = act(q, Lout, out);
+        if (train_tensors) {
+          grad_of(b.x), grad_of(b.out);
+          b.dc2 = act("d:" + q + ".conv2", L, in_planes);
+          b.dc1 = act("d:" + q + ".conv1", Lout, out);
+          if (b.up) {
+            b.dcs = act("d:" + q + ".shortcut", Lout, out);
+            b.g_a2_up = act("g:" + q + ".a2_up", Lout, in_planes);
+            b.g_x_up = act("g:" + q + ".x_up", Lout, in_planes);
+          } else {
+            b.g_a2 = act("g:" + q + ".a2", L, in_planes);
+          }
+        }
+        x = b.out, L = Lout;
+      }
+      in_planes = planes[i];
+    }
+    for (int k = 0; k + 1 < 8; ++k)
+      if (D.blk[k + 1].up) D.blk[k].out_up = D.blk[k + 1].x_up;
+    D.wc = pidx.at(p + ".conv1.conv.weight"), D.bc = pidx.at(p + ".conv1.conv.bias");
+    D.lo_w = pidx.at(p + ".linear_out.weight"), D.lo_b = pidx.at(p + ".linear_out.bias");
+    const int64_t mb = cfg.max_batch;
+    D.d = take(mb * 2 * z), D.dd = take(mb * 2 * z), D.gx0 = take(mb * 512);
+    D.y = take(mb * 64), D.ddec = take(mb * Lo), D.dy = take(mb * 64), D.dec = take(mb * Lo);
+    D.part = take(((mb + 3) / 4 + 1) * 196);
+  }
+
+  int64_t off_of(const std::string& n) { return params[pidx.at(n)].off; }
+  void build() {
+    build_spec();
+    const bool tr = !cfg.inference_only;
+    const int z = cfg.z_dim;
+    n_enc = cfg.multimodal ? 2 : 1, n_dec = n_enc;
+    if (cfg.multimodal) {
+      build_encoder(enc[0], "encoder_mod1", cfg.len_wave, tr);
+      build_encoder(enc[1], "encoder_mod2", cfg.len_isi, tr);
+      build_decoder(dec[0], "decoder_mod1", cfg.len_wave, tr);
+      build_decoder(dec[1], "decoder_mod2", cfg.len_isi, tr);
+    } else {
+      build_encoder(enc[0], "encoder", cfg.len_wave, tr);
+      build_decoder(dec[0], "decoder", cfg.len_wave, tr);
+    }
+    // head parameter map
+    HeadParams& H = headp;
+    memset(&H, 0xff, sizeof(H));  // all -1
+    const std::string f = cfg.multimodal ? "fusion_encoder" : "encoder_fc";
+    H.f0_w = off_of(f + ".0.weight"), H.f0_b = off_of(f + ".0.bias");
+    H.fbn_g = off_of(f + ".1.weight"), H.fbn_b = off_of(f + ".1.bias");
+    H.f3_w = off_of(f + ".3.weight"), H.f3_b = off_of(f + ".3.bias");
+    H.fbn_run = bns[bidx.at(f + ".1")].run_off, H.fbn_cnt = bidx.at(f + ".1");
+    if (!cfg.multimodal) {
+      H.ebn_g = off_of(f + ".4.weight"), H.ebn_b = off_of(f + ".4.bias");
+      H.ebn_run = bns[bidx.at(f + ".4")].run_off, H.ebn_cnt = bidx.at(f + ".4");
+    }
+    H.src_emb = off_of("source_embedding.weight"), H.cls_emb = off_of("class_embedding.weight");
+    H.zm_w = off_of("z_mean.weight"), H.zm_b = off_of("z_mean.bias");
+    H.zv_w = off_of("z_log_var.weight"), H.zv_b = off_of("z_log_var.bias");
+    for (int m = 0; m < n_dec; ++m) {
+      const std::string d = cfg.multimodal ? "decoder_fc_mod" + std::to_string(m + 1) : "decoder_fc";
+      H.d0_w[m] = off_of(d + ".0.weight"), H.d0_b[m] = off_of(d + ".0.bias");
+      H.d2_w[m] = off_of(d + ".2.weight"), H.d2_b[m] = off_of(d + ".2.bias");
+      H.dbn_g[m] = off_of(d + ".3.weight"), H.dbn_b[m] = off_of(d + ".3.bias");
+      H.dbn_run[m] = bns[bidx.at(d + ".3")].run_off, H.dbn_cnt[m] = bidx.at(d + ".3");
+    }
+    head_scratch = take(head_scratch_floats(z, cfg.class_hidden_dim, cfg.max_batch));
+    scal_off = take(64);
+    // partial-sum buffers.  BatchNorm statistics: [tiles of >= 64 logical rows][C][2]; the stem's weight-gradient
+    // partials ([tiles of 128 rows][192]) also fit.  BatchNorm backward: at most kBnBwdMaxChunks chunks x C x 3.
+    part_floats = 4096;
+    for (auto& a : acts)
+      part_floats = std::max<int64_t>(part_floats, (((int64_t)cfg.max_batch * a.L + 63) / 64 + 1) * a.C * 2);
+    bpart_floats = (int64_t)(kBnBwdMaxChunks + 1) * 512 * 3;
+    for (int i = 0; i < 2; ++i) part_off[i] = take(part_floats), bpart_off[i] = take(bpart_floats);
+    adam_part = take(1024);
+    for (auto& b : bns) {
+      b.coef_off = take(8 * (int64_t)b.C);
+      BnEvalEntry e;
+      e.gamma_off = params[b.gamma].off, e.beta_off = params[b.beta].off, e.run_off = b.run_off, e.coef_off = b.coef_off;
+      e.C = b.C;
+      bn_table.push_back(e);
+    }
+    wt_table_off = take((int64_t)(wt_table.size() * sizeof(WtEntry) + 3) / 4 + 4);
+    bn_table_off = take((int64_t)(bn_table.size() * sizeof(BnEvalEntry) + 3) / 4 + 4);
+  }
+
+  // ---- helpers ---------------------------------------------------------------------------------
+  float* A(int i) { return ws + acts[i].off; }
+  float* coef(int bn) { return ws + bns[bn].coef_off; }
+  float* Pp(int p) { return P + params[p].off; }
+  float* Gp(int p) { return G + params[p].off; }
+
+  void conv_fwd(const Conv& cv, int in, int out, int bn, int B, bool train, Branch& br) {
+    ConvGemm g{};
+    g.A = A(in), g.W = Pp(cv.w), g.bias = cv.b >= 0 ? Pp(cv.b) : nullptr, g.C = A(out);
+    g.part = (train && bn >= 0) ? br.part : nullptr;
+    g.M = B * acts[out].L, g.N = cv.cout, g.K = cv.k * cv.cin, g.Lout = acts[out].L;
+    g.in_rows = acts[in].L + 2, g.in_stride = cv.stride, g.in_off = cv.k == 3 ? 0 : 1, g.in_C = cv.cin;
+    g.out_rows = acts[out].L + 2, g.out_off = 1, g.out_lstride = 1, g.accumulate = 0;
+    const int tile = launch_conv_gemm_simt(g, br.st);
+    ++launches;
+    if (train && bn >= 0) bn_finalize(bn, br.part, (g.M + tile - 1) / tile, tile, g.M, br);
+  }
+  void bn_finalize(int bn, const float* part, int ntiles, int tile, int M, Branch& br) {
+    BnFinalize f{};
+    f.part = part, f.ntiles = ntiles, f.tile_rows = tile, f.M = M, f.C = bns[bn].C;
+    f.gamma = Pp(bns[bn].gamma), f.beta = Pp(bns[bn].beta);
+    f.run_mean = bn_mean + bns[bn].run_off, f.run_var = bn_var + bns[bn].run_off, f.run_count = bn_count + bn;
+    f.coef = coef(bn);
+    launch_bn_finalize_train(f, br.st);
+    ++launches;
+  }
+  void apply(int c, int bn, int r, int rbn, int out, int out_up, int B, Branch& br) {
+    BnApply a{};
+    a.c = A(c), a.coef = coef(bn), a.r = r >= 0 ? A(r) : nullptr, a.rcoef = rbn >= 0 ? coef(rbn) : nullptr;
+    a.out = A(out), a.out_up = out_up >= 0 ? A(out_up) : nullptr;
+    a.B = B, a.L = acts[c].L, a.C = acts[c].C, a.slope = kSlopeBackbone;
+    launch_bn_apply(a, br.st);
+    ++launches;
+  }
+  // dgrad as a stride-1 convolution of the (dilated) output gradient with the transposed weights
+  void dgrad(const Conv& cv, int dy, int gx, bool accumulate, int B, Branch& br) {
+    ConvGemm g{};
+    g.A = A(dy), g.W = ws + cv.wt_off, g.bias = nullptr, g.C = A(gx), g.part = nullptr;
+    g.M = B * acts[gx].L, g.N = cv.cin, g.K = cv.k * cv.cout, g.Lout = acts[gx].L;
+    g.in_rows = acts[dy].L + 2, g.in_stride = 1, g.in_off = cv.k == 3 ? 0 : 1, g.in_C = cv.cout;
+    g.out_rows = acts[gx].L + 2, g.out_off = 1, g.out_lstride = 1, g.accumulate = accumulate ? 1 : 0;
+    launch_conv_gemm_simt(g, br.st);
+    ++launches;
+  }
+  void wgrad(const Conv& cv, int dy, int x, int B, Branch& br) {
+    WgradGemm g{};
+    g.dY = A(dy), g.X = A(x), g.dW = Gp(cv.w);
+    g.M = cv.cout, g.N = cv.k * cv.cin, g.R = B * (acts[dy].L + 2), g.Cin = cv.cin, g.roff = cv.k == 3 ? -1 : 0;
+    launch_wgrad_simt(g, sm_count, br.st);
+    ++launches;
+  }
+  void bn_bwd(int g, bool g_up, int out, int c, int bn, int cs, int bnsi, int dc, int dil, int dcs, int dil_s, int gres,
+              int B, Branch& br) {
+    BnBwd a{};
+    a.g = A(g), a.g_up = g_up ? 1 : 0, a.out = A(out), a.c = A(c), a.coef = coef(bn);
+    a.cs = cs >= 0 ? A(cs) : nullptr, a.coef_s = cs >= 0 ? coef(bnsi) : nullptr;
+    a.part = br.bpart, a.B = B, a.L = acts[out].L, a.C = acts[out].C, a.slope = kSlopeBackbone;
+    a.gamma = Pp(bns[bn].gamma), a.dgamma = Gp(bns[bn].gamma), a.dbeta = Gp(bns[bn].beta);
+    if (cs >= 0) a.gamma_s = Pp(bns[bnsi].gamma), a.dgamma_s = Gp(bns[bnsi].gamma), a.dbeta_s = Gp(bns[bnsi].beta);
+    a.dc = A(dc), a.dil = dil, a.Ld = acts[dc].L;
+    if (cs >= 0) a.dcs = A(dcs), a.dil_s = dil_s, a.Ld_s = acts[dcs].L;
+    a.gres = gres >= 0 ? A(gres) : nullptr;
+    launch_bn_bwd(a, sm_count, br.st);
+    launches += kBnBwdLaunches;
+  }
+
+  void encoder_fwd(Encoder& E, const float* x, int B, bool train, Branch& br) {
+    launch_stem_fwd(x, Pp(E.stem_w), A(E.c0), train ? br.part : nullptr, B, E.Lin, E.L0, br.st);
+    ++launches;
+    if (train) bn_finalize(E.bn0, br.part, (B * E.L0 + 127) / 128, 128, B * E.L0, br);
+    apply(E.c0, E.bn0, -1, -1, E.a0, -1, B, br);
+    for (int i = 0; i < 8; ++i) {
+      EncBlock& b = E.blk[i];
+      conv_fwd(b.c1, b.x, b.c1o, b.bn1, B, train, br);
+      apply(b.c1o, b.bn1, -1, -1, b.a1, -1, B, br);
+      conv_fwd(b.c2, b.a1, b.c2o, b.bn2, B, train, br);
+      if (b.down) {
+        conv_fwd(b.cs, b.x, b.cso, b.bns, B, train, br);
+        apply(b.c2o, b.bn2, b.cso, b.bns, b.out, -1, B, br);
+      } else {
+        apply(b.c2o, b.bn2, b.x, -1, b.out, -1, B, br);
+      }
+    }
+    const int last = E.blk[7].out;
+    launch_pool_linear_fwd(A(last), B, acts[last].L, 512, Pp(E.lin_w), Pp(E.lin_b), 2 * cfg.z_dim, ws + E.pooled,
+                           ws + E.h, br.st);
+    ++launches;
+  }
+  void encoder_bwd(Encoder& E, const float* x, int B, Branch& br) {
+    const int last = E.blk[7].out;
+    launch_pool_linear_bwd(ws + E.dh, ws + E.pooled, Pp(E.lin_w), B, acts[last].L, 512, 2 * cfg.z_dim, A(gact.at(last)),
+                           Gp(E.lin_w), Gp(E.lin_b), br.st);
+    launches += kPoolLinearBwdLaunches;
+    for (int i = 7; i >= 0; --i) {
+      EncBlock& b = E.blk[i];
+      const int gx = gact.at(b.x), gout = gact.at(b.out);
+      bn_bwd(gout, false, b.out, b.c2o, b.bn2, b.down ? b.cso : -1, b.bns, b.dc2, 1, b.dcs, 2, b.down ? -1 : gx, B, br);
+      dgrad(b.c2, b.dc2, b.g_a1, false, B, br);
+      wgrad(b.c2, b.dc2, b.a1, B, br);
+      bn_bwd(b.g_a1, false, b.a1, b.c1o, b.bn1, -1, -1, b.dc1, b.down ? 2 : 1, -1, 1, -1, B, br);
+      if (b.down) {
+        dgrad(b.cs, b.dcs, gx, false, B, br);
+        wgrad(b.cs, b.dcs, b.x, B, br);
+      }
+      dgrad(b.c1, b.dc1, gx, true, B, br);
+      wgrad(b.c1, b.dc1, b.x, B, br);
+    }
+    bn_bwd(gact.at(E.a0), false, E.a0, E.c0, E.bn0, -1, -1, E.dc0, 1, -1, 1, -1, B, br);
+    const int np = launch_stem_wgrad(x, A(E.dc0), br.part, B, E.Lin, E.L0, br.st);
+    launch_reduce_partials(br.part, np, 192, Gp(E.stem_w), 0, br.st);
+    launches += 2;
+  }
+
+  void decoder_fwd(Decoder& D, int B, bool train, Branch& br) {
+    launch_dec_linear_fwd(ws + D.d, B, 2 * cfg.z_dim, Pp(D.lin_w), Pp(D.lin_b), 512, A(D.t0), nullptr, br.st);
+    ++launches;
+    for (int i = 0; i < 8; ++i) {
+      DecBlock& b = D.blk[i];
+      conv_fwd(b.c2, b.x, b.c2o, b.bn2, B, train, br);
+      apply(b.c2o, b.bn2, -1, -1, b.a2, b.a2_up, B, br);
+      if (b.up) {
+        conv_fwd(b.c1, b.a2_up, b.c1o, b.bn1, B, train, br);
+        conv_fwd(b.cs, b.x_up, b.cso, b.bns, B, train, br);
+        apply(b.c1o, b.bn1, b.cso, b.bns, b.out, b.out_up, B, br);
+      } else {
+        conv_fwd(b.c1, b.a2, b.c1o, b.bn1, B, train, br);
+        apply(b.c1o, b.bn1, b.x, -1, b.out, b.out_up, B, br);
+      }
+    }
+  }
+  DecTail tail_args(Decoder& D, const float* target, float* dec_out, int B, bool train, float loss_w) {
+    DecTail t{};
+    t.x = A(D.blk[7].out), t.wc = Pp(D.wc), t.bc = Pp(D.bc), t.Wo = Pp(D.lo_w), t.bo = Pp(D.lo_b);
+    t.target = target, t.dec = dec_out ? dec_out : ws + D.dec, t.B = B, t.Lo = D.Lo;
+    t.part = ws + D.part, t.loss_w = loss_w, t.train = train ? 1 : 0;
+    if (train) {
+      t.y = ws + D.y, t.ddec = ws + D.ddec, t.dy = ws + D.dy, t.g_x = A(gact.at(D.blk[7].out));
+    }
+    return t;
+  }
+  void decoder_tail(Decoder& D, int m, const float* target, float* dec_out, int B, bool train, float loss_w, Branch& br) {
+    DecTail t = tail_args(D, target, dec_out, B, train, loss_w);
+    const int ncta = launch_dec_tail(t, br.st);
+    float* sse = ws + scal_off + m;
+    if (train)
+      launch_dec_tail_reduce(t, ncta, Gp(D.wc), Gp(D.bc), Gp(D.lo_w), Gp(D.lo_b), sse, br.st);
+    else
+      launch_dec_tail_reduce(t, ncta, nullptr, nullptr, nullptr, nullptr, sse, br.st);
+    launches += 2;
+  }
+  void decoder_bwd(Decoder& D, int B, Branch& br) {
+    for (int i = 7; i >= 0; --i) {
+      DecBlock& b = D.blk[i];
+      const int gx = gact.at(b.x), gout = gact.at(b.out);
+      if (b.up) {
+        bn_bwd(gout, false, b.out, b.c1o, b.bn1, b.cso, b.bns, b.dc1, 1, b.dcs, 1, -1, B, br);
+        dgrad(b.c1, b.dc1, b.g_a2_up, false, B, br);
+        wgrad(b.c1, b.dc1, b.a2_up, B, br);
+        dgrad(b.cs, b.dcs, b.g_x_up, false, B, br);
+        wgrad(b.cs, b.dcs, b.x_up, B, br);
+        bn_bwd(b.g_a2_up, true, b.a2, b.c2o, b.bn2, -1, -1, b.dc2, 1, -1, 1, -1, B, br);
+        dgrad(b.c2, b.dc2, gx, false, B, br);
+        wgrad(b.c2, b.dc2, b.x, B, br);
+        launch_pairsum_acc(A(b.g_x_up), A(gx), B, acts[b.x].L, acts[b.x].C, br.st);
+        ++launches;
+      } else {
+        bn_bwd(gout, false, b.out, b.c1o, b.bn1, -1, -1, b.dc1, 1, -1, 1, gx, B, br);
+        dgrad(b.c1, b.dc1, b.g_a2, false, B, br);
+        wgrad(b.c1, b.dc1, b.a2, B, br);
+        bn_bwd(b.g_a2, false, b.a2, b.c2o, b.bn2, -1, -1, b.dc2, 1, -1, 1, -1, B, br);
+        dgrad(b.c2, b.dc2, gx, true, B, br);
+        wgrad(b.c2, b.dc2, b.x, B, br);
+      }
+    }
+    launch_dec_linear_bwd(A(gact.at(D.t0)), ws + D.d, Pp(D.lin_w), B, 2 * cfg.z_dim, 512, ws + D.gx0, ws + D.dd,
+                          Gp(D.lin_w), Gp(D.lin_b), br.st);
+    launches += kDecLinearBwdLaunches;
+  }
+
+  HeadArgs head_args(int B, const int64_t* src, const int64_t* cls, const float* eps, bool train, bool decode,
+                     float* out_enc, float* out_mu, float* out_logvar, float beta, int zscore) {
+    HeadArgs a{};
+    a.hp = headp, a.params = P, a.grads = G, a.run_mean = bn_mean, a.run_var = bn_var, a.run_count = bn_count;
+    a.z = cfg.z_dim, a.h = cfg.class_hidden_dim, a.n_enc = n_enc, a.n_dec = n_dec;
+    a.num_sources = cfg.num_sources, a.num_classes = cfg.num_classes, a.B = B;
+    for (int e = 0; e < n_enc; ++e) a.hin[e] = ws + enc[e].h, a.dh[e] = ws + enc[e].dh;
+    for (int m = 0; m < n_dec; ++m) a.dout[m] = ws + dec[m].d, a.dd[m] = ws + dec[m].dd;
+    a.src = src, a.cls = cls, a.eps = eps, a.scratch = ws + head_scratch;
+    a.out_enc = out_enc, a.out_mu = out_mu, a.out_logvar = out_logvar;
+    a.kl_sum = ws + scal_off + 2, a.train = train ? 1 : 0, a.decode = decode ? 1 : 0, a.zscore_ddof = zscore;
+    a.beta = beta;
+    return a;
+  }
+
+  void fork(cudaStream_t main) {
+    cudaEventRecord(ev_fork, main);
+    cudaStreamWaitEvent(side, ev_fork, 0);
+  }
+  void join(cudaStream_t main) {
+    cudaEventRecord(ev_join, side);
+    cudaStreamWaitEvent(main, ev_join, 0);
+  }
+  int fail(int code, const std::string& msg) {
+    err = msg;
+    return code;
+  }
+  int check(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail((int)e, std::string(what) + ": " + cudaGetErrorString(e));
+    return 0;
+  }
+  int validate(int B, const void* x1, const void* x2, const void* src) {
+    if (!bound) return fail(-2, "hippie_bind has not been called");
+    if (B < 1 || B > cfg.max_batch) return fail(-3, "B outside [1, max_batch]");
+    if (!x1 || !src || (cfg.multimodal && !x2)) return fail(-4, "null input pointer");
+    return 0;
+  }
+
+  // full forward (+ loss, + backward when train)
+  int run(bool train, bool backward, const float* x1, const float* x2, const int64_t* src, const int64_t* cls,
+          const float* eps, int B, float beta, float w1, float w2, float* scalars_out, float* out_enc, float* out_mu,
+          float* out_logvar, float* out_dec1, float* out_dec2, cudaStream_t main) {
+    launches = 0;
+    Branch b0{main, ws + part_off[0], ws + bpart_off[0]}, b1{side, ws + part_off[1], ws + bpart_off[1]};
+    const float* xin[2] = {x1, x2};
+    float* dec_out[2] = {out_dec1, out_dec2};
+    const float lw[2] = {cfg.multimodal ? w1 : 1.f, w2};
+    cudaMemsetAsync(ws + scal_off, 0, 64 * sizeof(float), main);
+    if (backward) {
+      cudaMemsetAsync(G, 0, param_floats * sizeof(float), main);
+      launch_refresh_wt(reinterpret_cast<const WtEntry*>(ws + wt_table_off), (int)wt_table.size(), P, ws, main);
+      ++launches;
+    }
+    if (!train) {
+      launch_bn_eval_coefs(reinterpret_cast<const BnEvalEntry*>(ws + bn_table_off), (int)bn_table.size(), P, bn_mean,
+                           bn_var, ws, main);
+      ++launches;
+    }
+    const bool two = n_enc == 2;
+    if (two) fork(main);
+    encoder_fwd(enc[0], xin[0], B, train, b0);
+    if (two) {
+      encoder_fwd(enc[1], xin[1], B, train, b1);
+      join(main);
+    }
+    HeadArgs ha = head_args(B, src, cls, eps, train, true, out_enc, out_mu, out_logvar, beta, -1);
+    launch_head_fwd(ha, main);
+    ++launches;
+    if (two) fork(main);
+    for (int m = 0; m < n_dec; ++m) {
+      Branch& br = m == 0 ? b0 : b1;
+      decoder_fwd(dec[m], B, train, br);
+      decoder_tail(dec[m], m, xin[m], dec_out[m], B, backward, lw[m], br);
+      if (backward) decoder_bwd(dec[m], B, br);
+    }
+    if (two) join(main);
+    if (scalars_out) {
+      launch_loss_finalize(ws + scal_off + 0, ws + scal_off + 1, ws + scal_off + 2, B, dec[0].Lo,
+                           cfg.multimodal ? dec[1].Lo : 1, beta, w1, w2, cfg.multimodal, scalars_out, main);
+      ++launches;
+    }
+    if (backward) {
+      launch_head_bwd(ha, main);
+      ++launches;
+      if (two) fork(main);
+      encoder_bwd(enc[0], xin[0], B, b0);
+      if (two) {
+        encoder_bwd(enc[1], xin[1], B, b1);
+        join(main);
+      }
+    }
+    return check(train ? "train_fwd_bwd" : "eval_forward");
+  }
+};
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+int hippie_abi_version(void) { return 1; }
+
+int hippie_create(const hippie_cfg* cfg, hippie_handle* out) {
+  if (!cfg || !out) return -1;
+  *out = nullptr;
+  if (cfg->z_dim < 1 || cfg->z_dim > 256 || cfg->class_hidden_dim < 1 || cfg->num_sources < 1 || cfg->num_classes < 1 ||
+      cfg->len_wave < 4 || (cfg->multimodal && cfg->len_isi < 4) || cfg->max_batch < 1)
+    return -1;
+  hippie_engine* e = new hippie_engine();
+  e->cfg = *cfg;
+  e->build();
+  *out = e;
+  return 0;
+}
+
+void hippie_destroy(hippie_handle h) {
+  if (!h) return;
+  if (h->side) cudaStreamDestroy(h->side);
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  if (h->ev_join) cudaEventDestroy(h->ev_join);
+  delete h;
+}
+
+const char* hippie_last_error(hippie_handle h) { return h ? h->err.c_str() : "null handle"; }
+
+int hippie_num_params(hippie_handle h) { return h ? (int)h->params.size() : -1; }
+int64_t hippie_param_floats(hippie_handle h) { return h ? h->param_floats : -1; }
+int hippie_param_info(hippie_handle h, int idx, char* name, int name_cap, int64_t* offset, int64_t* numel, int32_t* ndim,
+                      int64_t* shape3, int32_t* layout) {
+  if (!h || idx < 0 || idx >= (int)h->params.size()) return -1;
+  const Param& p = h->params[idx];
+  if (name && name_cap > 0) snprintf(name, name_cap, "%s", p.name.c_str());
+  if (offset) *offset = p.off;
+  if (numel) *numel = p.numel;
+  if (ndim) *ndim = p.ndim;
+  if (shape3) shape3[0] = p.shape[0], shape3[1] = p.shape[1], shape3[2] = p.shape[2];
+  if (layout) *layout = p.layout;
+  return 0;
+}
+int hippie_num_bn(hippie_handle h) { return h ? (int)h->bns.size() : -1; }
+int64_t hippie_bn_floats(hippie_handle h) { return h ? h->bn_floats : -1; }
+int hippie_bn_info(hippie_handle h, int idx, char* name, int name_cap, int64_t* offset, int64_t* channels) {
+  if (!h || idx < 0 || idx >= (int)h->bns.size()) return -1;
+  const BNInfo& b = h->bns[idx];
+  if (name && name_cap > 0) snprintf(name, name_cap, "%s", b.name.c_str());
+  if (offset) *offset = b.run_off;
+  if (channels) *channels = b.C;
+  return 0;
+}
+size_t hippie_workspace_bytes(hippie_handle h) { return h ? (size_t)h->ws_floats * sizeof(float) : 0; }
+int hippie_num_tensors(hippie_handle h) { return h ? (int)h->acts.size() : -1; }
+int hippie_tensor_info(hippie_handle h, int idx, char* name, int name_cap, int64_t* offset, int32_t* L, int32_t* C,
+                       int32_t* pad) {
+  if (!h || idx < 0 || idx >= (int)h->acts.size()) return -1;
+  const Act& a = h->acts[idx];
+  if (name && name_cap > 0) snprintf(name, name_cap, "%s", a.name.c_str());
+  if (offset) *offset = a.off;
+  if (L) *L = a.L;
+  if (C) *C = a.C;
+  if (pad) *pad = 1;
+  return 0;
+}
+
+int hippie_bind(hippie_handle h, float* params, float* grads, float* exp_avg, float* exp_avg_sq, float* bn_mean,
+                float* bn_var, int64_t* bn_count, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!h) return -1;
+  if (!params || !bn_mean || !bn_var || !bn_count || !workspace) return h->fail(-4, "null buffer");
+  if (!h->cfg.inference_only && (!grads || !exp_avg || !exp_avg_sq)) return h->fail(-4, "training engine needs grads and AdamW state");
+  if (workspace_bytes < (size_t)h->ws_floats * sizeof(float)) return h->fail(-5, "workspace too small");
+  int dev = 0;
+  cudaError_t ce = cudaGetDevice(&dev);
+  if (ce != cudaSuccess) return h->fail((int)ce, std::string("cudaGetDevice: ") + cudaGetErrorString(ce));
+  cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, dev);
+  int major = 0;
+  cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  if (major != 10) return h->fail(-6, "libhippie_b200 is built for sm_100a (B200) only");
+  cudaStream_t st = (cudaStream_t)stream;
+  h->P = params, h->G = grads, h->M1 = exp_avg, h->M2 = exp_avg_sq;
+  h->bn_mean = bn_mean, h->bn_var = bn_var, h->bn_count = bn_count, h->ws = (float*)workspace;
+  if (!h->side) {
+    cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking);
+    cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming);
+  }
+  cudaMemsetAsync(workspace, 0, (size_t)h->ws_floats * sizeof(float), st);
+  if (!h->wt_table.empty())
+    cudaMemcpyAsync(h->ws + h->wt_table_off, h->wt_table.data(), h->wt_table.size() * sizeof(WtEntry),
+                    cudaMemcpyHostToDevice, st);
+  cudaMemcpyAsync(h->ws + h->bn_table_off, h->bn_table.data(), h->bn_table.size() * sizeof(BnEvalEntry),
+                  cudaMemcpyHostToDevice, st);
+  cudaStreamSynchronize(st);
+  h->bound = true;
+  return h->check("hippie_bind");
+}
+
+int hippie_train_fwd_bwd(hippie_handle h, const float* x1, const float* x2, const int64_t* src, const int64_t* cls,
+                         const float* eps, int32_t B, float beta, float w1, float w2, float* scalars_out, float* out_enc,
+                         float* out_mu, float* out_logvar, float* out_dec1, float* out_dec2, void* stream) {
+  if (!h) return -1;
+  if (int rc = h->validate(B, x1, x2, src)) return rc;
+  if (h->cfg.inference_only) return h->fail(-7, "inference-only engine");
+  if (!eps) return h->fail(-4, "eps is required for training (reparameterisation noise)");
+  if (B < 2) return h->fail(-3, "training-mode BatchNorm needs B >= 2");
+  return h->run(true, true, x1, x2, src, cls, eps, B, beta, w1, w2, scalars_out, out_enc, out_mu, out_logvar, out_dec1,
+                out_dec2, (cudaStream_t)stream);
+}
+
+int hippie_eval_forward(hippie_handle h, const float* x1, const float* x2, const int64_t* src, const int64_t* cls,
+                        const float* eps, int32_t B, float beta, float w1, float w2, float* scalars_out, float* out_enc,
+                        float* out_mu, float* out_logvar, float* out_dec1, float* out_dec2, void* stream) {
+  if (!h) return -1;
+  if (int rc = h->validate(B, x1, x2, src)) return rc;
+  return h->run(false, false, x1, x2, src, cls, eps, B, beta, w1, w2, scalars_out, out_enc, out_mu, out_logvar,
+                out_dec1, out_dec2, (cudaStream_t)stream);
+}
+
+int hippie_embed(hippie_handle h, const float* x1, const float* x2, const int64_t* src, const int64_t* cls, int32_t B,
+                 int32_t zscore_ddof, float* out_enc, float* out_mu, float* out_logvar, void* stream) {
+  if (!h) return -1;
+  if (int rc = h->validate(B, x1, x2, src)) return rc;
+  cudaStream_t main = (cudaStream_t)stream;
+  h->launches = 0;
+  Branch b0{main, h->ws + h->part_off[0], h->ws + h->bpart_off[0]}, b1{h->side, h->ws + h->part_off[1], h->ws + h->bpart_off[1]};
+  launch_bn_eval_coefs(reinterpret_cast<const BnEvalEntry*>(h->ws + h->bn_table_off), (int)h->bn_table.size(), h->P,
+                       h->bn_mean, h->bn_var, h->ws, main);
+  ++h->launches;
+  const bool two = h->n_enc == 2;
+  if (two) h->fork(main);
+  h->encoder_fwd(h->enc[0], x1, B, false, b0);
+  if (two) {
+    h->encoder_fwd(h->enc[1], x2, B, false, b1);
+    h->join(main);
+  }
+  HeadArgs ha = h->head_args(B, src, cls, nullptr, false, false, out_enc, out_mu, out_logvar, 0.f, zscore_ddof);
+  ha.kl_sum = nullptr;
+  launch_head_fwd(ha, main);
+  ++h->launches;
+  return h->check("hippie_embed");
+}
+
+int hippie_clip_adamw(hippie_handle h, float lr, float beta1, float beta2, float eps, float weight_decay, float max_norm,
+                      float grad_scale, int32_t step, int32_t step_cls, int32_t has_cls_grad, float* scalars_out,
+                      void* stream) {
+  if (!h) return -1;
+  if (!h->bound) return h->fail(-2, "hippie_bind has not been called");
+  if (h->cfg.inference_only) return h->fail(-7, "inference-only engine");
+  if (!scalars_out) return h->fail(-4, "scalars_out is required");
+  if (step < 1) return h->fail(-3, "step is 1-based");
+  AdamArgs a{};
+  a.p = h->P, a.g = h->G, a.m = h->M1, a.v = h->M2, a.n = h->param_floats;
+  a.skip_lo = h->params[h->cls_emb].off, a.skip_hi = a.skip_lo + h->params[h->cls_emb].numel;
+  a.lr = lr, a.beta1 = beta1, a.beta2 = beta2, a.eps = eps, a.wd = weight_decay, a.max_norm = max_norm;
+  a.grad_scale = grad_scale, a.step = step, a.step_cls = step_cls, a.has_cls_grad = has_cls_grad;
+  a.partials = h->ws + h->adam_part, a.scalars = scalars_out;
+  launch_clip_adamw(a, (cudaStream_t)stream);
+  h->launches = kClipAdamLaunches;
+  return h->check("hippie_clip_adamw");
+}
+
+int hippie_last_launch_count(hippie_handle h) { return h ? h->launches : -1; }
+
+}  // extern "C"

@@ -1,0 +1,364 @@
+// Latent head of the cVAE: condition embeddings, fusion MLP (or the unimodal encoder_fc), z_mean /
+// z_log_var, reparameterisation, KL term and the decoder_fc MLPs -- forward and backward.
+//
+// Reference: MultiModalCVAE.encode / reparameterize / decode (hippie/model.py:397-422),
+//            hippieUnimodalCVAE (hippie/model.py:46-72), KL term (hippie/model.py:472-474).
+//
+// ~3.6 K parameters and B x 50 activations: the whole batch is handled by ONE CTA in training mode
+// (BatchNorm1d over the batch couples every sample), weights are read through L1, intermediates
+// live in a small global scratch that the backward pass re-reads.  In eval mode samples are
+// independent and the grid is split over sample ranges.
+#include "kernels.cuh"
+
+namespace hp {
+
+struct HeadScratch {
+  int64_t cat, f0, f1, e0, enc, mu, lv, zc, g0[2], g1[2], stats;
+  int64_t dg1, dg0, dzc, dmu, dlv, denc, de0, df1, df0, dcat, total;
+};
+
+__host__ __device__ inline HeadScratch head_layout(int z, int h, int B) {
+  HeadScratch L;
+  const int64_t Z2 = 2 * z, D0 = 2 * Z2 + 2 * h, DZ = z + 2 * h, Bn = B;
+  int64_t o = 0;
+  auto take = [&](int64_t n) {
+    int64_t r = o;
+    o += (n + 3) & ~(int64_t)3;
+    return r;
+  };
+  L.cat = take(Bn * D0), L.f0 = take(Bn * Z2), L.f1 = take(Bn * Z2), L.e0 = take(Bn * z), L.enc = take(Bn * z);
+  L.mu = take(Bn * z), L.lv = take(Bn * z), L.zc = take(Bn * DZ);
+  for (int m = 0; m < 2; ++m) L.g0[m] = take(Bn * Z2), L.g1[m] = take(Bn * Z2);
+  L.stats = take(2 * (Z2 + z + 2 * Z2));
+  L.dg1 = take(Bn * Z2), L.dg0 = take(Bn * Z2), L.dzc = take(Bn * DZ), L.dmu = take(Bn * z), L.dlv = take(Bn * z);
+  L.denc = take(Bn * z), L.de0 = take(Bn * z), L.df1 = take(Bn * Z2), L.df0 = take(Bn * Z2), L.dcat = take(Bn * D0);
+  L.total = o;
+  return L;
+}
+
+int64_t head_scratch_floats(int z, int h, int B) { return head_layout(z, h, B).total; }
+
+namespace {
+
+__device__ __forceinline__ float lrelu(float x, float slope) { return x > 0.f ? x : x * slope; }
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// out[b][j] = bias[j] + sum_i in[b][i] * W[j][i]   (optionally LeakyReLU)
+__device__ void ph_linear(const float* in, int ldi, const float* __restrict__ W, const float* __restrict__ bias,
+                          float* out, int ldo, int nin, int nout, int b_lo, int b_hi, float slope) {
+  const int total = (b_hi - b_lo) * nout;
+  for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+    const int b = b_lo + idx / nout, j = idx % nout;
+    const float* x = in + (int64_t)b * ldi;
+    const float* w = W + (int64_t)j * nin;
+    float s = 0.f;
+    for (int i = 0; i < nin; ++i) s = fmaf(x[i], w[i], s);
+    s += bias[j];
+    out[(int64_t)b * ldo + j] = slope >= 0.f ? lrelu(s, slope) : s;
+  }
+}
+
+// BatchNorm1d over the batch (training), one warp per feature, + LeakyReLU
+__device__ void ph_bn_train(const float* x, int ldx, int F, int B, const float* __restrict__ gamma,
+                            const float* __restrict__ beta, float* stat, float* rm, float* rv, int64_t* cnt,
+                            float* out, int ldo, float slope) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  for (int j = warp; j < F; j += nw) {
+    float s = 0.f;
+    for (int b = lane; b < B; b += 32) s += x[(int64_t)b * ldx + j];
+    const float mean = warp_sum(s) / (float)B;
+    float q = 0.f;
+    for (int b = lane; b < B; b += 32) {
+      float d = x[(int64_t)b * ldx + j] - mean;
+      q = fmaf(d, d, q);
+    }
+    q = warp_sum(q);
+    const float invstd = 1.f / sqrtf(q / (float)B + kBnEps);
+    if (lane == 0) {
+      stat[j] = mean, stat[F + j] = invstd;
+      rm[j] = (1.f - kBnMomentum) * rm[j] + kBnMomentum * mean;
+      rv[j] = (1.f - kBnMomentum) * rv[j] + kBnMomentum * (q / (float)max(B - 1, 1));
+    }
+    const float g = gamma[j] * invstd, be = beta[j];
+    for (int b = lane; b < B; b += 32)
+      out[(int64_t)b * ldo + j] = lrelu(fmaf(x[(int64_t)b * ldx + j] - mean, g, be), slope);
+  }
+  if (threadIdx.x == 0) *cnt += 1;
+}
+
+__device__ void ph_bn_eval(const float* x, int ldx, int F, int b_lo, int b_hi, const float* __restrict__ gamma,
+                           const float* __restrict__ beta, const float* rm, const float* rv, float* out, int ldo,
+                           float slope) {
+  const int total = (b_hi - b_lo) * F;
+  for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+    const int b = b_lo + idx / F, j = idx % F;
+    const float invstd = 1.f / sqrtf(rv[j] + kBnEps);
+    out[(int64_t)b * ldo + j] = lrelu(fmaf(x[(int64_t)b * ldx + j] - rm[j], gamma[j] * invstd, beta[j]), slope);
+  }
+}
+
+// dx[b][i] (=|+=) (sum_j dy[b][j] * W[j][i]) * lrelu'(mask[b][i])
+__device__ void ph_dgrad(const float* dy, int ldy, const float* __restrict__ W, int nin, int nout, float* dx, int ldx,
+                         const float* mask, int ldm, float slope, bool acc, int B) {
+  const int total = B * nin;
+  for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+    const int b = idx / nin, i = idx % nin;
+    const float* g = dy + (int64_t)b * ldy;
+    float s = 0.f;
+    for (int j = 0; j < nout; ++j) s = fmaf(g[j], W[(int64_t)j * nin + i], s);
+    if (mask) s *= mask[(int64_t)b * ldm + i] > 0.f ? 1.f : slope;
+    float* d = dx + (int64_t)b * ldx + i;
+    *d = acc ? *d + s : s;
+  }
+}
+
+// dW[j][i] = sum_b dy[b][j] * x[b][i];  db[j] = sum_b dy[b][j]
+__device__ void ph_wgrad(const float* dy, int ldy, const float* x, int ldx, int nin, int nout, float* dW, float* db,
+                         int B) {
+  const int total = nout * (nin + 1);
+  for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+    const int j = idx / (nin + 1), i = idx % (nin + 1);
+    float s = 0.f;
+    if (i < nin) {
+      for (int b = 0; b < B; ++b) s = fmaf(dy[(int64_t)b * ldy + j], x[(int64_t)b * ldx + i], s);
+      dW[(int64_t)j * nin + i] = s;
+    } else {
+      for (int b = 0; b < B; ++b) s += dy[(int64_t)b * ldy + j];
+      db[j] = s;
+    }
+  }
+}
+
+// backward of y = lrelu(bn(x)) over the batch; g is the gradient w.r.t. y
+__device__ void ph_bn_bwd(const float* g, int ldg, const float* y, int ldy, const float* x, int ldx, const float* stat,
+                          int F, const float* __restrict__ gamma, float* dgamma, float* dbeta, float* dx, int lddx,
+                          float slope, int B) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  for (int j = warp; j < F; j += nw) {
+    const float mean = stat[j], invstd = stat[F + j];
+    float s1 = 0.f, s2 = 0.f;
+    for (int b = lane; b < B; b += 32) {
+      const float gp = g[(int64_t)b * ldg + j] * (y[(int64_t)b * ldy + j] > 0.f ? 1.f : slope);
+      s1 += gp;
+      s2 = fmaf(gp, (x[(int64_t)b * ldx + j] - mean) * invstd, s2);
+    }
+    s1 = warp_sum(s1), s2 = warp_sum(s2);
+    if (lane == 0) dgamma[j] = s2, dbeta[j] = s1;
+    const float k = gamma[j] * invstd, m1 = s1 / (float)B, m2 = s2 / (float)B;
+    for (int b = lane; b < B; b += 32) {
+      const float gp = g[(int64_t)b * ldg + j] * (y[(int64_t)b * ldy + j] > 0.f ? 1.f : slope);
+      dx[(int64_t)b * lddx + j] = k * (gp - m1 - (x[(int64_t)b * ldx + j] - mean) * invstd * m2);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(1024) head_fwd_kernel(HeadArgs a) {
+  const HeadScratch L = head_layout(a.z, a.h, a.B);
+  float* S = a.scratch;
+  const HeadParams& P = a.hp;
+  const float* W = a.params;
+  const int z = a.z, h = a.h, Z2 = 2 * z, E = a.n_enc * Z2, D0 = E + 2 * h, DZ = z + 2 * h;
+  const int per = (a.B + gridDim.x - 1) / gridDim.x;
+  const int b_lo = min(a.B, (int)blockIdx.x * per), b_hi = min(a.B, b_lo + per);
+  const int nb = b_hi - b_lo;
+  __shared__ float sred[32];
+
+  // cat = [h1, (h2,) source_emb, class_emb]   (hippie/model.py:405-406, 425-426)
+  for (int idx = threadIdx.x; idx < nb * D0; idx += blockDim.x) {
+    const int b = b_lo + idx / D0, j = idx % D0;
+    float v;
+    if (j < E)
+      v = a.hin[j / Z2][(int64_t)b * Z2 + (j % Z2)];
+    else if (j < E + h)
+      v = W[P.src_emb + a.src[b] * h + (j - E)];
+    else
+      v = a.cls ? W[P.cls_emb + a.cls[b] * h + (j - E - h)] : 0.f;
+    S[L.cat + (int64_t)b * D0 + j] = v;
+  }
+  __syncthreads();
+  ph_linear(S + L.cat, D0, W + P.f0_w, W + P.f0_b, S + L.f0, Z2, D0, Z2, b_lo, b_hi, -1.f);
+  __syncthreads();
+  if (a.train)
+    ph_bn_train(S + L.f0, Z2, Z2, a.B, W + P.fbn_g, W + P.fbn_b, S + L.stats, a.run_mean + P.fbn_run,
+                a.run_var + P.fbn_run, a.run_count + P.fbn_cnt, S + L.f1, Z2, kSlopeHead);
+  else
+    ph_bn_eval(S + L.f0, Z2, Z2, b_lo, b_hi, W + P.fbn_g, W + P.fbn_b, a.run_mean + P.fbn_run, a.run_var + P.fbn_run,
+               S + L.f1, Z2, kSlopeHead);
+  __syncthreads();
+  ph_linear(S + L.f1, Z2, W + P.f3_w, W + P.f3_b, S + L.e0, z, Z2, z, b_lo, b_hi, -1.f);
+  __syncthreads();
+  if (P.ebn_g >= 0) {  // unimodal encoder_fc ends with BatchNorm1d(z) + LeakyReLU(0.2)  (hippie/model.py:21-28)
+    if (a.train)
+      ph_bn_train(S + L.e0, z, z, a.B, W + P.ebn_g, W + P.ebn_b, S + L.stats + 2 * Z2, a.run_mean + P.ebn_run,
+                  a.run_var + P.ebn_run, a.run_count + P.ebn_cnt, S + L.enc, z, kSlopeHead);
+    else
+      ph_bn_eval(S + L.e0, z, z, b_lo, b_hi, W + P.ebn_g, W + P.ebn_b, a.run_mean + P.ebn_run, a.run_var + P.ebn_run,
+                 S + L.enc, z, kSlopeHead);
+  } else {
+    for (int idx = threadIdx.x; idx < nb * z; idx += blockDim.x)
+      S[L.enc + (int64_t)b_lo * z + idx] = S[L.e0 + (int64_t)b_lo * z + idx];
+  }
+  __syncthreads();
+
+  // mu, logvar, z = mu + eps * exp(0.5 logvar), KL   (hippie/model.py:397-400, 408, 472)
+  float klp = 0.f;
+  for (int idx = threadIdx.x; idx < nb * z; idx += blockDim.x) {
+    const int b = b_lo + idx / z, i = idx % z;
+    const float* e = S + L.enc + (int64_t)b * z;
+    float m = 0.f, v = 0.f;
+    for (int k = 0; k < z; ++k) {
+      m = fmaf(e[k], W[P.zm_w + i * z + k], m);
+      v = fmaf(e[k], W[P.zv_w + i * z + k], v);
+    }
+    m += W[P.zm_b + i], v += W[P.zv_b + i];
+    S[L.mu + (int64_t)b * z + i] = m, S[L.lv + (int64_t)b * z + i] = v;
+    if (a.out_mu) a.out_mu[(int64_t)b * z + i] = m;
+    if (a.out_logvar) a.out_logvar[(int64_t)b * z + i] = v;
+    const float ev = expf(v);
+    klp += -0.5f * (1.f + v - m * m - ev);
+    if (a.decode) {
+      const float std = expf(0.5f * v);
+      S[L.zc + (int64_t)b * DZ + i] = fmaf(a.eps[(int64_t)b * z + i], std, m);
+    }
+  }
+  if (a.out_enc) {
+    if (a.zscore_ddof < 0) {
+      for (int idx = threadIdx.x; idx < nb * z; idx += blockDim.x)
+        a.out_enc[(int64_t)b_lo * z + idx] = S[L.enc + (int64_t)b_lo * z + idx];
+    } else {  // per-row z-score (scripts/train_model_with_multimodal.py:31 ddof 0; scripts/utils.py:87-88 ddof 1)
+      for (int bb = threadIdx.x; bb < nb; bb += blockDim.x) {
+        const float* e = S + L.enc + (int64_t)(b_lo + bb) * z;
+        float s = 0.f;
+        for (int k = 0; k < z; ++k) s += e[k];
+        const float mean = s / (float)z;
+        float q = 0.f;
+        for (int k = 0; k < z; ++k) q += (e[k] - mean) * (e[k] - mean);
+        const float sd = sqrtf(q / (float)(z - a.zscore_ddof));
+        for (int k = 0; k < z; ++k) a.out_enc[(int64_t)(b_lo + bb) * z + k] = (e[k] - mean) / sd;
+      }
+    }
+  }
+  klp = warp_sum(klp);
+  if ((threadIdx.x & 31) == 0) sred[threadIdx.x >> 5] = klp;
+  __syncthreads();
+  if (threadIdx.x == 0 && a.kl_sum) {
+    float s = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += sred[w];
+    atomicAdd(a.kl_sum, s);
+  }
+  if (!a.decode) return;
+
+  // zc = [z, source_emb, class_emb]   (hippie/model.py:412-413)
+  for (int idx = threadIdx.x; idx < nb * 2 * h; idx += blockDim.x) {
+    const int b = b_lo + idx / (2 * h), j = idx % (2 * h);
+    S[L.zc + (int64_t)b * DZ + z + j] = S[L.cat + (int64_t)b * D0 + E + j];
+  }
+  __syncthreads();
+  for (int m = 0; m < a.n_dec; ++m) {  // decoder_fc: Linear, LeakyReLU(.2), Linear, BatchNorm1d, LeakyReLU(.2)
+    ph_linear(S + L.zc, DZ, W + P.d0_w[m], W + P.d0_b[m], S + L.g0[m], Z2, DZ, Z2, b_lo, b_hi, kSlopeHead);
+    __syncthreads();
+    ph_linear(S + L.g0[m], Z2, W + P.d2_w[m], W + P.d2_b[m], S + L.g1[m], Z2, Z2, Z2, b_lo, b_hi, -1.f);
+    __syncthreads();
+    if (a.train)
+      ph_bn_train(S + L.g1[m], Z2, Z2, a.B, W + P.dbn_g[m], W + P.dbn_b[m], S + L.stats + 2 * (Z2 + z) + m * 2 * Z2,
+                  a.run_mean + P.dbn_run[m], a.run_var + P.dbn_run[m], a.run_count + P.dbn_cnt[m], a.dout[m], Z2,
+                  kSlopeHead);
+    else
+      ph_bn_eval(S + L.g1[m], Z2, Z2, b_lo, b_hi, W + P.dbn_g[m], W + P.dbn_b[m], a.run_mean + P.dbn_run[m],
+                 a.run_var + P.dbn_run[m], a.dout[m], Z2, kSlopeHead);
+  }
+}
+
+__global__ void __launch_bounds__(1024) head_bwd_kernel(HeadArgs a) {
+  const HeadScratch L = head_layout(a.z, a.h, a.B);
+  float* S = a.scratch;
+  const HeadParams& P = a.hp;
+  const float* W = a.params;
+  float* G = a.grads;
+  const int z = a.z, h = a.h, Z2 = 2 * z, E = a.n_enc * Z2, D0 = E + 2 * h, DZ = z + 2 * h, B = a.B;
+
+  for (int m = 0; m < a.n_dec; ++m) {
+    const float* stat = S + L.stats + 2 * (Z2 + z) + m * 2 * Z2;
+    ph_bn_bwd(a.dd[m], Z2, a.dout[m], Z2, S + L.g1[m], Z2, stat, Z2, W + P.dbn_g[m], G + P.dbn_g[m], G + P.dbn_b[m],
+              S + L.dg1, Z2, kSlopeHead, B);
+    __syncthreads();
+    ph_wgrad(S + L.dg1, Z2, S + L.g0[m], Z2, Z2, Z2, G + P.d2_w[m], G + P.d2_b[m], B);
+    ph_dgrad(S + L.dg1, Z2, W + P.d2_w[m], Z2, Z2, S + L.dg0, Z2, S + L.g0[m], Z2, kSlopeHead, false, B);
+    __syncthreads();
+    ph_wgrad(S + L.dg0, Z2, S + L.zc, DZ, DZ, Z2, G + P.d0_w[m], G + P.d0_b[m], B);
+    ph_dgrad(S + L.dg0, Z2, W + P.d0_w[m], DZ, Z2, S + L.dzc, DZ, nullptr, 0, 0.f, m > 0, B);
+    __syncthreads();
+  }
+  // reparameterisation + KL  (hippie/model.py:397-400, 472-474): total = ... + beta * mean_b(kl_b)
+  const float kscale = a.beta / (float)B;
+  for (int idx = threadIdx.x; idx < B * z; idx += blockDim.x) {
+    const int b = idx / z, i = idx % z;
+    const float dz = S[L.dzc + (int64_t)b * DZ + i];
+    const float mu = S[L.mu + idx], lv = S[L.lv + idx];
+    const float std = expf(0.5f * lv);
+    S[L.dmu + idx] = dz + kscale * mu;
+    S[L.dlv + idx] = dz * a.eps[idx] * 0.5f * std + kscale * 0.5f * (expf(lv) - 1.f);
+  }
+  __syncthreads();
+  ph_wgrad(S + L.dmu, z, S + L.enc, z, z, z, G + P.zm_w, G + P.zm_b, B);
+  ph_wgrad(S + L.dlv, z, S + L.enc, z, z, z, G + P.zv_w, G + P.zv_b, B);
+  ph_dgrad(S + L.dmu, z, W + P.zm_w, z, z, S + L.denc, z, nullptr, 0, 0.f, false, B);
+  __syncthreads();
+  ph_dgrad(S + L.dlv, z, W + P.zv_w, z, z, S + L.denc, z, nullptr, 0, 0.f, true, B);
+  __syncthreads();
+  const float* de0 = S + L.denc;
+  if (P.ebn_g >= 0) {
+    ph_bn_bwd(S + L.denc, z, S + L.enc, z, S + L.e0, z, S + L.stats + 2 * Z2, z, W + P.ebn_g, G + P.ebn_g,
+              G + P.ebn_b, S + L.de0, z, kSlopeHead, B);
+    de0 = S + L.de0;
+    __syncthreads();
+  }
+  ph_wgrad(de0, z, S + L.f1, Z2, Z2, z, G + P.f3_w, G + P.f3_b, B);
+  ph_dgrad(de0, z, W + P.f3_w, Z2, z, S + L.df1, Z2, nullptr, 0, 0.f, false, B);
+  __syncthreads();
+  ph_bn_bwd(S + L.df1, Z2, S + L.f1, Z2, S + L.f0, Z2, S + L.stats, Z2, W + P.fbn_g, G + P.fbn_g, G + P.fbn_b,
+            S + L.df0, Z2, kSlopeHead, B);
+  __syncthreads();
+  ph_wgrad(S + L.df0, Z2, S + L.cat, D0, D0, Z2, G + P.f0_w, G + P.f0_b, B);
+  ph_dgrad(S + L.df0, Z2, W + P.f0_w, D0, Z2, S + L.dcat, D0, nullptr, 0, 0.f, false, B);
+  __syncthreads();
+  for (int e = 0; e < a.n_enc; ++e)
+    for (int idx = threadIdx.x; idx < B * Z2; idx += blockDim.x)
+      a.dh[e][idx] = S[L.dcat + (int64_t)(idx / Z2) * D0 + e * Z2 + (idx % Z2)];
+  // embedding gradients (scatter-add of the two places each embedding is used)
+  for (int idx = threadIdx.x; idx < a.num_sources * h; idx += blockDim.x) {
+    const int s = idx / h, k = idx % h;
+    float acc = 0.f;
+    for (int b = 0; b < B; ++b)
+      if (a.src[b] == s) acc += S[L.dcat + (int64_t)b * D0 + E + k] + S[L.dzc + (int64_t)b * DZ + z + k];
+    G[P.src_emb + idx] = acc;
+  }
+  if (a.cls) {
+    for (int idx = threadIdx.x; idx < a.num_classes * h; idx += blockDim.x) {
+      const int s = idx / h, k = idx % h;
+      float acc = 0.f;
+      for (int b = 0; b < B; ++b)
+        if (a.cls[b] == s) acc += S[L.dcat + (int64_t)b * D0 + E + h + k] + S[L.dzc + (int64_t)b * DZ + z + h + k];
+      G[P.cls_emb + idx] = acc;
+    }
+  }
+}
+
+}  // namespace
+
+void launch_head_fwd(const HeadArgs& a, cudaStream_t s) {
+  int grid = 1;
+  if (!a.train) {
+    grid = (a.B + 255) / 256;
+    if (grid > 148) grid = 148;
+    if (grid < 1) grid = 1;
+  }
+  head_fwd_kernel<<<grid, a.train ? 1024 : 256, 0, s>>>(a);
+}
+void launch_head_bwd(const HeadArgs& a, cudaStream_t s) { head_bwd_kernel<<<1, 1024, 0, s>>>(a); }
+
+}  // namespace hp

@@ -1,0 +1,807 @@
+// HBM-bound kernels of the cVAE step: stem conv, BatchNorm finalize / apply / backward, pooling +
+// linear tails, decoder head and tail (+ MSE), gradient clipping + AdamW.  All tensors are
+// channels-last padded rows (kernels.cuh).  Reference anchors are given per kernel.
+#include "kernels.cuh"
+
+namespace hp {
+
+namespace {
+
+__device__ __forceinline__ float lrelu(float x, float slope) { return x > 0.f ? x : x * slope; }
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Stem: Conv1d(1, 64, k3, s2, p1, bias=False)   reference hippie/backbones.py:78,95
+// 128 logical rows per CTA; thread = (channel, row group of 4).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float xin(const float* x, int Lin, int i) { return (i >= 0 && i < Lin) ? __ldg(x + i) : 0.f; }
+
+__global__ void __launch_bounds__(256) stem_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                       float* __restrict__ c0, float* __restrict__ part, int B,
+                                                       int Lin, int Lout) {
+  __shared__ float red[4][64];
+  __shared__ float smean[64];
+  const int co = threadIdx.x & 63, rg = threadIdx.x >> 6;
+  const int M = B * Lout, m0 = blockIdx.x * 128;
+  const float w0 = w[co * 3 + 0], w1 = w[co * 3 + 1], w2 = w[co * 3 + 2];
+  float s = 0.f;
+  for (int r = rg; r < 128; r += 4) {
+    int m = m0 + r;
+    if (m >= M) break;
+    int b = m / Lout, l = m - b * Lout;
+    const float* xb = x + (int64_t)b * Lin;
+    float v = w0 * xin(xb, Lin, 2 * l - 1);
+    v = fmaf(w1, xin(xb, Lin, 2 * l), v);
+    v = fmaf(w2, xin(xb, Lin, 2 * l + 1), v);
+    c0[((int64_t)b * (Lout + 2) + 1 + l) * 64 + co] = v;
+    s += v;
+  }
+  if (!part) return;
+  red[rg][co] = s;
+  __syncthreads();
+  const int nvalid = min(128, M - m0);
+  float colsum = red[0][co] + red[1][co] + red[2][co] + red[3][co];
+  if (rg == 0) smean[co] = colsum / (float)nvalid;
+  __syncthreads();
+  const float mu = smean[co];
+  float q = 0.f;
+  for (int r = rg; r < 128; r += 4) {
+    int m = m0 + r;
+    if (m >= M) break;
+    int b = m / Lout, l = m - b * Lout;
+    float d = c0[((int64_t)b * (Lout + 2) + 1 + l) * 64 + co] - mu;
+    q += d * d;
+  }
+  __syncthreads();
+  red[rg][co] = q;
+  __syncthreads();
+  if (rg == 0) {
+    float m2 = red[0][co] + red[1][co] + red[2][co] + red[3][co];
+    part[((int64_t)blockIdx.x * 64 + co) * 2 + 0] = colsum;
+    part[((int64_t)blockIdx.x * 64 + co) * 2 + 1] = m2;
+  }
+}
+
+__global__ void __launch_bounds__(256) stem_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dc0,
+                                                         float* __restrict__ part, int B, int Lin, int Lout) {
+  __shared__ float red[4][192];
+  const int co = threadIdx.x & 63, rg = threadIdx.x >> 6;
+  const int M = B * Lout, m0 = blockIdx.x * 128;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+  for (int r = rg; r < 128; r += 4) {
+    int m = m0 + r;
+    if (m >= M) break;
+    int b = m / Lout, l = m - b * Lout;
+    const float* xb = x + (int64_t)b * Lin;
+    float g = dc0[((int64_t)b * (Lout + 2) + 1 + l) * 64 + co];
+    a0 = fmaf(g, xin(xb, Lin, 2 * l - 1), a0);
+    a1 = fmaf(g, xin(xb, Lin, 2 * l), a1);
+    a2 = fmaf(g, xin(xb, Lin, 2 * l + 1), a2);
+  }
+  red[rg][co * 3 + 0] = a0, red[rg][co * 3 + 1] = a1, red[rg][co * 3 + 2] = a2;
+  __syncthreads();
+  if (threadIdx.x < 192) {
+    int i = threadIdx.x;
+    part[(int64_t)blockIdx.x * 192 + i] = red[0][i] + red[1][i] + red[2][i] + red[3][i];
+  }
+}
+
+__global__ void reduce_partials_kernel(const float* __restrict__ part, int nparts, int n, float* __restrict__ out,
+                                       int accumulate) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double s = 0.0;
+  for (int p = 0; p < nparts; ++p) s += (double)part[(int64_t)p * n + i];
+  out[i] = accumulate ? out[i] + (float)s : (float)s;
+}
+
+// ------------------------------------------------------------------------------------------------
+// BatchNorm1d, training statistics (nn.BatchNorm1d defaults: eps 1e-5, momentum 0.1, biased variance
+// to normalise, unbiased into running_var).  One warp per channel, Chan's parallel combination of
+// the per-tile (sum, centred M2) partials in double.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) bn_finalize_train_kernel(BnFinalize f) {
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (c >= f.C) return;
+  double S = 0.0;
+  for (int t = lane; t < f.ntiles; t += 32) S += (double)f.part[((int64_t)t * f.C + c) * 2];
+  S = warp_sum_d(S);
+  const double mean = S / (double)f.M;
+  double M2 = 0.0;
+  for (int t = lane; t < f.ntiles; t += 32) {
+    int nt = min(f.tile_rows, f.M - t * f.tile_rows);
+    double st = (double)f.part[((int64_t)t * f.C + c) * 2], m2 = (double)f.part[((int64_t)t * f.C + c) * 2 + 1];
+    double d = st / (double)nt - mean;
+    M2 += m2 + (double)nt * d * d;
+  }
+  M2 = warp_sum_d(M2);
+  if (lane == 0) {
+    const double var_b = M2 / (double)f.M;
+    const float invstd = (float)(1.0 / sqrt(var_b + (double)kBnEps));
+    const float meanf = (float)mean;
+    f.coef[0 * f.C + c] = f.gamma[c] * invstd;
+    f.coef[1 * f.C + c] = f.beta[c];
+    f.coef[2 * f.C + c] = meanf;
+    f.coef[3 * f.C + c] = invstd;
+    const float var_u = (float)(M2 / (double)max(f.M - 1, 1));
+    f.run_mean[c] = (1.f - kBnMomentum) * f.run_mean[c] + kBnMomentum * meanf;
+    f.run_var[c] = (1.f - kBnMomentum) * f.run_var[c] + kBnMomentum * var_u;
+    if (c == 0) *f.run_count += 1;
+  }
+}
+
+__global__ void bn_eval_coefs_kernel(const BnEvalEntry* __restrict__ tab, const float* __restrict__ params,
+                                     const float* __restrict__ run_mean, const float* __restrict__ run_var,
+                                     float* __restrict__ ws) {
+  const BnEvalEntry e = tab[blockIdx.x];
+  float* coef = ws + e.coef_off;
+  for (int c = threadIdx.x; c < e.C; c += blockDim.x) {
+    float invstd = 1.f / sqrtf(run_var[e.run_off + c] + kBnEps);
+    coef[0 * e.C + c] = params[e.gamma_off + c] * invstd;
+    coef[1 * e.C + c] = params[e.beta_off + c];
+    coef[2 * e.C + c] = run_mean[e.run_off + c];
+    coef[3 * e.C + c] = invstd;
+  }
+}
+
+// out = lrelu((c - mean)*scale + beta + residual)   reference hippie/backbones.py:37-40,66-69,95
+template <int RES>  // 0 none, 1 identity, 2 BatchNorm'd shortcut
+__global__ void __launch_bounds__(256) bn_apply_kernel(BnApply a) {
+  const int C4 = a.C >> 2;
+  const int64_t total = (int64_t)a.B * a.L * C4;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int cq = (int)(i % C4);
+    const int64_t m = i / C4;
+    const int b = (int)(m / a.L), l = (int)(m - (int64_t)b * a.L);
+    const int64_t row = (int64_t)b * (a.L + 2) + 1 + l;
+    const float4 x = *reinterpret_cast<const float4*>(a.c + row * a.C + cq * 4);
+    const float4 sc = *reinterpret_cast<const float4*>(a.coef + 0 * a.C + cq * 4);
+    const float4 be = *reinterpret_cast<const float4*>(a.coef + 1 * a.C + cq * 4);
+    const float4 mu = *reinterpret_cast<const float4*>(a.coef + 2 * a.C + cq * 4);
+    float4 y;
+    y.x = fmaf(x.x - mu.x, sc.x, be.x), y.y = fmaf(x.y - mu.y, sc.y, be.y);
+    y.z = fmaf(x.z - mu.z, sc.z, be.z), y.w = fmaf(x.w - mu.w, sc.w, be.w);
+    if (RES == 1) {
+      const float4 r = *reinterpret_cast<const float4*>(a.r + row * a.C + cq * 4);
+      y.x += r.x, y.y += r.y, y.z += r.z, y.w += r.w;
+    } else if (RES == 2) {
+      const float4 r = *reinterpret_cast<const float4*>(a.r + row * a.C + cq * 4);
+      const float4 rs = *reinterpret_cast<const float4*>(a.rcoef + 0 * a.C + cq * 4);
+      const float4 rb = *reinterpret_cast<const float4*>(a.rcoef + 1 * a.C + cq * 4);
+      const float4 rm = *reinterpret_cast<const float4*>(a.rcoef + 2 * a.C + cq * 4);
+      y.x += fmaf(r.x - rm.x, rs.x, rb.x), y.y += fmaf(r.y - rm.y, rs.y, rb.y);
+      y.z += fmaf(r.z - rm.z, rs.z, rb.z), y.w += fmaf(r.w - rm.w, rs.w, rb.w);
+    }
+    y.x = lrelu(y.x, a.slope), y.y = lrelu(y.y, a.slope), y.z = lrelu(y.z, a.slope), y.w = lrelu(y.w, a.slope);
+    *reinterpret_cast<float4*>(a.out + row * a.C + cq * 4) = y;
+    if (a.out_up) {
+      const int64_t ru = (int64_t)b * (2 * a.L + 2) + 1 + 2 * l;
+      *reinterpret_cast<float4*>(a.out_up + ru * a.C + cq * 4) = y;
+      *reinterpret_cast<float4*>(a.out_up + (ru + 1) * a.C + cq * 4) = y;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// BatchNorm backward (train mode), fused with the LeakyReLU backward and the residual split.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float4 load_g(const BnBwd& a, int b, int l, int cq) {
+  if (a.g_up) {
+    const int64_t ru = (int64_t)b * (2 * a.L + 2) + 1 + 2 * l;
+    const float4 g0 = *reinterpret_cast<const float4*>(a.g + ru * a.C + cq * 4);
+    const float4 g1 = *reinterpret_cast<const float4*>(a.g + (ru + 1) * a.C + cq * 4);
+    return make_float4(g0.x + g1.x, g0.y + g1.y, g0.z + g1.z, g0.w + g1.w);
+  }
+  const int64_t row = (int64_t)b * (a.L + 2) + 1 + l;
+  return *reinterpret_cast<const float4*>(a.g + row * a.C + cq * 4);
+}
+
+// part[chunk][C][3] = (S1, S2, S2s)
+__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(BnBwd a, int rows_per_cta) {
+  __shared__ float4 red[3][256];
+  const int C4 = a.C >> 2;
+  const int RL = 256 / C4;  // row lanes
+  const int cq = threadIdx.x % C4, rl = threadIdx.x / C4;
+  const int M = a.B * a.L;
+  const int m_begin = blockIdx.x * rows_per_cta, m_end = min(M, m_begin + rows_per_cta);
+  float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1, s3 = s1;
+  if (rl < RL) {
+    const float4 mu = *reinterpret_cast<const float4*>(a.coef + 2 * a.C + cq * 4);
+    const float4 is = *reinterpret_cast<const float4*>(a.coef + 3 * a.C + cq * 4);
+    float4 mus = mu, iss = is;
+    if (a.cs) {
+      mus = *reinterpret_cast<const float4*>(a.coef_s + 2 * a.C + cq * 4);
+      iss = *reinterpret_cast<const float4*>(a.coef_s + 3 * a.C + cq * 4);
+    }
+    for (int m = m_begin + rl; m < m_end; m += RL) {
+      const int b = m / a.L, l = m - b * a.L;
+      const int64_t row = (int64_t)b * (a.L + 2) + 1 + l;
+      float4 g = load_g(a, b, l, cq);
+      const float4 o = *reinterpret_cast<const float4*>(a.out + row * a.C + cq * 4);
+      g.x *= o.x > 0.f ? 1.f : a.slope, g.y *= o.y > 0.f ? 1.f : a.slope;
+      g.z *= o.z > 0.f ? 1.f : a.slope, g.w *= o.w > 0.f ? 1.f : a.slope;
+      const float4 x = *reinterpret_cast<const float4*>(a.c + row * a.C + cq * 4);
+      s1.x += g.x, s1.y += g.y, s1.z += g.z, s1.w += g.w;
+      s2.x = fmaf(g.x, (x.x - mu.x) * is.x, s2.x), s2.y = fmaf(g.y, (x.y - mu.y) * is.y, s2.y);
+      s2.z = fmaf(g.z, (x.z - mu.z) * is.z, s2.z), s2.w = fmaf(g.w, (x.w - mu.w) * is.w, s2.w);
+      if (a.cs) {
+        const float4 xs = *reinterpret_cast<const float4*>(a.cs + row * a.C + cq * 4);
+        s3.x = fmaf(g.x, (xs.x - mus.x) * iss.x, s3.x), s3.y = fmaf(g.y, (xs.y - mus.y) * iss.y, s3.y);
+        s3.z = fmaf(g.z, (xs.z - mus.z) * iss.z, s3.z), s3.w = fmaf(g.w, (xs.w - mus.w) * iss.w, s3.w);
+      }
+    }
+  }
+  red[0][threadIdx.x] = s1, red[1][threadIdx.x] = s2, red[2][threadIdx.x] = s3;
+  __syncthreads();
+  if (threadIdx.x < C4) {
+    for (int k = 0; k < 3; ++k) {
+      float4 t = red[k][cq];
+      for (int r = 1; r < RL; ++r) {
+        float4 u = red[k][r * C4 + cq];
+        t.x += u.x, t.y += u.y, t.z += u.z, t.w += u.w;
+      }
+      float* dst = a.part + ((int64_t)blockIdx.x * a.C + cq * 4) * 3;
+      dst[0 * 3 + k] = t.x, dst[1 * 3 + k] = t.y, dst[2 * 3 + k] = t.z, dst[3 * 3 + k] = t.w;
+    }
+  }
+}
+
+// coef[4]=k=gamma*invstd, [5]=m1=S1/n, [6]=m2=S2/n ; dgamma=S2, dbeta=S1
+__global__ void __launch_bounds__(256) bn_bwd_finalize_kernel(BnBwd a, int nchunks) {
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (c >= a.C) return;
+  double s1 = 0.0, s2 = 0.0, s3 = 0.0;
+  for (int t = lane; t < nchunks; t += 32) {
+    const float* p = a.part + ((int64_t)t * a.C + c) * 3;
+    s1 += (double)p[0], s2 += (double)p[1], s3 += (double)p[2];
+  }
+  s1 = warp_sum_d(s1), s2 = warp_sum_d(s2), s3 = warp_sum_d(s3);
+  if (lane == 0) {
+    const double n = (double)a.B * a.L;
+    a.coef[4 * a.C + c] = a.gamma[c] * a.coef[3 * a.C + c];
+    a.coef[5 * a.C + c] = (float)(s1 / n);
+    a.coef[6 * a.C + c] = (float)(s2 / n);
+    a.dgamma[c] = (float)s2;
+    a.dbeta[c] = (float)s1;
+    if (a.cs) {
+      a.coef_s[4 * a.C + c] = a.gamma_s[c] * a.coef_s[3 * a.C + c];
+      a.coef_s[5 * a.C + c] = (float)(s1 / n);
+      a.coef_s[6 * a.C + c] = (float)(s3 / n);
+      a.dgamma_s[c] = (float)s3;
+      a.dbeta_s[c] = (float)s1;
+    }
+  }
+}
+
+__device__ __forceinline__ float4 bn_dx(float4 g, float4 x, float4 mu, float4 is, float4 k, float4 m1, float4 m2) {
+  float4 r;
+  r.x = k.x * (g.x - m1.x - (x.x - mu.x) * is.x * m2.x);
+  r.y = k.y * (g.y - m1.y - (x.y - mu.y) * is.y * m2.y);
+  r.z = k.z * (g.z - m1.z - (x.z - mu.z) * is.z * m2.z);
+  r.w = k.w * (g.w - m1.w - (x.w - mu.w) * is.w * m2.w);
+  return r;
+}
+
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(BnBwd a) {
+  const int C4 = a.C >> 2;
+  const int64_t total = (int64_t)a.B * a.L * C4;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int cq = (int)(i % C4);
+    const int64_t m = i / C4;
+    const int b = (int)(m / a.L), l = (int)(m - (int64_t)b * a.L);
+    const int64_t row = (int64_t)b * (a.L + 2) + 1 + l;
+    float4 g = load_g(a, b, l, cq);
+    const float4 o = *reinterpret_cast<const float4*>(a.out + row * a.C + cq * 4);
+    g.x *= o.x > 0.f ? 1.f : a.slope, g.y *= o.y > 0.f ? 1.f : a.slope;
+    g.z *= o.z > 0.f ? 1.f : a.slope, g.w *= o.w > 0.f ? 1.f : a.slope;
+    if (a.gres) *reinterpret_cast<float4*>(a.gres + row * a.C + cq * 4) = g;
+    {
+      const float4 x = *reinterpret_cast<const float4*>(a.c + row * a.C + cq * 4);
+      const float4 mu = *reinterpret_cast<const float4*>(a.coef + 2 * a.C + cq * 4);
+      const float4 is = *reinterpret_cast<const float4*>(a.coef + 3 * a.C + cq * 4);
+      const float4 k = *reinterpret_cast<const float4*>(a.coef + 4 * a.C + cq * 4);
+      const float4 m1 = *reinterpret_cast<const float4*>(a.coef + 5 * a.C + cq * 4);
+      const float4 m2 = *reinterpret_cast<const float4*>(a.coef + 6 * a.C + cq * 4);
+      const int64_t drow = (int64_t)b * (a.Ld + 2) + 1 + (int64_t)a.dil * l;
+      *reinterpret_cast<float4*>(a.dc + drow * a.C + cq * 4) = bn_dx(g, x, mu, is, k, m1, m2);
+    }
+    if (a.cs) {
+      const float4 x = *reinterpret_cast<const float4*>(a.cs + row * a.C + cq * 4);
+      const float4 mu = *reinterpret_cast<const float4*>(a.coef_s + 2 * a.C + cq * 4);
+      const float4 is = *reinterpret_cast<const float4*>(a.coef_s + 3 * a.C + cq * 4);
+      const float4 k = *reinterpret_cast<const float4*>(a.coef_s + 4 * a.C + cq * 4);
+      const float4 m1 = *reinterpret_cast<const float4*>(a.coef_s + 5 * a.C + cq * 4);
+      const float4 m2 = *reinterpret_cast<const float4*>(a.coef_s + 6 * a.C + cq * 4);
+      const int64_t drow = (int64_t)b * (a.Ld_s + 2) + 1 + (int64_t)a.dil_s * l;
+      *reinterpret_cast<float4*>(a.dcs + drow * a.C + cq * 4) = bn_dx(g, x, mu, is, k, m1, m2);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) pairsum_acc_kernel(const float* __restrict__ src, float* __restrict__ dst, int B,
+                                                          int L, int C) {
+  const int C4 = C >> 2;
+  const int64_t total = (int64_t)B * L * C4;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int cq = (int)(i % C4);
+    const int64_t m = i / C4;
+    const int b = (int)(m / L), l = (int)(m - (int64_t)b * L);
+    const int64_t row = (int64_t)b * (L + 2) + 1 + l, ru = (int64_t)b * (2 * L + 2) + 1 + 2 * l;
+    float4 d = *reinterpret_cast<float4*>(dst + row * C + cq * 4);
+    const float4 s0 = *reinterpret_cast<const float4*>(src + ru * C + cq * 4);
+    const float4 s1 = *reinterpret_cast<const float4*>(src + (ru + 1) * C + cq * 4);
+    d.x += s0.x + s1.x, d.y += s0.y + s1.y, d.z += s0.z + s1.z, d.w += s0.w + s1.w;
+    *reinterpret_cast<float4*>(dst + row * C + cq * 4) = d;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Encoder tail: adaptive_avg_pool1d(x, 1) + Linear(512 -> F)   reference hippie/backbones.py:100-102
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) pool_linear_fwd_kernel(const float* __restrict__ x4, int L, int C,
+                                                              const float* __restrict__ W,
+                                                              const float* __restrict__ bias, int F,
+                                                              float* __restrict__ pooled, float* __restrict__ h) {
+  extern __shared__ float sp[];  // [C]
+  const int b = blockIdx.x;
+  const float inv = 1.f / (float)L;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float s = 0.f;
+    for (int l = 0; l < L; ++l) s += x4[((int64_t)b * (L + 2) + 1 + l) * C + c];
+    s *= inv;
+    sp[c] = s;
+    pooled[(int64_t)b * C + c] = s;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  for (int f = warp; f < F; f += nw) {
+    float s = 0.f;
+    for (int c = lane; c < C; c += 32) s = fmaf(sp[c], __ldg(W + (int64_t)f * C + c), s);
+    s = warp_sum(s);
+    if (lane == 0) h[(int64_t)b * F + f] = s + bias[f];
+  }
+}
+
+__global__ void __launch_bounds__(128) pool_linear_bwd_x_kernel(const float* __restrict__ dh,
+                                                                const float* __restrict__ W, int L, int C, int F,
+                                                                float* __restrict__ g_x4) {
+  extern __shared__ float sd[];  // [F]
+  const int b = blockIdx.x;
+  for (int f = threadIdx.x; f < F; f += blockDim.x) sd[f] = dh[(int64_t)b * F + f];
+  __syncthreads();
+  const float inv = 1.f / (float)L;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float s = 0.f;
+    for (int f = 0; f < F; ++f) s = fmaf(sd[f], __ldg(W + (int64_t)f * C + c), s);
+    s *= inv;
+    for (int l = 0; l < L; ++l) g_x4[((int64_t)b * (L + 2) + 1 + l) * C + c] = s;
+  }
+}
+
+// dW[f][c] = sum_b dh[b][f] * pooled[b][c];  db[f] = sum_b dh[b][f].   grid = F, block = 256
+__global__ void __launch_bounds__(256) linear_wgrad_rows_kernel(const float* __restrict__ dy, int ldy,
+                                                                const float* __restrict__ x, int ldx, int B, int nin,
+                                                                float* __restrict__ dW, float* __restrict__ db) {
+  const int f = blockIdx.x;
+  for (int c = threadIdx.x; c < nin; c += blockDim.x) {
+    float s = 0.f;
+    for (int b = 0; b < B; ++b) s = fmaf(__ldg(dy + (int64_t)b * ldy + f), __ldg(x + (int64_t)b * ldx + c), s);
+    dW[(int64_t)f * nin + c] = s;
+  }
+  if (threadIdx.x < 32 && db) {
+    float s = 0.f;
+    for (int b = threadIdx.x; b < B; b += 32) s += dy[(int64_t)b * ldy + f];
+    s = warp_sum(s);
+    if (threadIdx.x == 0) db[f] = s;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Decoder head: Linear(F -> 512), unsqueeze(-1), nearest x4   reference hippie/backbones.py:129-131
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) dec_linear_fwd_kernel(const float* __restrict__ d, int F,
+                                                             const float* __restrict__ W,
+                                                             const float* __restrict__ bias, int C,
+                                                             float* __restrict__ t0) {
+  extern __shared__ float sd[];  // [F]
+  const int b = blockIdx.x;
+  for (int f = threadIdx.x; f < F; f += blockDim.x) sd[f] = d[(int64_t)b * F + f];
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float s = 0.f;
+    const float* w = W + (int64_t)c * F;
+    for (int f = 0; f < F; ++f) s = fmaf(sd[f], __ldg(w + f), s);
+    s += bias[c];
+#pragma unroll
+    for (int l = 0; l < 4; ++l) t0[((int64_t)b * 6 + 1 + l) * C + c] = s;
+  }
+}
+
+__global__ void __launch_bounds__(256) dec_linear_bwd_x_kernel(const float* __restrict__ g_t0,
+                                                               const float* __restrict__ W, int F, int C,
+                                                               float* __restrict__ gx0, float* __restrict__ dd) {
+  extern __shared__ float sg[];  // [C]
+  const int b = blockIdx.x;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float s = 0.f;
+#pragma unroll
+    for (int l = 0; l < 4; ++l) s += g_t0[((int64_t)b * 6 + 1 + l) * C + c];
+    sg[c] = s;
+    gx0[(int64_t)b * C + c] = s;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  for (int f = warp; f < F; f += nw) {
+    float s = 0.f;
+    for (int c = lane; c < C; c += 32) s = fmaf(sg[c], __ldg(W + (int64_t)c * F + f), s);
+    s = warp_sum(s);
+    if (lane == 0) dd[(int64_t)b * F + f] = s;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Decoder tail + MSE (+ backward down to the layer1 output)
+//   reference hippie/backbones.py:117-118,136-139; hippie/model.py:465-466
+// ------------------------------------------------------------------------------------------------
+constexpr int kTailSPB = 4;  // samples per CTA
+__global__ void __launch_bounds__(256) dec_tail_kernel(DecTail t) {
+  extern __shared__ float sm[];
+  float* xs = sm;                      // [34][65]
+  float* Wos = xs + 34 * 65;           // [Lo][65]
+  float* ys = Wos + t.Lo * 65;         // [64]
+  float* dds = ys + 64;                // [Lo]
+  float* dys = dds + ((t.Lo + 3) & ~3);  // [66]: dys[1 + p], zero guards
+  float* wcs = dys + 68;               // [192]
+  __shared__ float sred[8];
+  const int tid = threadIdx.x;
+  for (int i = tid; i < t.Lo * 64; i += 256) Wos[(i >> 6) * 65 + (i & 63)] = t.Wo[i];
+  for (int i = tid; i < 192; i += 256) wcs[i] = t.wc[i];
+  if (tid < 65) xs[0 * 65 + tid] = 0.f, xs[33 * 65 + tid] = 0.f;
+  if (tid == 0) dys[0] = 0.f, dys[65] = 0.f;
+  const float bc = t.bc[0];
+  float dw_acc = 0.f, dbc_acc = 0.f, sse_acc = 0.f;
+  const float gscale = t.train ? t.loss_w * 2.f / ((float)t.B * (float)t.Lo) : 0.f;
+
+  for (int sb = 0; sb < kTailSPB; ++sb) {
+    const int b = blockIdx.x * kTailSPB + sb;
+    if (b >= t.B) break;  // uniform across the CTA
+    __syncthreads();
+    for (int i = tid; i < 32 * 64; i += 256) xs[(1 + (i >> 6)) * 65 + (i & 63)] = t.x[((int64_t)b * 34 + 1) * 64 + i];
+    __syncthreads();
+    {  // y[p] = bc + sum_t sum_c u[p+t-1][c] * wc[t][c];  u[q] = x[q >> 1], zero outside [0, 64)
+      const int p = tid >> 2, part = tid & 3;
+      float s = 0.f;
+#pragma unroll
+      for (int tt = 0; tt < 3; ++tt) {
+        const int q = p + tt - 1;
+        const int row = q < 0 ? 0 : (q >= 64 ? 33 : 1 + (q >> 1));
+#pragma unroll
+        for (int c = 0; c < 16; ++c) s = fmaf(xs[row * 65 + part * 16 + c], wcs[tt * 64 + part * 16 + c], s);
+      }
+      s += __shfl_xor_sync(0xffffffffu, s, 1);
+      s += __shfl_xor_sync(0xffffffffu, s, 2);
+      if (part == 0) {
+        s += bc;
+        ys[p] = s;
+        if (t.y) t.y[(int64_t)b * 64 + p] = s;
+      }
+    }
+    __syncthreads();
+    float sq = 0.f;
+    if (tid < t.Lo) {
+      float s = 0.f;
+#pragma unroll 8
+      for (int p = 0; p < 64; ++p) s = fmaf(ys[p], Wos[tid * 65 + p], s);
+      s += t.bo[tid];
+      t.dec[(int64_t)b * t.Lo + tid] = s;
+      if (t.target) {
+        const float diff = s - t.target[(int64_t)b * t.Lo + tid];
+        sq = diff * diff;
+        const float gd = gscale * diff;
+        dds[tid] = gd;
+        if (t.train) t.ddec[(int64_t)b * t.Lo + tid] = gd;
+      }
+    }
+    if (t.target) {
+      sq = warp_sum(sq);
+      if ((tid & 31) == 0) sred[tid >> 5] = sq;
+    }
+    __syncthreads();
+    if (t.target && tid == 0) {
+      float s = 0.f;
+      for (int w = 0; w < 8; ++w) s += sred[w];
+      sse_acc += s;
+    }
+    if (!t.train) continue;
+    if (tid < 64) {  // dy[p] = sum_o ddec[o] * Wo[o][p]
+      float s = 0.f;
+      for (int o = 0; o < t.Lo; ++o) s = fmaf(dds[o], Wos[o * 65 + tid], s);
+      dys[1 + tid] = s;
+      t.dy[(int64_t)b * 64 + tid] = s;
+    }
+    __syncthreads();
+    {  // gradient w.r.t. x: du[q][c] = sum_t dy[q-t+1] * wc[t][c];  g_x[l] = du[2l] + du[2l+1]
+      const int c = tid & 63, lg = tid >> 6;
+      const float w0 = wcs[c], w1 = wcs[64 + c], w2 = wcs[128 + c];
+      for (int l = lg; l < 32; l += 4) {
+        const int q = 2 * l;  // dys index offset +1
+        const float du0 = dys[1 + q + 1] * w0 + dys[1 + q] * w1 + dys[1 + q - 1] * w2;
+        const float du1 = dys[1 + q + 2] * w0 + dys[1 + q + 1] * w1 + dys[1 + q] * w2;
+        t.g_x[((int64_t)b * 34 + 1 + l) * 64 + c] = du0 + du1;
+      }
+    }
+    if (tid < 192) {  // dwc[t][c] += sum_p dy[p] * u[p+t-1][c]
+      const int tt = tid >> 6, c = tid & 63;
+      float s = 0.f;
+      for (int p = 0; p < 64; ++p) {
+        const int q = p + tt - 1;
+        const int row = q < 0 ? 0 : (q >= 64 ? 33 : 1 + (q >> 1));
+        s = fmaf(dys[1 + p], xs[row * 65 + c], s);
+      }
+      dw_acc += s;
+    } else if (tid == 192) {
+      float s = 0.f;
+      for (int p = 0; p < 64; ++p) s += dys[1 + p];
+      dbc_acc += s;
+    }
+  }
+  if (t.part) {
+    float* pp = t.part + (int64_t)blockIdx.x * 196;
+    if (tid < 192) pp[tid] = dw_acc;
+    if (tid == 192) pp[192] = dbc_acc;
+    if (tid == 0) pp[193] = sse_acc;
+  }
+}
+
+// grid = Lo + 1.  block o < Lo: dWo[o][p] = sum_b ddec[b][o] * y[b][p], dbo[o];  last block: partials.
+__global__ void __launch_bounds__(256) dec_tail_reduce_kernel(DecTail t, int ncta, float* dwc, float* dbc, float* dWo,
+                                                              float* dbo, float* sse) {
+  const int o = blockIdx.x, tid = threadIdx.x;
+  if (o < t.Lo) {
+    if (!t.train) return;
+    __shared__ float red[4][64];
+    const int p = tid & 63, bg = tid >> 6;
+    float s = 0.f, sb = 0.f;
+    for (int b = bg; b < t.B; b += 4) {
+      const float g = t.ddec[(int64_t)b * t.Lo + o];
+      s = fmaf(g, t.y[(int64_t)b * 64 + p], s);
+      sb += g;
+    }
+    red[bg][p] = s;
+    __syncthreads();
+    if (bg == 0) dWo[o * 64 + p] = red[0][p] + red[1][p] + red[2][p] + red[3][p];
+    __syncthreads();
+    if (p == 0) red[bg][0] = sb;
+    __syncthreads();
+    if (tid == 0) dbo[o] = red[0][0] + red[1][0] + red[2][0] + red[3][0];
+  } else {
+    for (int i = tid; i < 194; i += 256) {
+      if (i < 193 && !t.train) continue;
+      double s = 0.0;
+      for (int c = 0; c < ncta; ++c) s += (double)t.part[(int64_t)c * 196 + i];
+      if (i < 192)
+        dwc[i] = (float)s;
+      else if (i == 192)
+        dbc[0] = (float)s;
+      else
+        *sse = (float)s;
+    }
+  }
+}
+
+__global__ void loss_finalize_kernel(const float* sse1, const float* sse2, const float* kl_sum, int B, int Lo1, int Lo2,
+                                     float beta, float w1, float w2, int multimodal, float* scalars) {
+  const float mse1 = *sse1 / ((float)B * (float)Lo1);
+  const float mse2 = multimodal ? *sse2 / ((float)B * (float)Lo2) : 0.f;
+  const float kl = *kl_sum / (float)B;
+  const float mse = multimodal ? w1 * mse1 + w2 * mse2 : mse1;
+  scalars[0] = mse + beta * kl;
+  scalars[1] = mse1;
+  scalars[2] = mse2;
+  scalars[3] = kl;
+}
+
+// ------------------------------------------------------------------------------------------------
+// clip_grad_norm_ (torch/nn/utils/clip_grad.py; Lightning gradient_clip_val,
+// reference scripts/train_model_with_multimodal.py:55,701) + torch.optim.AdamW (hippie/model.py:447)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g, int64_t n, float scale,
+                                                    float* __restrict__ partials) {
+  __shared__ float red[8];
+  float s = 0.f;
+  const int64_t n4 = n >> 2;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 v = *reinterpret_cast<const float4*>(g + i * 4);
+    v.x *= scale, v.y *= scale, v.z *= scale, v.w *= scale;
+    s += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+  }
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < 8; ++w) t += red[w];
+    partials[blockIdx.x] = t;
+  }
+}
+
+__global__ void __launch_bounds__(256) clip_coef_kernel(const float* __restrict__ partials, int n, float max_norm,
+                                                        float* __restrict__ scalars) {
+  __shared__ double red[8];
+  double s = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) s += (double)partials[i];
+  s = warp_sum_d(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += red[w];
+    const float norm = (float)sqrt(t);
+    float coef = 1.f;
+    if (max_norm > 0.f) coef = fminf(max_norm / (norm + 1e-6f), 1.f);
+    scalars[4] = norm;
+    scalars[5] = coef;
+  }
+}
+
+__global__ void __launch_bounds__(256) adamw_kernel(AdamArgs a, float decay, float step_size, float bc2_sqrt,
+                                                    float step_size_cls, float bc2_sqrt_cls) {
+  const float coef = a.scalars[5];
+  const float omb1 = 1.f - a.beta1, omb2 = 1.f - a.beta2;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += (int64_t)gridDim.x * blockDim.x) {
+    float ss = step_size, bs = bc2_sqrt;
+    if (i >= a.skip_lo && i < a.skip_hi) {
+      if (!a.has_cls_grad) continue;
+      ss = step_size_cls, bs = bc2_sqrt_cls;
+    }
+    float g = a.g[i] * a.grad_scale;
+    g *= coef;
+    float p = a.p[i] * decay;
+    float m = a.m[i];
+    m = m + omb1 * (g - m);  // lerp_(grad, 1 - beta1)
+    float v = a.v[i] * a.beta2;
+    v = fmaf(omb2 * g, g, v);  // addcmul_(grad, grad, value = 1 - beta2)
+    const float denom = sqrtf(v) / bs + a.eps;
+    p = p - ss * (m / denom);
+    a.p[i] = p, a.m[i] = m, a.v[i] = v;
+  }
+}
+
+// wt[ci][k-1-t][co] = w[co][t][ci]
+__global__ void __launch_bounds__(256) refresh_wt_kernel(const WtEntry* __restrict__ tab,
+                                                         const float* __restrict__ params, float* __restrict__ ws) {
+  __shared__ float tile[32][33];
+  const WtEntry e = tab[blockIdx.z];
+  const int nco = e.cout / 32, nci = e.cin / 32;
+  const int tiles = nco * nci * e.k;
+  for (int tt = blockIdx.x; tt < tiles; tt += gridDim.x) {
+    const int t = tt % e.k, rest = tt / e.k, cit = rest % nci, cot = rest / nci;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8)  // read rows co, contiguous ci
+      tile[r][tx] = params[e.w_off + ((int64_t)(cot * 32 + r) * e.k + t) * e.cin + cit * 32 + tx];
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8)  // write rows ci, contiguous co
+      ws[e.wt_off + ((int64_t)(cit * 32 + r) * e.k + (e.k - 1 - t)) * e.cout + cot * 32 + tx] = tile[tx][r];
+  }
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// launchers
+// ------------------------------------------------------------------------------------------------
+static inline int ew_grid(int64_t work_items, int block = 256) {
+  int64_t g = (work_items + block - 1) / block;
+  if (g > 148 * 8) g = 148 * 8;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+void launch_stem_fwd(const float* x, const float* w, float* c0, float* part, int B, int Lin, int Lout, cudaStream_t s) {
+  int grid = (B * Lout + 127) / 128;
+  stem_fwd_kernel<<<grid, 256, 0, s>>>(x, w, c0, part, B, Lin, Lout);
+}
+int launch_stem_wgrad(const float* x, const float* dc0, float* part, int B, int Lin, int Lout, cudaStream_t s) {
+  int grid = (B * Lout + 127) / 128;
+  stem_wgrad_kernel<<<grid, 256, 0, s>>>(x, dc0, part, B, Lin, Lout);
+  return grid;
+}
+void launch_reduce_partials(const float* part, int nparts, int n, float* out, int accumulate, cudaStream_t s) {
+  reduce_partials_kernel<<<(n + 127) / 128, 128, 0, s>>>(part, nparts, n, out, accumulate);
+}
+void launch_bn_finalize_train(const BnFinalize& f, cudaStream_t s) {
+  bn_finalize_train_kernel<<<(f.C * 32 + 255) / 256, 256, 0, s>>>(f);
+}
+void launch_bn_eval_coefs(const BnEvalEntry* table_dev, int n, const float* params, const float* run_mean,
+                          const float* run_var, float* ws, cudaStream_t s) {
+  bn_eval_coefs_kernel<<<n, 128, 0, s>>>(table_dev, params, run_mean, run_var, ws);
+}
+void launch_bn_apply(const BnApply& a, cudaStream_t s) {
+  int grid = ew_grid((int64_t)a.B * a.L * (a.C / 4));
+  if (!a.r)
+    bn_apply_kernel<0><<<grid, 256, 0, s>>>(a);
+  else if (!a.rcoef)
+    bn_apply_kernel<1><<<grid, 256, 0, s>>>(a);
+  else
+    bn_apply_kernel<2><<<grid, 256, 0, s>>>(a);
+}
+void launch_bn_bwd(const BnBwd& a, int sm_count, cudaStream_t s) {
+  const int M = a.B * a.L;
+  (void)sm_count;
+  int rows = (M + kBnBwdMaxChunks - 1) / kBnBwdMaxChunks;
+  if (rows < 16) rows = 16;
+  const int nchunks = (M + rows - 1) / rows;
+  bn_bwd_reduce_kernel<<<nchunks, 256, 0, s>>>(a, rows);
+  bn_bwd_finalize_kernel<<<(a.C * 32 + 255) / 256, 256, 0, s>>>(a, nchunks);
+  bn_bwd_apply_kernel<<<ew_grid((int64_t)M * (a.C / 4)), 256, 0, s>>>(a);
+}
+void launch_pairsum_acc(const float* src, float* dst, int B, int L, int C, cudaStream_t s) {
+  pairsum_acc_kernel<<<ew_grid((int64_t)B * L * (C / 4)), 256, 0, s>>>(src, dst, B, L, C);
+}
+void launch_pool_linear_fwd(const float* x4, int B, int L, int C, const float* W, const float* bias, int F,
+                            float* pooled, float* h, cudaStream_t s) {
+  pool_linear_fwd_kernel<<<B, 128, C * sizeof(float), s>>>(x4, L, C, W, bias, F, pooled, h);
+}
+void launch_pool_linear_bwd(const float* dh, const float* pooled, const float* W, int B, int L, int C, int F,
+                            float* g_x4, float* dW, float* db, cudaStream_t s) {
+  pool_linear_bwd_x_kernel<<<B, 128, F * sizeof(float), s>>>(dh, W, L, C, F, g_x4);
+  linear_wgrad_rows_kernel<<<F, 256, 0, s>>>(dh, F, pooled, C, B, C, dW, db);
+}
+void launch_dec_linear_fwd(const float* d, int B, int F, const float* W, const float* bias, int C, float* t0,
+                           float* /*t0_up*/, cudaStream_t s) {
+  dec_linear_fwd_kernel<<<B, 256, F * sizeof(float), s>>>(d, F, W, bias, C, t0);
+}
+void launch_dec_linear_bwd(const float* g_t0, const float* d, const float* W, int B, int F, int C, float* gx0,
+                           float* dd, float* dW, float* db, cudaStream_t s) {
+  dec_linear_bwd_x_kernel<<<B, 256, C * sizeof(float), s>>>(g_t0, W, F, C, gx0, dd);
+  // dW[c][f] = sum_b gx0[b][c] * d[b][f];  db[c] = sum_b gx0[b][c]
+  linear_wgrad_rows_kernel<<<C, 128, 0, s>>>(gx0, C, d, F, B, F, dW, db);
+}
+static size_t dec_tail_smem(int Lo) { return (size_t)(34 * 65 + Lo * 65 + 64 + ((Lo + 3) & ~3) + 68 + 192) * sizeof(float); }
+int launch_dec_tail(const DecTail& t, cudaStream_t s) {
+  const int ncta = (t.B + kTailSPB - 1) / kTailSPB;
+  const size_t smem = dec_tail_smem(t.Lo);
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    cudaFuncSetAttribute(dec_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    configured = smem;
+  }
+  dec_tail_kernel<<<ncta, 256, smem, s>>>(t);
+  return ncta;
+}
+void launch_dec_tail_reduce(const DecTail& t, int ncta, float* dwc, float* dbc, float* dWo, float* dbo, float* sse,
+                            cudaStream_t s) {
+  dec_tail_reduce_kernel<<<t.Lo + 1, 256, 0, s>>>(t, ncta, dwc, dbc, dWo, dbo, sse);
+}
+void launch_loss_finalize(const float* sse1, const float* sse2, const float* kl_sum, int B, int Lo1, int Lo2,
+                          float beta, float w1, float w2, int multimodal, float* scalars, cudaStream_t s) {
+  loss_finalize_kernel<<<1, 1, 0, s>>>(sse1, sse2, kl_sum, B, Lo1, Lo2, beta, w1, w2, multimodal, scalars);
+}
+void launch_clip_adamw(const AdamArgs& a, cudaStream_t s) {
+  const int nblk = 1024;
+  sumsq_kernel<<<nblk, 256, 0, s>>>(a.g, a.n, a.grad_scale, a.partials);
+  clip_coef_kernel<<<1, 256, 0, s>>>(a.partials, nblk, a.max_norm, a.scalars);
+  // scalar factors exactly as torch.optim.adam._single_tensor_adam computes them (python doubles -> fp32)
+  const double bc1 = 1.0 - pow((double)a.beta1, (double)a.step), bc2 = 1.0 - pow((double)a.beta2, (double)a.step);
+  const int sc = a.step_cls > 0 ? a.step_cls : 1;
+  const double bc1c = 1.0 - pow((double)a.beta1, (double)sc), bc2c = 1.0 - pow((double)a.beta2, (double)sc);
+  const float decay = (float)(1.0 - (double)a.lr * (double)a.wd);
+  adamw_kernel<<<ew_grid(a.n), 256, 0, s>>>(a, decay, (float)((double)a.lr / bc1), (float)sqrt(bc2),
+                                            (float)((double)a.lr / bc1c), (float)sqrt(bc2c));
+}
+void launch_refresh_wt(const WtEntry* table_dev, int n, const float* params, float* ws, cudaStream_t s) {
+  dim3 grid(64, 1, n);
+  refresh_wt_kernel<<<grid, 256, 0, s>>>(table_dev, params, ws);
+}
+
+}  // namespace hp

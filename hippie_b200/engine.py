@@ -1,0 +1,256 @@
+"""Python owner of the flat device buffers + thin wrapper over the C ABI (include/hippie_b200.h).
+
+PyTorch is plumbing here: it allocates device memory, provides the CUDA stream and (for data
+parallel training) the NCCL all-reduce of the flat gradient buffer.  All arithmetic of the
+cVAE step happens inside libhippie_b200.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import List, Optional, Tuple
+
+import torch
+
+from . import _lib
+
+LAYOUT_NATIVE = 0
+LAYOUT_CONV_OKI = 1
+
+
+@dataclass(frozen=True)
+class ParamInfo:
+    name: str
+    offset: int
+    numel: int
+    shape: Tuple[int, ...]
+    layout: int
+
+
+@dataclass(frozen=True)
+class BnInfo:
+    name: str
+    offset: int
+    channels: int
+    index: int
+
+
+@dataclass(frozen=True)
+class TensorInfo:
+    name: str
+    offset: int
+    L: int
+    C: int
+    pad: int
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+class Engine:
+    """One handle per (process, device).  `Engine(...)` only builds the layout (no CUDA needed);
+    `allocate(device)` creates the flat buffers on the GPU and binds them."""
+
+    def __init__(self, z_dim: int, len_wave: int = 50, len_isi: int = 100, class_hidden_dim: int = 5,
+                 num_sources: int = 5, num_classes: int = 5, multimodal: bool = True, max_batch: int = 512,
+                 inference_only: bool = False, conv_path: int = 0):
+        self._L = _lib.lib()
+        self.cfg = _lib.HippieCfg(z_dim, class_hidden_dim, num_sources, num_classes, len_wave, len_isi,
+                                  1 if multimodal else 0, max_batch, 1 if inference_only else 0, conv_path)
+        self._h = C.c_void_p()
+        rc = self._L.hippie_create(C.byref(self.cfg), C.byref(self._h))
+        if rc != 0:
+            raise ValueError(f"hippie_create failed ({rc}): invalid configuration")
+        self.z_dim, self.multimodal, self.max_batch, self.inference_only = z_dim, multimodal, max_batch, inference_only
+        self.len_wave, self.len_isi = len_wave, len_isi
+        self.param_floats = int(self._L.hippie_param_floats(self._h))
+        self.bn_floats = int(self._L.hippie_bn_floats(self._h))
+        self.workspace_bytes = int(self._L.hippie_workspace_bytes(self._h))
+        self.params: List[ParamInfo] = []
+        name = C.create_string_buffer(256)
+        off, numel, ndim, layout = C.c_int64(), C.c_int64(), C.c_int32(), C.c_int32()
+        shape = (C.c_int64 * 3)()
+        for i in range(self._L.hippie_num_params(self._h)):
+            self._L.hippie_param_info(self._h, i, name, 256, C.byref(off), C.byref(numel), C.byref(ndim), shape,
+                                      C.byref(layout))
+            self.params.append(ParamInfo(name.value.decode(), off.value, numel.value,
+                                         tuple(int(shape[k]) for k in range(ndim.value)), layout.value))
+        self.bns: List[BnInfo] = []
+        ch = C.c_int64()
+        for i in range(self._L.hippie_num_bn(self._h)):
+            self._L.hippie_bn_info(self._h, i, name, 256, C.byref(off), C.byref(ch))
+            self.bns.append(BnInfo(name.value.decode(), off.value, ch.value, i))
+        self.tensors: List[TensorInfo] = []
+        tl, tc, tp = C.c_int32(), C.c_int32(), C.c_int32()
+        for i in range(self._L.hippie_num_tensors(self._h)):
+            self._L.hippie_tensor_info(self._h, i, name, 256, C.byref(off), C.byref(tl), C.byref(tc), C.byref(tp))
+            self.tensors.append(TensorInfo(name.value.decode(), off.value, tl.value, tc.value, tp.value))
+        self.device: Optional[torch.device] = None
+        self.flat_params = self.flat_grads = self.exp_avg = self.exp_avg_sq = None
+        self.bn_mean = self.bn_var = self.bn_count = self.workspace = None
+
+    # ------------------------------------------------------------------------------------------
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None) is not None and self._h.value:
+                self._L.hippie_destroy(self._h)
+                self._h = C.c_void_p()
+        except Exception:
+            pass
+
+    def _check(self, rc: int):
+        if rc != 0:
+            msg = self._L.hippie_last_error(self._h)
+            raise RuntimeError(f"libhippie_b200 error {rc}: {msg.decode() if msg else ''}")
+
+    @staticmethod
+    def _stream() -> C.c_void_p:
+        return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    # ------------------------------------------------------------------------------------------
+    def allocate(self, device="cuda:0"):
+        """Creates the flat fp32 buffers (params | grads | exp_avg | exp_avg_sq), BatchNorm buffers and the
+        workspace on `device` and hands them to the engine (hippie_bind)."""
+        device = torch.device(device)
+        if device.type != "cuda" or not torch.cuda.is_available():
+            raise RuntimeError("hippie_b200 runs on CUDA (sm_100a) only; there is no CPU fallback")
+        self.device = device
+        with torch.cuda.device(device):
+            n = self.param_floats
+            self.flat_params = torch.zeros(n, dtype=torch.float32, device=device)
+            if not self.inference_only:
+                self.flat_grads = torch.zeros(n, dtype=torch.float32, device=device)
+                self.exp_avg = torch.zeros(n, dtype=torch.float32, device=device)
+                self.exp_avg_sq = torch.zeros(n, dtype=torch.float32, device=device)
+            self.bn_mean = torch.zeros(self.bn_floats, dtype=torch.float32, device=device)
+            self.bn_var = torch.ones(self.bn_floats, dtype=torch.float32, device=device)
+            self.bn_count = torch.zeros(len(self.bns), dtype=torch.int64, device=device)
+            self.workspace = torch.empty(self.workspace_bytes, dtype=torch.uint8, device=device)
+            self._check(self._L.hippie_bind(self._h, _ptr(self.flat_params), _ptr(self.flat_grads), _ptr(self.exp_avg),
+                                            _ptr(self.exp_avg_sq), _ptr(self.bn_mean), _ptr(self.bn_var),
+                                            _ptr(self.bn_count), _ptr(self.workspace), self.workspace_bytes,
+                                            self._stream()))
+        return self
+
+    # ---- views ---------------------------------------------------------------------------------
+    @staticmethod
+    def view_of(flat: torch.Tensor, p: ParamInfo) -> torch.Tensor:
+        """The torch-shaped view of one parameter inside a flat buffer.  Conv1d weights are stored
+        [Cout][k][Cin] (channels-last GEMM operand); the view is permuted back to torch's [Cout][Cin][k]."""
+        t = flat[p.offset:p.offset + p.numel]
+        if p.layout == LAYOUT_CONV_OKI:
+            co, ci, k = p.shape
+            return t.view(co, k, ci).permute(0, 2, 1)
+        return t.view(p.shape)
+
+    def tensor_view(self, name: str, B: int) -> torch.Tensor:
+        """[B, C, L] view (torch layout) of a named activation / gradient tensor in the workspace."""
+        ti = next(t for t in self.tensors if t.name == name)
+        ws = self.workspace.view(torch.float32)
+        rows = ti.L + 2 * ti.pad
+        t = ws[ti.offset:ti.offset + B * rows * ti.C].view(B, rows, ti.C)
+        return t[:, ti.pad:ti.pad + ti.L, :].permute(0, 2, 1)
+
+    # ---- calls ---------------------------------------------------------------------------------
+    def _io(self, x1, x2, src, cls, eps, B):
+        assert x1.dtype == torch.float32 and x1.is_contiguous() and x1.is_cuda
+        assert src.dtype == torch.int64 and src.is_contiguous()
+        if self.multimodal:
+            assert x2 is not None and x2.dtype == torch.float32 and x2.is_contiguous()
+            assert x2.numel() == B * self.len_isi
+        assert x1.numel() == B * self.len_wave
+        if cls is not None:
+            assert cls.dtype == torch.int64 and cls.is_contiguous()
+        if eps is not None:
+            assert eps.dtype == torch.float32 and eps.is_contiguous() and eps.numel() == B * self.z_dim
+
+    def train_fwd_bwd(self, x1, x2, src, cls, eps, beta: float, w1: float = 1.0, w2: float = 1.0, scalars=None,
+                      outputs: bool = False):
+        """training_step + zero_grad + backward.  Returns (scalars[8] device tensor, outputs dict or None)."""
+        B = x1.shape[0]
+        self._io(x1, x2, src, cls, eps, B)
+        if scalars is None:
+            scalars = torch.zeros(8, dtype=torch.float32, device=self.device)
+        outs = self._out_buffers(B) if outputs else {}
+        self._check(self._L.hippie_train_fwd_bwd(
+            self._h, _ptr(x1), _ptr(x2), _ptr(src), _ptr(cls), _ptr(eps), B, beta, w1, w2, _ptr(scalars),
+            _ptr(outs.get("enc")), _ptr(outs.get("mu")), _ptr(outs.get("logvar")), _ptr(outs.get("dec1")),
+            _ptr(outs.get("dec2")), self._stream()))
+        return scalars, (outs if outputs else None)
+
+    def eval_forward(self, x1, x2, src, cls, eps, beta: float = 1.0, w1: float = 1.0, w2: float = 1.0, scalars=None):
+        B = x1.shape[0]
+        self._io(x1, x2, src, cls, eps, B)
+        outs = self._out_buffers(B)
+        self._check(self._L.hippie_eval_forward(
+            self._h, _ptr(x1), _ptr(x2), _ptr(src), _ptr(cls), _ptr(eps), B, beta, w1, w2, _ptr(scalars),
+            _ptr(outs.get("enc")), _ptr(outs.get("mu")), _ptr(outs.get("logvar")), _ptr(outs.get("dec1")),
+            _ptr(outs.get("dec2")), self._stream()))
+        return outs
+
+    def embed(self, x1, x2, src, cls=None, zscore_ddof: int = -1, out=None):
+        B = x1.shape[0]
+        self._io(x1, x2, src, cls, None, B)
+        z = self.z_dim
+        if out is None:
+            out = {k: torch.empty(B, z, dtype=torch.float32, device=self.device) for k in ("enc", "mu", "logvar")}
+        self._check(self._L.hippie_embed(self._h, _ptr(x1), _ptr(x2), _ptr(src), _ptr(cls), B, zscore_ddof,
+                                         _ptr(out["enc"]), _ptr(out["mu"]), _ptr(out["logvar"]), self._stream()))
+        return out
+
+    def clip_adamw(self, lr: float, weight_decay: float, step: int, max_norm: Optional[float] = None,
+                   grad_scale: float = 1.0, betas=(0.9, 0.999), eps: float = 1e-8, step_cls: int = 0,
+                   has_cls_grad: bool = False, scalars=None):
+        if scalars is None:
+            scalars = torch.zeros(8, dtype=torch.float32, device=self.device)
+        self._check(self._L.hippie_clip_adamw(self._h, lr, betas[0], betas[1], eps, weight_decay,
+                                              -1.0 if max_norm is None else float(max_norm), grad_scale, step, step_cls,
+                                              1 if has_cls_grad else 0, _ptr(scalars), self._stream()))
+        return scalars
+
+    def last_launch_count(self) -> int:
+        return int(self._L.hippie_last_launch_count(self._h))
+
+    def _out_buffers(self, B):
+        z, dev = self.z_dim, self.device
+        o = {k: torch.empty(B, z, dtype=torch.float32, device=dev) for k in ("enc", "mu", "logvar")}
+        o["dec1"] = torch.empty(B, 1, self.len_wave, dtype=torch.float32, device=dev)
+        if self.multimodal:
+            o["dec2"] = torch.empty(B, 1, self.len_isi, dtype=torch.float32, device=dev)
+        return o
+
+    # ---- state exchange (used by the nn.Module mirror and the tests) ---------------------------
+    def load_named(self, state: dict, strict: bool = True):
+        """Copies a {reference state_dict key: tensor} mapping into the flat buffers."""
+        missing = []
+        with torch.no_grad():
+            for p in self.params:
+                if p.name in state:
+                    self.view_of(self.flat_params, p).copy_(state[p.name].to(self.device, torch.float32))
+                else:
+                    missing.append(p.name)
+            for b in self.bns:
+                for key, buf in ((".running_mean", self.bn_mean), (".running_var", self.bn_var)):
+                    if b.name + key in state:
+                        buf[b.offset:b.offset + b.channels].copy_(state[b.name + key].to(self.device, torch.float32))
+                    else:
+                        missing.append(b.name + key)
+                if b.name + ".num_batches_tracked" in state:
+                    self.bn_count[b.index] = int(state[b.name + ".num_batches_tracked"])
+        if strict and missing:
+            raise KeyError(f"missing keys: {missing[:5]}{'...' if len(missing) > 5 else ''}")
+        return missing
+
+    def named_state(self) -> dict:
+        out = {}
+        for p in self.params:
+            out[p.name] = self.view_of(self.flat_params, p)
+        for b in self.bns:
+            out[b.name + ".running_mean"] = self.bn_mean[b.offset:b.offset + b.channels]
+            out[b.name + ".running_var"] = self.bn_var[b.offset:b.offset + b.channels]
+            out[b.name + ".num_batches_tracked"] = self.bn_count[b.index]
+        return out
+
+    def named_grads(self) -> dict:
+        return {p.name: self.view_of(self.flat_grads, p) for p in self.params}

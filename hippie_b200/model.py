@@ -1,0 +1,468 @@
+"""Drop-in mirror of the reference's `hippie/model.py` on top of the sm_100a engine.
+
+Same class names, constructor signatures, `forward` / `training_step` / `validation_step` contracts and
+`state_dict()` keys as the reference (hippie/model.py:12-72, 75-162, 350-432, 434-533); the arithmetic
+is done by libhippie_b200.so.  Parameters and BatchNorm buffers are views into the engine's flat fp32
+buffers, so `state_dict()` / `load_state_dict()` / `.ckpt` interchange keep working unchanged.
+
+There is no CPU fallback: the classes can be constructed, saved and loaded on the CPU, but any
+forward / training call requires the model to be on a CUDA device.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional
+
+import torch
+import torch.nn as nn
+
+from .engine import Engine, LAYOUT_CONV_OKI
+
+
+class _Node(nn.Module):
+    """Anonymous container used to reproduce the reference's module tree (and hence its state_dict keys)."""
+
+
+def _init_like_reference(p, flat_cpu: torch.Tensor):
+    """torch's default initialisers in the reference's construction order (== engine param order), drawn on the
+    CPU generator exactly like nn.Conv1d / nn.Linear / nn.Embedding / nn.BatchNorm1d do, so that after
+    `torch.manual_seed(s)` the values equal the reference model's bit for bit (scripts/
+    train_model_with_multimodal.py:78,663).  Returns nothing; writes into the flat buffer."""
+    raise NotImplementedError
+
+
+class _EngineModule(nn.Module):
+    """Base of MultiModalCVAE / hippieUnimodalCVAE: owns the Engine and the flat buffers."""
+
+    def __init__(self, *, z_dim, len_wave, len_isi, class_hidden_dim, num_sources, num_classes, multimodal,
+                 max_batch=512):
+        super().__init__()
+        self.z_dim = z_dim
+        self.class_hidden_dim = class_hidden_dim
+        self.num_sources = num_sources
+        self.num_classes = num_classes
+        self._max_batch = max_batch
+        self._cfg = dict(z_dim=z_dim, len_wave=len_wave, len_isi=len_isi, class_hidden_dim=class_hidden_dim,
+                         num_sources=num_sources, num_classes=num_classes, multimodal=multimodal)
+        object.__setattr__(self, "_engine", Engine(max_batch=max_batch, **self._cfg))
+        eng = self._engine
+        # CPU-resident flat storage until the module is moved to a CUDA device
+        self._flat = {
+            "params": torch.zeros(eng.param_floats),
+            "bn_mean": torch.zeros(eng.bn_floats),
+            "bn_var": torch.ones(eng.bn_floats),
+            "bn_count": torch.zeros(len(eng.bns), dtype=torch.int64),
+        }
+        self._param_objs = {}
+        self._build_tree()
+        self._reset_parameters()
+
+    # ---- module tree ---------------------------------------------------------------------------------
+    def _node(self, dotted: str) -> nn.Module:
+        m = self
+        for part in dotted.split("."):
+            if part not in m._modules:
+                m.add_module(part, _Node())
+            m = m._modules[part]
+        return m
+
+    def _build_tree(self):
+        eng = self._engine
+        bn_by_name = {b.name: b for b in eng.bns}
+        for p in eng.params:
+            mod_name, leaf = p.name.rsplit(".", 1)
+            node = self._node(mod_name)
+            param = nn.Parameter(Engine.view_of(self._flat["params"], p))
+            node.register_parameter(leaf, param)
+            self._param_objs[p.name] = param
+            if leaf == "bias" and mod_name in bn_by_name:  # BatchNorm: buffers follow weight, bias
+                b = bn_by_name[mod_name]
+                node.register_buffer("running_mean", self._flat["bn_mean"][b.offset:b.offset + b.channels])
+                node.register_buffer("running_var", self._flat["bn_var"][b.offset:b.offset + b.channels])
+                node.register_buffer("num_batches_tracked", self._flat["bn_count"][b.index])
+
+    def _rebind(self):
+        """Points every nn.Parameter / buffer at the current flat storage (after a device move)."""
+        eng = self._engine
+        for p in eng.params:
+            param = self._param_objs[p.name]
+            param.data = Engine.view_of(self._flat["params"], p)
+            param.grad = None
+        for b in eng.bns:
+            node = self._node(b.name)
+            node._buffers["running_mean"] = self._flat["bn_mean"][b.offset:b.offset + b.channels]
+            node._buffers["running_var"] = self._flat["bn_var"][b.offset:b.offset + b.channels]
+            node._buffers["num_batches_tracked"] = self._flat["bn_count"][b.index]
+
+    def _attach_grads(self):
+        """Exposes the engine's flat gradient buffer as `.grad` views (what loss.backward() fills in torch)."""
+        eng = self._engine
+        if eng.flat_grads is None:
+            return
+        for p in eng.params:
+            self._param_objs[p.name].grad = Engine.view_of(eng.flat_grads, p)
+
+    def _reset_parameters(self):
+        """nn.Conv1d / nn.Linear: kaiming_uniform_(a=sqrt(5)) weights, U(+-1/sqrt(fan_in)) biases;
+        nn.Embedding: N(0,1); nn.BatchNorm1d: ones / zeros -- drawn in construction order on the CPU
+        generator, as the reference does when it builds the model right after torch.manual_seed(42)."""
+        eng = self._engine
+        bn_names = {b.name for b in eng.bns}
+        fan_in_of = {}
+        with torch.no_grad():
+            for p in eng.params:
+                mod_name, leaf = p.name.rsplit(".", 1)
+                view = Engine.view_of(self._flat["params"], p)
+                if mod_name in bn_names:
+                    view.fill_(1.0 if leaf == "weight" else 0.0)
+                elif mod_name.endswith("_embedding"):
+                    view.copy_(torch.empty(p.shape).normal_())
+                elif leaf == "weight":
+                    fan_in = p.shape[1] * (p.shape[2] if len(p.shape) == 3 else 1)
+                    fan_in_of[mod_name] = fan_in
+                    gain = math.sqrt(2.0 / (1 + math.sqrt(5) ** 2))
+                    bound = math.sqrt(3.0) * gain / math.sqrt(fan_in)
+                    view.copy_(torch.empty(p.shape).uniform_(-bound, bound))
+                else:
+                    bound = 1 / math.sqrt(fan_in_of[mod_name])
+                    view.copy_(torch.empty(p.shape).uniform_(-bound, bound))
+
+    # ---- device moves ----------------------------------------------------------------------------------
+    def _apply(self, fn, recurse=True):
+        probe = fn(torch.zeros(1, dtype=torch.float32, device=self._flat["params"].device))
+        if probe.dtype != torch.float32:
+            raise TypeError("hippie_b200 models are fp32 only (the reference trains in fp32)")
+        if probe.device == self._flat["params"].device:
+            return self
+        eng = self._engine
+        if probe.device.type == "cuda":
+            old = self._flat
+            eng.allocate(probe.device)
+            eng.flat_params.copy_(old["params"])
+            eng.bn_mean.copy_(old["bn_mean"])
+            eng.bn_var.copy_(old["bn_var"])
+            eng.bn_count.copy_(old["bn_count"])
+            self._flat = {"params": eng.flat_params, "bn_mean": eng.bn_mean, "bn_var": eng.bn_var,
+                          "bn_count": eng.bn_count}
+        else:
+            self._flat = {k: v.detach().to(probe.device).clone() for k, v in self._flat.items()}
+        self._rebind()
+        return self
+
+    @property
+    def engine(self) -> Engine:
+        return self._engine
+
+    @property
+    def on_cuda(self) -> bool:
+        return self._flat["params"].is_cuda
+
+    def _require_cuda(self):
+        if not self.on_cuda:
+            raise RuntimeError("hippie_b200 has no CPU path: move the model to a CUDA device (model.to('cuda'))")
+
+    def _prep(self, data, n):
+        dev = self._flat["params"].device
+        data = data.to(dev, torch.float32, non_blocking=True).contiguous()
+        if data.shape[0] > self._max_batch:
+            raise ValueError(f"batch {data.shape[0]} exceeds max_batch={self._max_batch} this model was built with")
+        assert data.numel() == data.shape[0] * n, f"expected [B,1,{n}] input, got {tuple(data.shape)}"
+        return data
+
+    def _labels(self, t):
+        return None if t is None else t.to(self._flat["params"].device, torch.int64, non_blocking=True).contiguous()
+
+    def reparameterize(self, mu, logvar):
+        """reference hippie/model.py:397-400 (host-side convenience; the engine fuses this step)."""
+        std = torch.exp(0.5 * logvar)
+        return mu + torch.randn_like(std) * std
+
+    def _draw_eps(self, B):
+        # the reference draws randn_like(std) from the default generator of the tensor's device (hippie/model.py:399)
+        return torch.randn(B, self.z_dim, device=self._flat["params"].device, dtype=torch.float32)
+
+    def _forward_impl(self, x1, x2, source_labels, class_labels, eps=None):
+        self._require_cuda()
+        eng = self._engine
+        src, cls = self._labels(source_labels), self._labels(class_labels)
+        B = x1.shape[0]
+        if eps is None:
+            eps = self._draw_eps(B)
+        if self.training:
+            outs = eng.train_forward(x1, x2, src, cls, eps)
+        else:
+            outs = eng.eval_forward(x1, x2, src, cls, eps)
+        return outs
+
+
+class MultiModalCVAE(_EngineModule):
+    """reference hippie/model.py:350-432."""
+
+    def __init__(self, z_dim, output_size_wave, output_size_isi, class_hidden_dim, num_sources, num_classes,
+                 max_batch=512):
+        super().__init__(z_dim=z_dim, len_wave=output_size_wave, len_isi=output_size_isi,
+                         class_hidden_dim=class_hidden_dim, num_sources=num_sources, num_classes=num_classes,
+                         multimodal=True, max_batch=max_batch)
+        self.output_size_wave, self.output_size_isi = output_size_wave, output_size_isi
+
+    def forward(self, data1, data2, source_labels, class_labels=None, eps=None):
+        x1, x2 = self._prep(data1, self.output_size_wave), self._prep(data2, self.output_size_isi)
+        o = self._forward_impl(x1, x2, source_labels, class_labels, eps)
+        return o["enc"], o["mu"], o["logvar"], o["dec1"], o["dec2"]
+
+    def embed(self, data1, data2, source_labels, class_labels=None, zscore_ddof=-1):
+        """Encoders + fusion only (get_embeddings_multimodal's `model(sample)[0]`, scripts/
+        train_model_with_multimodal.py:22-34, without running the two decoders the reference discards)."""
+        self._require_cuda()
+        x1, x2 = self._prep(data1, self.output_size_wave), self._prep(data2, self.output_size_isi)
+        return self._engine.embed(x1, x2, self._labels(source_labels), self._labels(class_labels), zscore_ddof)
+
+
+class hippieUnimodalCVAE(_EngineModule):
+    """reference hippie/model.py:12-72."""
+
+    def __init__(self, z_dim, output_size, class_hidden_dim, num_sources, num_classes, max_batch=512):
+        super().__init__(z_dim=z_dim, len_wave=output_size, len_isi=output_size, class_hidden_dim=class_hidden_dim,
+                         num_sources=num_sources, num_classes=num_classes, multimodal=False, max_batch=max_batch)
+        self.output_size = output_size
+
+    def forward(self, data, source_labels, class_labels=None, eps=None):
+        x = self._prep(data, self.output_size)
+        o = self._forward_impl(x, None, source_labels, class_labels, eps)
+        return o["enc"], o["mu"], o["logvar"], o["dec1"]
+
+    def embed(self, data, source_labels, class_labels=None, zscore_ddof=-1):
+        self._require_cuda()
+        x = self._prep(data, self.output_size)
+        return self._engine.embed(x, None, self._labels(source_labels), self._labels(class_labels), zscore_ddof)
+
+
+# ------------------------------------------------------------------------------------------------------
+class FusedAdamW(torch.optim.Optimizer):
+    """torch.optim.AdamW (reference hippie/model.py:447) fused with Lightning's gradient clipping
+    (scripts/train_model_with_multimodal.py:55,701) over the engine's flat buffers: one reduction + one
+    update launch instead of 285 per-tensor ops.  `state_dict()` keeps torch's AdamW format."""
+
+    def __init__(self, model: _EngineModule, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2):
+        self._model = model
+        super().__init__(list(model.parameters()), dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay,
+                                                        amsgrad=False, maximize=False, foreach=None, capturable=False,
+                                                        differentiable=False, fused=None))
+        self._step = 0
+        self._step_cls = 0
+        self.has_cls_grad = False
+        self.last_scalars = None
+
+    @torch.no_grad()
+    def step(self, closure=None, max_norm: Optional[float] = None, grad_scale: float = 1.0):
+        loss = closure() if closure is not None else None
+        self._model._require_cuda()
+        g = self.param_groups[0]
+        self._step += 1
+        if self.has_cls_grad:
+            self._step_cls += 1
+        self.last_scalars = self._model.engine.clip_adamw(
+            g["lr"], g["weight_decay"], self._step, max_norm=max_norm, grad_scale=grad_scale, betas=g["betas"],
+            eps=g["eps"], step_cls=max(self._step_cls, 1), has_cls_grad=self.has_cls_grad)
+        return loss
+
+    def zero_grad(self, set_to_none: bool = True):
+        pass  # the engine zero-fills the flat gradient buffer at the start of every train_fwd_bwd
+
+    def state_dict(self):
+        eng = self._model.engine
+        state = {}
+        if self._step > 0 and eng.exp_avg is not None:
+            for i, p in enumerate(eng.params):
+                is_cls = p.name == "class_embedding.weight"
+                st = self._step_cls if is_cls else self._step
+                if st == 0:
+                    continue
+                state[i] = {"step": torch.tensor(float(st)),
+                            "exp_avg": Engine.view_of(eng.exp_avg, p).detach().clone(),
+                            "exp_avg_sq": Engine.view_of(eng.exp_avg_sq, p).detach().clone()}
+        groups = [{k: v for k, v in self.param_groups[0].items() if k != "params"}]
+        groups[0]["params"] = list(range(len(eng.params)))
+        return {"state": state, "param_groups": groups}
+
+    def load_state_dict(self, sd):
+        eng = self._model.engine
+        self._model._require_cuda()
+        g = sd["param_groups"][0]
+        for k in ("lr", "betas", "eps", "weight_decay"):
+            if k in g:
+                self.param_groups[0][k] = g[k]
+        self._step = self._step_cls = 0
+        with torch.no_grad():
+            eng.exp_avg.zero_(), eng.exp_avg_sq.zero_()
+            for i, st in sd["state"].items():
+                p = eng.params[int(i)]
+                Engine.view_of(eng.exp_avg, p).copy_(st["exp_avg"])
+                Engine.view_of(eng.exp_avg_sq, p).copy_(st["exp_avg_sq"])
+                if p.name == "class_embedding.weight":
+                    self._step_cls = int(st["step"])
+                else:
+                    self._step = max(self._step, int(st["step"]))
+
+
+class _TrainModuleBase(nn.Module):
+    """What the reference inherits from pl.LightningModule, reduced to what its scripts use."""
+    _SCALAR_RING = 4096
+
+    def __init__(self, base_model, alpha_max, learning_rate, weight_decay, beta):
+        super().__init__()
+        self.model = base_model
+        self.lr = learning_rate
+        self.weight_decay = weight_decay
+        self.alpha_max = alpha_max
+        self.beta = beta
+        self.val_loss = []
+        self.train_loss = []
+        self.optimizer = FusedAdamW(self.model, lr=self.lr, weight_decay=self.weight_decay)
+        self.logged = {}
+        self.current_epoch = 0
+        self.global_step = 0
+        self._ring = None
+        self._ring_pos = 0
+        self.world_size = 1  # set by the data-parallel trainer
+
+    def log(self, name, value, *a, **k):
+        self.logged[name] = value
+
+    def configure_optimizers(self):
+        return self.optimizer
+
+    def _scalars(self):
+        dev = self.model._flat["params"].device
+        if self._ring is None or self._ring.device != dev:
+            self._ring = torch.zeros(self._SCALAR_RING, 8, dtype=torch.float32, device=dev)
+        s = self._ring[self._ring_pos]
+        self._ring_pos = (self._ring_pos + 1) % self._SCALAR_RING
+        return s
+
+    @staticmethod
+    def _mean(vals):
+        if not vals:
+            return float("nan")
+        if isinstance(vals[0], torch.Tensor):
+            return torch.stack([v.detach().float() for v in vals]).mean().item()  # one sync per epoch
+        return sum(vals) / len(vals)
+
+    def on_validation_epoch_end(self):
+        avg_loss = self._mean(self.val_loss)
+        print(f"Average validation loss is {avg_loss:.2f}")
+        self.val_loss = []
+        return avg_loss
+
+    def on_train_epoch_end(self):
+        avg_loss = self._mean(self.train_loss)
+        print(f"Average training loss is {avg_loss:.2f}")
+        self.train_loss = []
+        return avg_loss
+
+    @staticmethod
+    def _split_labels(labels):
+        # reference hippie/model.py:456-462: labels [B,2] = [class, source]; [B] = source only
+        if labels.ndim == 2:
+            class_labels, source_labels = labels.unbind(1)
+            return source_labels, class_labels
+        return labels, None
+
+
+class MultiModalCVAETrainModule(_TrainModuleBase):
+    """reference hippie/model.py:434-533."""
+
+    def __init__(self, base_model, alpha_max=0.5, learning_rate=0.01, weight_decay=0.01, beta=1, mod1_weight=1.0,
+                 mod2_weight=1.0):
+        super().__init__(base_model, alpha_max, learning_rate, weight_decay, beta)
+        self.mod1_weight = mod1_weight
+        self.mod2_weight = mod2_weight
+
+    def training_step(self, batch, batch_idx, eps=None):
+        """forward + loss + backward in one fused engine call.  Returns the 0-dim total loss (device tensor);
+        gradients are in the engine's flat buffer (exposed as `.grad` views).  Unlike the reference
+        (`.item()` every step, hippie/model.py:480) nothing here synchronises with the host."""
+        m = self.model
+        m._require_cuda()
+        data1, data2, labels = batch
+        x1, x2 = m._prep(data1, m.output_size_wave), m._prep(data2, m.output_size_isi)
+        src, cls = self._split_labels(m._labels(labels))
+        src = src.contiguous()
+        cls = cls.contiguous() if cls is not None else None
+        if eps is None:
+            eps = m._draw_eps(x1.shape[0])
+        s = self._scalars()
+        m.engine.train_fwd_bwd(x1, x2, src, cls, eps, float(self.beta), float(self.mod1_weight),
+                               float(self.mod2_weight), scalars=s)
+        self.optimizer.has_cls_grad = cls is not None
+        self.log("train_loss", s[0]), self.log("train_mse_loss1", s[1])
+        self.log("train_mse_loss2", s[2]), self.log("train_kl_loss", s[3])
+        self.train_loss.append(s[0])
+        self.global_step += 1
+        return s[0]
+
+    def validation_step(self, batch, batch_idx, eps=None):
+        m = self.model
+        m._require_cuda()
+        data1, data2, labels = batch
+        x1, x2 = m._prep(data1, m.output_size_wave), m._prep(data2, m.output_size_isi)
+        src, cls = self._split_labels(m._labels(labels))
+        src = src.contiguous()
+        cls = cls.contiguous() if cls is not None else None
+        if eps is None:
+            eps = m._draw_eps(x1.shape[0])
+        s = self._scalars()
+        m.engine.eval_forward(x1, x2, src, cls, eps, float(self.beta), float(self.mod1_weight),
+                              float(self.mod2_weight), scalars=s)
+        self.val_loss.append(s[0])
+        self.log("val_loss", s[0]), self.log("val_mse_loss1", s[1])
+        self.log("val_mse_loss2", s[2]), self.log("val_kl_loss", s[3])
+        return s[0]
+
+    def forward(self, batch):
+        data1, data2, labels = batch
+        src, cls = self._split_labels(labels)
+        return self.model(data1, data2, source_labels=src, class_labels=cls)
+
+
+class hippieUnimodalEmbeddingModelCVAE(_TrainModuleBase):
+    """reference hippie/model.py:75-162."""
+
+    def __init__(self, base_model, alpha_max=0.5, learning_rate=0.01, weight_decay=0.01, beta=1):
+        super().__init__(base_model, alpha_max, learning_rate, weight_decay, beta)
+
+    def _step(self, batch, train, eps):
+        m = self.model
+        m._require_cuda()
+        data, labels = batch
+        x = m._prep(data, m.output_size)
+        src, cls = self._split_labels(m._labels(labels))
+        src = src.contiguous()
+        cls = cls.contiguous() if cls is not None else None
+        if eps is None:
+            eps = m._draw_eps(x.shape[0])
+        s = self._scalars()
+        if train:
+            m.engine.train_fwd_bwd(x, None, src, cls, eps, float(self.beta), 1.0, 1.0, scalars=s)
+            self.optimizer.has_cls_grad = cls is not None
+        else:
+            m.engine.eval_forward(x, None, src, cls, eps, float(self.beta), 1.0, 1.0, scalars=s)
+        return s
+
+    def training_step(self, batch, batch_idx, eps=None):
+        s = self._step(batch, True, eps)
+        self.log("train_loss", s[0]), self.log("train_mse_loss", s[1]), self.log("train_kl_loss", s[3])
+        self.train_loss.append(s[0])
+        self.global_step += 1
+        return s[0]
+
+    def validation_step(self, batch, batch_idx, eps=None):
+        s = self._step(batch, False, eps)
+        self.val_loss.append(s[0])
+        self.log("val_loss", s[0]), self.log("val_mse_loss", s[1]), self.log("val_kl_loss", s[3])
+        return s[0]
+
+    def forward(self, batch):
+        data, labels = batch
+        src, cls = self._split_labels(labels)
+        return self.model(data, source_labels=src, class_labels=cls)

@@ -1,0 +1,139 @@
+/*
+ * hippie_b200.h -- C ABI of libhippie_b200.so, the sm_100a engine behind HIPPIE's cVAE hot path.
+ *
+ * The reference (aghatpande/HIPPIE) has no native code and no FFI: its hot path is the Python
+ * call chain  MultiModalCVAETrainModule.training_step -> MultiModalCVAE.forward -> ResNet18Enc /
+ * ResNet18Dec -> torch ATen, followed by Lightning's clip_grad_norm_ and torch.optim.AdamW.step.
+ * Each entry point below replaces one link of that chain; the reference interface it stands in
+ * for is cited as /root/reference/<file>:<line>.  INTEGRATION.md shows the ctypes binding a
+ * maintainer of the reference would add.
+ *
+ * Conventions
+ *   - plain C: pointers, sizes and PODs only; no torch types.  All tensor pointers are DEVICE
+ *     pointers owned by the caller (PyTorch); the engine never allocates, frees or resizes them.
+ *   - every launch goes to the caller-supplied `stream` (a cudaStream_t passed as void*); two
+ *     internal side streams are forked from / joined to it with events, so the whole call is
+ *     CUDA-graph capturable.  No hidden host syncs, no host reads of device data.
+ *   - return value: 0 = ok, <0 = argument/config error, >0 = cudaError_t.  hippie_last_error()
+ *     returns a message for the most recent non-zero return of that handle.
+ *   - one handle per (process, device); not thread-safe.
+ *   - activations live in the caller's workspace as channels-last rows [B][L+2][C] with one zero
+ *     row on either side of every sample (DESIGN.md "Data layout in HBM").
+ */
+#ifndef HIPPIE_B200_H
+#define HIPPIE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default) /* the library is built with -fvisibility=hidden */
+#endif
+
+typedef struct hippie_engine* hippie_handle;
+
+/* Constructor arguments of MultiModalCVAE (hippie/model.py:352) / hippieUnimodalCVAE (:13). */
+typedef struct hippie_cfg {
+  int32_t z_dim;
+  int32_t class_hidden_dim;
+  int32_t num_sources;
+  int32_t num_classes;
+  int32_t len_wave;   /* output_size_wave (50); the single output_size when unimodal          */
+  int32_t len_isi;    /* output_size_isi (100); ignored when unimodal                          */
+  int32_t multimodal; /* 1 = MultiModalCVAE, 0 = hippieUnimodalCVAE                             */
+  int32_t max_batch;  /* largest B any call will pass; sizes the workspace                      */
+  int32_t inference_only; /* 1 = no gradient tensors in the workspace (embedding engines)      */
+  int32_t conv_path;  /* 0 = auto (tcgen05 where available), 1 = force the FP32 CUDA-core GEMM  */
+} hippie_cfg;
+
+/* Layout kinds of a parameter inside the flat buffer. */
+enum {
+  HIPPIE_LAYOUT_NATIVE = 0,  /* same element order as the torch tensor                          */
+  HIPPIE_LAYOUT_CONV_OKI = 1 /* Conv1d weight stored [Cout][k][Cin]; torch shape is [Cout][Cin][k] */
+};
+
+int hippie_abi_version(void);
+
+int hippie_create(const hippie_cfg* cfg, hippie_handle* out);
+void hippie_destroy(hippie_handle h);
+const char* hippie_last_error(hippie_handle h);
+
+/* ---- layout enumeration, in state_dict() order (hippie/model.py:360-395 construction order) ----
+ * Parameters: `offset`/`numel` in floats inside the flat params / grads / exp_avg / exp_avg_sq
+ * buffers (each hippie_param_floats() long; offsets are 16-byte aligned, gaps stay zero).
+ * `shape` is the torch shape (ndim <= 3).  */
+int hippie_num_params(hippie_handle h);
+int64_t hippie_param_floats(hippie_handle h);
+int hippie_param_info(hippie_handle h, int idx, char* name, int name_cap, int64_t* offset, int64_t* numel,
+                      int32_t* ndim, int64_t* shape3, int32_t* layout);
+/* BatchNorm1d buffers: running_mean at bn_mean[offset..offset+C), running_var likewise in bn_var,
+ * num_batches_tracked at bn_count[idx] (int64). */
+int hippie_num_bn(hippie_handle h);
+int64_t hippie_bn_floats(hippie_handle h);
+int hippie_bn_info(hippie_handle h, int idx, char* name, int name_cap, int64_t* offset, int64_t* channels);
+
+/* Workspace the caller must provide (bytes, for cfg.max_batch). */
+size_t hippie_workspace_bytes(hippie_handle h);
+
+/* Named activation tensors inside the workspace (debug / parity tests): offset in floats,
+ * positions L, channels C, pad rows per side (row of (b,l) = b*(L+2*pad)+pad+l). */
+int hippie_num_tensors(hippie_handle h);
+int hippie_tensor_info(hippie_handle h, int idx, char* name, int name_cap, int64_t* offset, int32_t* L,
+                       int32_t* C, int32_t* pad);
+
+/* Replaces nn.Module parameter/buffer ownership + torch.optim.AdamW state (hippie/model.py:447):
+ * hands the engine the flat device buffers.  Zero-fills the workspace (async on `stream`). */
+int hippie_bind(hippie_handle h, float* params, float* grads, float* exp_avg, float* exp_avg_sq, float* bn_mean,
+                float* bn_var, int64_t* bn_count, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Replaces training_step + zero_grad + loss.backward() (hippie/model.py:454-482).
+ *   x1 [B,1,len_wave] f32, x2 [B,1,len_isi] f32 (NULL when unimodal), src int64 [B],
+ *   cls int64 [B] or NULL (class embedding := 0, hippie/model.py:426), eps f32 [B,z] = the N(0,1)
+ *   draw of reparameterize (hippie/model.py:397-400).
+ * Writes the gradient of the loss w.r.t. every parameter into `grads` (zero-filled first),
+ * updates BatchNorm running statistics, and writes scalars_out[0..3] = total, mse1, mse2, kl_mean
+ * (device floats).  out_* (device, may be NULL): enc [B,z], mu [B,z], logvar [B,z],
+ * dec1 [B,len_wave], dec2 [B,len_isi]. */
+int hippie_train_fwd_bwd(hippie_handle h, const float* x1, const float* x2, const int64_t* src, const int64_t* cls,
+                         const float* eps, int32_t B, float beta, float w1, float w2, float* scalars_out,
+                         float* out_enc, float* out_mu, float* out_logvar, float* out_dec1, float* out_dec2,
+                         void* stream);
+
+/* Replaces Lightning's gradient_clip_val (scripts/train_model_with_multimodal.py:55,701 ->
+ * torch.nn.utils.clip_grad_norm_) followed by torch.optim.AdamW.step (hippie/model.py:447).
+ *   grad_scale multiplies every gradient first (1/world after a summing all-reduce);
+ *   max_norm <= 0 disables clipping; step / step_cls are the 1-based AdamW step counts of the
+ *   ordinary parameters and of class_embedding.weight; has_cls_grad = 0 leaves class_embedding
+ *   untouched (torch skips params whose grad is None).
+ * scalars_out[4] = total gradient norm (after grad_scale), scalars_out[5] = clip coefficient. */
+int hippie_clip_adamw(hippie_handle h, float lr, float beta1, float beta2, float eps, float weight_decay,
+                      float max_norm, float grad_scale, int32_t step, int32_t step_cls, int32_t has_cls_grad,
+                      float* scalars_out, void* stream);
+
+/* Replaces module.eval(); module(batch) (hippie/model.py:510-520): full forward with running
+ * statistics.  Outputs as above (any may be NULL); scalars_out (may be NULL) gets the validation
+ * loss terms of validation_step (hippie/model.py:484-508). */
+int hippie_eval_forward(hippie_handle h, const float* x1, const float* x2, const int64_t* src, const int64_t* cls,
+                        const float* eps, int32_t B, float beta, float w1, float w2, float* scalars_out,
+                        float* out_enc, float* out_mu, float* out_logvar, float* out_dec1, float* out_dec2,
+                        void* stream);
+
+/* Replaces get_embeddings_multimodal's model(sample)[0] (scripts/train_model_with_multimodal.py:
+ * 22-34): encoders + fusion only (the reference also runs both decoders and discards them).
+ * zscore_ddof: -1 = raw `encoded`; 0 / 1 = per-row z-score with that ddof fused in. */
+int hippie_embed(hippie_handle h, const float* x1, const float* x2, const int64_t* src, const int64_t* cls,
+                 int32_t B, int32_t zscore_ddof, float* out_enc, float* out_mu, float* out_logvar, void* stream);
+
+/* Number of kernel launches issued by the most recent call of each kind (bench.py gpu_launches). */
+int hippie_last_launch_count(hippie_handle h);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* HIPPIE_B200_H */
