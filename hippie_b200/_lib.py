@@ -59,10 +59,14 @@ SIGNATURES = {
                                        C.c_float, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, C.c_void_p]),
     "hippie_eval_forward": (C.c_int, [_H, _f32p, _f32p, _i64p, _i64p, _f32p, C.c_int32, C.c_float, C.c_float,
                                       C.c_float, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, C.c_void_p]),
+    "hippie_train_forward": (C.c_int, [_H, _f32p, _f32p, _i64p, _i64p, _f32p, C.c_int32, C.c_float, C.c_float,
+                                       C.c_float, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, C.c_void_p]),
     "hippie_embed": (C.c_int, [_H, _f32p, _f32p, _i64p, _i64p, C.c_int32, C.c_int32, _f32p, _f32p, _f32p, C.c_void_p]),
     "hippie_clip_adamw": (C.c_int, [_H, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
                                     C.c_int32, C.c_int32, C.c_int32, _f32p, C.c_void_p]),
     "hippie_last_launch_count": (C.c_int, [_H]),
+    "hippie_profile": (C.c_int, [_H, C.c_int]),
+    "hippie_profile_read": (C.c_int, [_H, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int)]),
 }
 
 

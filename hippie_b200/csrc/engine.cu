@@ -114,6 +114,28 @@ struct hippie_engine {
   cudaStream_t side = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   int launches = 0;
+  // profiling aid (bench.py roofline): CUDA events around every implicit-GEMM launch
+  struct ProfRec {
+    int kind;
+    cudaEvent_t e0, e1;
+    double flop;
+  };
+  bool profiling = false;
+  std::vector<ProfRec> prof;
+  cudaEvent_t prof_begin(Branch& br) {
+    if (!profiling) return nullptr;
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, br.st);
+    return e;
+  }
+  void prof_end(cudaEvent_t e0, int kind, double flop, Branch& br) {
+    if (!profiling) return;
+    cudaEvent_t e1;
+    cudaEventCreate(&e1);
+    cudaEventRecord(e1, br.st);
+    prof.push_back({kind, e0, e1, flop});
+  }
 
   // ---- construction -------------------------------------------------------------------------
   int64_t take(int64_t floats) {
@@ -441,7 +463,9 @@ struct hippie_engine {
     g.M = B * acts[out].L, g.N = cv.cout, g.K = cv.k * cv.cin, g.Lout = acts[out].L;
     g.in_rows = acts[in].L + 2, g.in_stride = cv.stride, g.in_off = cv.k == 3 ? 0 : 1, g.in_C = cv.cin;
     g.out_rows = acts[out].L + 2, g.out_off = 1, g.out_lstride = 1, g.accumulate = 0;
+    cudaEvent_t pe = prof_begin(br);
     const int tile = launch_conv_gemm_simt(g, br.st);
+    prof_end(pe, 0, 2.0 * g.M * g.N * g.K, br);
     ++launches;
     if (train && bn >= 0) bn_finalize(bn, br.part, (g.M + tile - 1) / tile, tile, g.M, br);
   }
@@ -469,14 +493,19 @@ struct hippie_engine {
     g.M = B * acts[gx].L, g.N = cv.cin, g.K = cv.k * cv.cout, g.Lout = acts[gx].L;
     g.in_rows = acts[dy].L + 2, g.in_stride = 1, g.in_off = cv.k == 3 ? 0 : 1, g.in_C = cv.cout;
     g.out_rows = acts[gx].L + 2, g.out_off = 1, g.out_lstride = 1, g.accumulate = accumulate ? 1 : 0;
+    cudaEvent_t pe = prof_begin(br);
     launch_conv_gemm_simt(g, br.st);
+    prof_end(pe, 1, 2.0 * g.M * g.N * g.K, br);
     ++launches;
   }
   void wgrad(const Conv& cv, int dy, int x, int B, Branch& br) {
     WgradGemm g{};
     g.dY = A(dy), g.X = A(x), g.dW = Gp(cv.w);
     g.M = cv.cout, g.N = cv.k * cv.cin, g.R = B * (acts[dy].L + 2), g.Cin = cv.cin, g.roff = cv.k == 3 ? -1 : 0;
+    cudaEvent_t pe = prof_begin(br);
     launch_wgrad_simt(g, sm_count, br.st);
+    // algorithmic FLOPs: only the B*Lout real output rows contribute (pad / dilation rows are zeros)
+    prof_end(pe, 2, 2.0 * (double)g.M * g.N * (double)B * acts[dy].L / (cv.stride == 2 ? 2.0 : 1.0), br);
     ++launches;
   }
   void bn_bwd(int g, bool g_up, int out, int c, int bn, int cs, int bnsi, int dc, int dil, int dcs, int dil_s, int gres,
@@ -651,7 +680,7 @@ struct hippie_engine {
           const float* eps, int B, float beta, float w1, float w2, float* scalars_out, float* out_enc, float* out_mu,
           float* out_logvar, float* out_dec1, float* out_dec2, cudaStream_t main) {
     launches = 0;
-    Branch b0{main, ws + part_off[0], ws + bpart_off[0]}, b1{side, ws + part_off[1], ws + bpart_off[1]};
+    Branch b0{main, ws + part_off[0], ws + bpart_off[0]}, b1{profiling ? main : side, ws + part_off[1], ws + bpart_off[1]};
     const float* xin[2] = {x1, x2};
     float* dec_out[2] = {out_dec1, out_dec2};
     const float lw[2] = {cfg.multimodal ? w1 : 1.f, w2};
@@ -824,6 +853,16 @@ int hippie_eval_forward(hippie_handle h, const float* x1, const float* x2, const
                 out_dec1, out_dec2, (cudaStream_t)stream);
 }
 
+int hippie_train_forward(hippie_handle h, const float* x1, const float* x2, const int64_t* src, const int64_t* cls,
+                         const float* eps, int32_t B, float beta, float w1, float w2, float* scalars_out, float* out_enc,
+                         float* out_mu, float* out_logvar, float* out_dec1, float* out_dec2, void* stream) {
+  if (!h) return -1;
+  if (int rc = h->validate(B, x1, x2, src)) return rc;
+  if (B < 2) return h->fail(-3, "training-mode BatchNorm needs B >= 2");
+  return h->run(true, false, x1, x2, src, cls, eps, B, beta, w1, w2, scalars_out, out_enc, out_mu, out_logvar, out_dec1,
+                out_dec2, (cudaStream_t)stream);
+}
+
 int hippie_embed(hippie_handle h, const float* x1, const float* x2, const int64_t* src, const int64_t* cls, int32_t B,
                  int32_t zscore_ddof, float* out_enc, float* out_mu, float* out_logvar, void* stream) {
   if (!h) return -1;
@@ -868,5 +907,26 @@ int hippie_clip_adamw(hippie_handle h, float lr, float beta1, float beta2, float
 }
 
 int hippie_last_launch_count(hippie_handle h) { return h ? h->launches : -1; }
+
+int hippie_profile(hippie_handle h, int enable) {
+  if (!h) return -1;
+  for (auto& r : h->prof) cudaEventDestroy(r.e0), cudaEventDestroy(r.e1);
+  h->prof.clear();
+  h->profiling = enable != 0;
+  return 0;
+}
+
+int hippie_profile_read(hippie_handle h, int kind, double* total_ms, double* total_flop, int* launches) {
+  if (!h || !total_ms || !total_flop || !launches) return -1;
+  *total_ms = 0, *total_flop = 0, *launches = 0;
+  for (auto& r : h->prof) {
+    if (r.kind != kind) continue;
+    cudaEventSynchronize(r.e1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, r.e0, r.e1);
+    *total_ms += ms, *total_flop += r.flop, *launches += 1;
+  }
+  return h->check("hippie_profile_read");
+}
 
 }  // extern "C"

@@ -222,7 +222,7 @@ __global__ void __launch_bounds__(1024) head_fwd_kernel(HeadArgs a) {
     klp += -0.5f * (1.f + v - m * m - ev);
     if (a.decode) {
       const float std = expf(0.5f * v);
-      S[L.zc + (int64_t)b * DZ + i] = fmaf(a.eps[(int64_t)b * z + i], std, m);
+      S[L.zc + (int64_t)b * DZ + i] = a.eps ? fmaf(a.eps[(int64_t)b * z + i], std, m) : m;
     }
   }
   if (a.out_enc) {

@@ -1,0 +1,156 @@
+"""Host-side datasets and sampler with the reference's semantics (reference hippie/dataloading.py:18-151).
+
+Per item: float32 cast, log(isi + 1), linear interpolation (align_corners=False) of the waveform to 50 and of
+the ISI histogram to 100 samples, `view(1, -1)`; labels as int64.  Indexing, shuffling and label encoding stay
+on the host so they are bit-identical to the reference; the tensors they produce are what the engine consumes.
+
+Differences from the reference, all additive:
+  * `EphysDatasetLabeled` accepts mode="both" (the reference's multimodal CLI passes it,
+    scripts/train_model_with_multimodal.py:638, but the reference class asserts it away -- SURVEY.md F4);
+  * `normalize=True` works (the reference calls np.min on a tensor and raises, dataloading.py:84);
+  * `BalancedBatchSampler` takes an optional `seed` for its over-sampling draws (the reference uses the
+    unseeded global `random`); seed=None keeps the reference behaviour;
+  * `EphysTensorDataset.batch()` serves whole pre-transformed batches (one gather instead of B __getitem__ calls).
+"""
+from __future__ import annotations
+
+import random
+from typing import Optional
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+from torch.utils.data import Dataset, Sampler
+
+WAVE_LEN = 50
+ISI_LEN = 100
+
+
+def _transform(waveform: torch.Tensor, isi_dist: torch.Tensor, normalize: bool):
+    waveform = waveform.float()
+    isi_dist = torch.log(isi_dist.float() + 1)
+    if normalize:
+        lo, hi = waveform.min(), waveform.max()
+        waveform = (waveform - lo) / (hi - lo) * 2 - 1
+        isi_dist = (isi_dist - isi_dist.mean()) / isi_dist.std()
+    waveform = F.interpolate(waveform.view(1, 1, -1), size=(WAVE_LEN,), mode="linear").view(1, -1)
+    isi_dist = F.interpolate(isi_dist.view(1, 1, -1), size=(ISI_LEN,), mode="linear").view(1, -1)
+    return waveform, isi_dist
+
+
+class EphysDataset(Dataset):
+    """reference hippie/dataloading.py:18-59."""
+
+    def __init__(self, waveforms, isi_dists, mode, normalize=True):
+        self.waveforms = np.array(waveforms)
+        self.isi_dists = np.array(isi_dists)
+        assert mode in ("wave", "time", "both")
+        self.mode = mode
+        assert len(self.waveforms) == len(self.isi_dists)
+        self.normalize = normalize
+
+    def __getitem__(self, idx):
+        waveform, isi_dist = _transform(torch.as_tensor(self.waveforms[idx, ...]),
+                                        torch.as_tensor(self.isi_dists[idx, ...]), self.normalize)
+        if self.mode == "wave":
+            return waveform, -1
+        if self.mode == "time":
+            return isi_dist, -1
+        return waveform, isi_dist
+
+    def __len__(self):
+        return len(self.waveforms)
+
+
+class EphysDatasetLabeled(Dataset):
+    """reference hippie/dataloading.py:62-104, plus the missing mode="both" -> (wave, isi, label)."""
+
+    def __init__(self, waveforms, isi_dists, labels, mode, normalize=True):
+        self.waveforms = np.array(waveforms)
+        self.isi_dists = np.array(isi_dists)
+        self.labels = np.array(labels)
+        assert mode in ("wave", "time", "both")
+        self.mode = mode
+        assert len(self.waveforms) == len(self.isi_dists)
+        assert len(self.waveforms) == len(self.labels)
+        self.normalize = normalize
+
+    def __getitem__(self, idx):
+        waveform, isi_dist = _transform(torch.as_tensor(self.waveforms[idx, ...]),
+                                        torch.as_tensor(self.isi_dists[idx, ...]), self.normalize)
+        label = torch.as_tensor(self.labels[idx]).long()
+        if self.mode == "wave":
+            return waveform, label
+        if self.mode == "time":
+            return isi_dist, label
+        return waveform, isi_dist, label
+
+    def __len__(self):
+        return len(self.waveforms)
+
+
+class EphysTensorDataset(Dataset):
+    """The same transform applied once to every row up front (rows may have different raw widths per source, so
+    the transform is per source table), stored as dense [N,1,50] / [N,1,100] / labels tensors.  `batch(indices)`
+    gathers a whole batch in one call -- the Python per-item path of the reference tops out near 20 K items/s."""
+
+    def __init__(self, waveforms, isi_dists, labels=None, normalize=False):
+        wf, isi = np.asarray(waveforms), np.asarray(isi_dists)
+        assert len(wf) == len(isi)
+        w = torch.as_tensor(wf).float()
+        t = torch.log(torch.as_tensor(isi).float() + 1)
+        if normalize:
+            lo, hi = w.min(dim=1, keepdim=True).values, w.max(dim=1, keepdim=True).values
+            w = (w - lo) / (hi - lo) * 2 - 1
+            t = (t - t.mean(dim=1, keepdim=True)) / t.std(dim=1, keepdim=True)
+        self.wave = F.interpolate(w.unsqueeze(1), size=(WAVE_LEN,), mode="linear")
+        self.isi = F.interpolate(t.unsqueeze(1), size=(ISI_LEN,), mode="linear")
+        self.labels = None if labels is None else torch.as_tensor(np.asarray(labels)).long()
+
+    def __len__(self):
+        return self.wave.shape[0]
+
+    def __getitem__(self, idx):
+        if self.labels is None:
+            return self.wave[idx], self.isi[idx]
+        return self.wave[idx], self.isi[idx], self.labels[idx]
+
+    def batch(self, indices):
+        idx = torch.as_tensor(indices, dtype=torch.long)
+        if self.labels is None:
+            return self.wave[idx], self.isi[idx]
+        return self.wave[idx], self.isi[idx], self.labels[idx]
+
+
+class BalancedBatchSampler(Sampler):
+    """Round-robin over classes with the minority classes over-sampled to the majority count
+    (reference hippie/dataloading.py:107-151)."""
+
+    def __init__(self, dataset, labels=None, seed: Optional[int] = None):
+        if labels is None:
+            raise Exception("You should pass the tensor of labels to the constructor as second argument")
+        self.labels = labels
+        rng = random if seed is None else random.Random(seed)
+        self.dataset = {}
+        for idx in range(len(dataset)):
+            self.dataset.setdefault(self._get_label(dataset, idx), []).append(idx)
+        self.balanced_max = max(len(v) for v in self.dataset.values()) if self.dataset else 0
+        for label in self.dataset:
+            while len(self.dataset[label]) < self.balanced_max:
+                self.dataset[label].append(rng.choice(self.dataset[label]))
+        self.keys = list(self.dataset.keys())
+        self.currentkey = 0
+        self.indices = [-1] * len(self.keys)
+
+    def _get_label(self, dataset, idx, labels=None):
+        return self.labels[idx].item()
+
+    def __iter__(self):
+        while self.indices[self.currentkey] < self.balanced_max - 1:
+            self.indices[self.currentkey] += 1
+            yield self.dataset[self.keys[self.currentkey]][self.indices[self.currentkey]]
+            self.currentkey = (self.currentkey + 1) % len(self.keys)
+        self.indices = [-1] * len(self.keys)
+
+    def __len__(self):
+        return self.balanced_max * len(self.keys)

@@ -179,11 +179,15 @@ class Engine:
             _ptr(outs.get("dec2")), self._stream()))
         return scalars, (outs if outputs else None)
 
-    def eval_forward(self, x1, x2, src, cls, eps, beta: float = 1.0, w1: float = 1.0, w2: float = 1.0, scalars=None):
+    def train_forward(self, x1, x2, src, cls, eps, beta: float = 1.0, w1: float = 1.0, w2: float = 1.0, scalars=None):
+        return self.eval_forward(x1, x2, src, cls, eps, beta, w1, w2, scalars, _fn="hippie_train_forward")
+
+    def eval_forward(self, x1, x2, src, cls, eps, beta: float = 1.0, w1: float = 1.0, w2: float = 1.0, scalars=None,
+                     _fn="hippie_eval_forward"):
         B = x1.shape[0]
         self._io(x1, x2, src, cls, eps, B)
         outs = self._out_buffers(B)
-        self._check(self._L.hippie_eval_forward(
+        self._check(getattr(self._L, _fn)(
             self._h, _ptr(x1), _ptr(x2), _ptr(src), _ptr(cls), _ptr(eps), B, beta, w1, w2, _ptr(scalars),
             _ptr(outs.get("enc")), _ptr(outs.get("mu")), _ptr(outs.get("logvar")), _ptr(outs.get("dec1")),
             _ptr(outs.get("dec2")), self._stream()))

@@ -1,0 +1,46 @@
+"""Data-parallel plumbing (one process per GPU, torch.distributed): batch sharding and the gradient exchange.
+
+The reference has no explicit parallelism; under Lightning's implicit DDP every rank runs the step on its own
+shard, BatchNorm statistics stay per rank, gradients are summed and divided by the world size before clipping
+(SURVEY.md section 8e).  Here the exchange is ONE all-reduce of the engine's flat fp32 gradient buffer; the
+1/world factor is folded into the fused clip + AdamW kernel (`grad_scale`)."""
+from __future__ import annotations
+
+from typing import List, Sequence
+
+import torch
+import torch.distributed as dist
+
+
+def shard_batch_indices(perm: Sequence[int], step: int, rank: int, world: int, per_rank_batch: int) -> List[int]:
+    """Global step `step` consumes world*per_rank_batch consecutive indices of the epoch permutation; rank r takes
+    the r-th contiguous slice (ragged tail allowed)."""
+    g0 = step * world * per_rank_batch
+    lo = g0 + rank * per_rank_batch
+    return list(perm[lo:min(lo + per_rank_batch, min(len(perm), g0 + world * per_rank_batch))])
+
+
+def shard_units(n: int, rank: int, world: int):
+    """Contiguous shard [lo, hi) of n independent units for communication-free embedding inference; concatenating
+    the shards in rank order restores the row order of the CSV."""
+    base, rem = divmod(n, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def all_reduce_gradients(flat_grads: torch.Tensor, group=None) -> float:
+    """Sums the flat gradient buffer over the ranks (NCCL over NVLink on GPUs, gloo in the CPU tests) and returns
+    the factor the optimizer kernel must apply (1/world)."""
+    if not dist.is_available() or not dist.is_initialized():
+        return 1.0
+    world = dist.get_world_size(group)
+    if world > 1:
+        dist.all_reduce(flat_grads, op=dist.ReduceOp.SUM, group=group)
+    return 1.0 / world
+
+
+def broadcast_state(tensors: Sequence[torch.Tensor], src: int = 0, group=None):
+    """Rank `src`'s parameters / BatchNorm buffers / AdamW state to everybody (DDP's initial broadcast)."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        for t in tensors:
+            dist.broadcast(t, src=src, group=group)

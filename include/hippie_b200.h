@@ -121,6 +121,14 @@ int hippie_eval_forward(hippie_handle h, const float* x1, const float* x2, const
                         float* out_enc, float* out_mu, float* out_logvar, float* out_dec1, float* out_dec2,
                         void* stream);
 
+/* Replaces module.train(); module(batch) without a backward pass (MultiModalCVAE.forward in training mode,
+ * hippie/model.py:424-432): batch statistics, running-statistics update, no gradients.  Same arguments as
+ * hippie_eval_forward. */
+int hippie_train_forward(hippie_handle h, const float* x1, const float* x2, const int64_t* src, const int64_t* cls,
+                         const float* eps, int32_t B, float beta, float w1, float w2, float* scalars_out,
+                         float* out_enc, float* out_mu, float* out_logvar, float* out_dec1, float* out_dec2,
+                         void* stream);
+
 /* Replaces get_embeddings_multimodal's model(sample)[0] (scripts/train_model_with_multimodal.py:
  * 22-34): encoders + fusion only (the reference also runs both decoders and discards them).
  * zscore_ddof: -1 = raw `encoded`; 0 / 1 = per-row z-score with that ddof fused in. */
@@ -129,6 +137,13 @@ int hippie_embed(hippie_handle h, const float* x1, const float* x2, const int64_
 
 /* Number of kernel launches issued by the most recent call of each kind (bench.py gpu_launches). */
 int hippie_last_launch_count(hippie_handle h);
+
+/* Measurement aid for bench.py (not part of the reference interface): when enabled, every implicit-GEMM launch
+ * (kind 0 = conv forward, 1 = dgrad, 2 = wgrad) of the following calls is bracketed by CUDA events on the stream it
+ * is launched on, and both branches run on the caller's stream so the per-launch times are not shared.
+ * hippie_profile_read sums, per kind, the event durations and the algorithmic FLOPs (2*M*N*K over real rows). */
+int hippie_profile(hippie_handle h, int enable);
+int hippie_profile_read(hippie_handle h, int kind, double* total_ms, double* total_flop, int* launches);
 
 #if defined(__GNUC__)
 #pragma GCC visibility pop

@@ -1,0 +1,193 @@
+"""CPU-side tests: the C-ABI library loads and exports what include/hippie_b200.h declares, the layout and the
+nn.Module mirror agree with the oracle (== the reference's construction order and initial values), host logic."""
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import cvae_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    import ctypes
+    from hippie_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "hippie_b200.h")).read()
+    declared = sorted(set(re.findall(r"\b(hippie_[a-z_0-9]+)\s*\(", hdr)))
+    assert len(declared) >= 20
+    L = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(L, name), name
+    assert sorted(_lib.SIGNATURES) == declared  # the ctypes binding covers the whole header
+    assert _lib.lib().hippie_abi_version() == _lib.ABI_VERSION
+
+
+@pytest.mark.parametrize("cfg", [O.CVAEConfig(z_dim=10), O.CVAEConfig(z_dim=32, num_classes=4),
+                                 O.CVAEConfig(z_dim=64), O.CVAEConfig(z_dim=10, multimodal=False, output_size_wave=50),
+                                 O.CVAEConfig(z_dim=10, multimodal=False, output_size_wave=100)])
+def test_layout_matches_reference_construction_order(cfg):
+    from hippie_b200.engine import Engine, LAYOUT_CONV_OKI
+    e = Engine(cfg.z_dim, cfg.output_size_wave, cfg.output_size_isi, cfg.class_hidden_dim, cfg.num_sources,
+               cfg.num_classes, cfg.multimodal, 64)
+    spec = {n: (k, s) for n, k, s in O.model_spec(cfg)}
+    assert [p.name for p in e.params] == O.param_names(cfg)
+    end = 0
+    for p in e.params:
+        kind, shp = spec[p.name]
+        assert p.shape == tuple(O._torch_shape(kind, shp))
+        assert p.offset % 4 == 0 and p.offset >= end
+        assert (p.layout == LAYOUT_CONV_OKI) == (kind == "conv_w")
+        end = p.offset + p.numel
+    assert e.param_floats >= end and e.param_floats % 4 == 0
+    bn = [n[:-len(".running_mean")] for n, k, _ in O.model_spec(cfg) if n.endswith(".running_mean")]
+    assert [b.name for b in e.bns] == bn
+    assert sum(p.numel for p in e.params) == sum(int(np.prod(O._torch_shape(k, s))) for n, k, s in O.model_spec(cfg)
+                                                 if not O.is_buffer(k))
+
+
+def test_error_codes_without_gpu():
+    from hippie_b200.engine import Engine
+    with pytest.raises(ValueError):
+        Engine(0, 50, 100, 5, 5, 5, True, 64)
+    e = Engine(10, 50, 100, 5, 5, 5, True, 64)
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            e.allocate("cuda:0")
+
+
+@pytest.mark.parametrize("multimodal", [True, False])
+def test_module_mirror_state_dict_bit_exact_with_reference_init(multimodal):
+    from hippie_b200.model import MultiModalCVAE, MultiModalCVAETrainModule, hippieUnimodalCVAE, \
+        hippieUnimodalEmbeddingModelCVAE
+    torch.manual_seed(42)
+    if multimodal:
+        cfg = O.CVAEConfig(z_dim=10)
+        m = MultiModalCVAE(10, 50, 100, class_hidden_dim=5, num_sources=5, num_classes=5, max_batch=8)
+        tm = MultiModalCVAETrainModule(m, learning_rate=1e-3, weight_decay=0.01, beta=0.5)
+    else:
+        cfg = O.CVAEConfig(z_dim=10, multimodal=False, output_size_wave=100, num_classes=4)
+        m = hippieUnimodalCVAE(10, 100, 5, 5, 4, max_batch=8)
+        tm = hippieUnimodalEmbeddingModelCVAE(m, learning_rate=1e-3)
+    ref = O.init_state(cfg, seed=42)
+    sd = m.state_dict()
+    assert list(sd.keys()) == list(ref.keys())
+    for k in ref:
+        assert sd[k].shape == ref[k].shape and sd[k].dtype == ref[k].dtype, k
+        assert torch.equal(sd[k], ref[k]), k
+    assert list(tm.state_dict().keys()) == ["model." + k for k in ref]
+    assert len(list(m.parameters())) == len(O.param_names(cfg))
+    # load_state_dict round trip through the flat buffer (conv weights are stored [Cout][k][Cin])
+    new = {k: (torch.randn_like(v) if v.is_floating_point() else v + 5) for k, v in ref.items()}
+    m.load_state_dict(new)
+    for k in new:
+        assert torch.equal(m.state_dict()[k], new[k]), k
+    w = m.state_dict()["decoder.layer4.1.conv1.conv.weight" if not multimodal else "decoder_mod1.layer4.1.conv1.conv.weight"]
+    assert w.shape == (256, 512, 3) and not w.is_contiguous()
+    # strict=False partial load, as the reference's stage-3 does after popping class_embedding
+    part = {k: v for k, v in ref.items() if k != "class_embedding.weight"}
+    res = m.load_state_dict(part, strict=False)
+    assert res.missing_keys == ["class_embedding.weight"]
+    # no CPU path
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        if multimodal:
+            m(torch.zeros(2, 1, 50), torch.zeros(2, 1, 100), torch.zeros(2, dtype=torch.long))
+        else:
+            m(torch.zeros(2, 1, 100), torch.zeros(2, dtype=torch.long))
+    # torch-format optimizer state
+    osd = tm.optimizer.state_dict()
+    assert osd["param_groups"][0]["lr"] == 1e-3 and osd["state"] == {}
+
+
+def test_ckpt_roundtrip(tmp_path):
+    from hippie_b200.model import MultiModalCVAE, MultiModalCVAETrainModule
+    torch.manual_seed(1)
+    tm = MultiModalCVAETrainModule(MultiModalCVAE(10, 50, 100, 5, 5, 5, max_batch=8))
+    path = tmp_path / "epoch=0-step=1.ckpt"
+    torch.save({"state_dict": tm.state_dict(), "epoch": 0, "global_step": 1}, path)
+    torch.manual_seed(2)
+    tm2 = MultiModalCVAETrainModule(MultiModalCVAE(10, 50, 100, 5, 5, 5, max_batch=8))
+    sd = torch.load(path)["state_dict"]
+    tm2.load_state_dict(sd)
+    for (k, a), (_, b) in zip(tm.state_dict().items(), tm2.state_dict().items()):
+        assert torch.equal(a, b), k
+
+
+def test_dataset_items_match_oracle_and_fixture(golden_dir):
+    from hippie_b200.dataloading import EphysDataset, EphysDatasetLabeled, EphysTensorDataset
+    fx = np.load(os.path.join(golden_dir, "cellexplorer_raw48.npz"))
+    ds = EphysDataset(fx["wf"], fx["isi"], mode="both", normalize=False)
+    lab = np.arange(len(ds)) % 4
+    dl = EphysDatasetLabeled(fx["wf"], fx["isi"], lab, mode="both", normalize=False)
+    dt = EphysTensorDataset(fx["wf"], fx["isi"], lab)
+    for i in range(len(ds)):
+        a, b = ds[i]
+        assert np.array_equal(a.numpy(), fx["x1"][i]) and np.array_equal(b.numpy(), fx["x2"][i])
+        oa, ob = O.dataset_item(fx["wf"][i], fx["isi"][i])
+        assert torch.equal(a, oa) and torch.equal(b, ob)
+        w, t, l = dl[i]
+        assert torch.equal(w, a) and torch.equal(t, b) and l.dtype == torch.int64 and int(l) == lab[i]
+        assert torch.equal(dt[i][0], a) and torch.equal(dt[i][1], b)
+    w, t, l = dt.batch([3, 1, 2])
+    assert w.shape == (3, 1, 50) and t.shape == (3, 1, 100) and l.tolist() == [lab[3], lab[1], lab[2]]
+    assert EphysDatasetLabeled(fx["wf"], fx["isi"], lab, mode="wave", normalize=False)[0][0].shape == (1, 50)
+    # empty dataset
+    assert len(EphysDataset(np.zeros((0, 47)), np.zeros((0, 100)), mode="both", normalize=False)) == 0
+
+
+def test_balanced_sampler_round_robin_and_seed():
+    from hippie_b200.dataloading import BalancedBatchSampler
+    labels = torch.tensor([0] * 5 + [1] * 2 + [2] * 1)
+    s = BalancedBatchSampler(range(len(labels)), labels, seed=0)
+    idx = list(iter(s))
+    assert len(idx) == len(s) == 15
+    assert [int(labels[i]) for i in idx] == [0, 1, 2] * 5  # strict round robin over classes
+    assert sorted(i for i in idx if labels[i] == 0) == [0, 1, 2, 3, 4]  # majority class: every item exactly once
+    assert list(iter(BalancedBatchSampler(range(len(labels)), labels, seed=0))) == idx
+    assert list(iter(s)) == idx  # re-iterable
+
+
+def test_shard_helpers():
+    from hippie_b200.parallel import shard_batch_indices, shard_units
+    perm = list(range(100, 100 + 23))
+    got = [shard_batch_indices(perm, s, r, 2, 4) for s in range(3) for r in range(2)]
+    assert got[0] == perm[0:4] and got[1] == perm[4:8] and got[4] == perm[16:20] and got[5] == perm[20:23]
+    assert sum(got, []) == perm  # bit-exact partition of the permutation, in order
+    spans = [shard_units(10, r, 4) for r in range(4)]
+    assert spans == [(0, 3), (3, 6), (6, 8), (8, 10)]
+    assert shard_units(0, 0, 2) == (0, 0)
+
+
+_GLOO_WORKER = r'''
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from hippie_b200.parallel import all_reduce_gradients, broadcast_state, shard_batch_indices
+dist.init_process_group("gloo")
+r, w = dist.get_rank(), dist.get_world_size()
+g = torch.arange(12, dtype=torch.float32) * (r + 1)
+scale = all_reduce_gradients(g)
+assert scale == 0.5 and torch.equal(g * scale, torch.arange(12, dtype=torch.float32) * 1.5), g
+p = torch.full((5,), float(r))
+broadcast_state([p], src=0)
+assert torch.equal(p, torch.zeros(5))
+mine = shard_batch_indices(list(range(10)), 0, r, w, 3)
+allv = [None, None]
+dist.all_gather_object(allv, mine)
+assert allv == [[0, 1, 2], [3, 4, 5]]
+dist.destroy_process_group()
+print("ok", r)
+'''
+
+
+def test_data_parallel_exchange_gloo_world2(tmp_path):
+    script = tmp_path / "w.py"
+    script.write_text(_GLOO_WORKER)
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29571", str(script), ROOT],
+                         capture_output=True, text=True, timeout=240)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert out.stdout.count("ok") == 2
