@@ -65,6 +65,7 @@ SIGNATURES = {
     "hippie_clip_adamw": (C.c_int, [_H, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
                                     C.c_int32, C.c_int32, C.c_int32, _f32p, C.c_void_p]),
     "hippie_last_launch_count": (C.c_int, [_H]),
+    "hippie_conv_path_in_use": (C.c_int, [_H]),
     "hippie_profile": (C.c_int, [_H, C.c_int]),
     "hippie_profile_read": (C.c_int, [_H, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int)]),
 }

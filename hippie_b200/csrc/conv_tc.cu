@@ -1,0 +1,618 @@
+// tcgen05 implicit-GEMM conv1d (forward and dgrad) with fp32-level accuracy via the 3xTF32 split.
+//
+//   C[m, n] (+)= sum_k A[row(m), k] * W[n, k]        A rows = contiguous k*Cin windows of the padded
+//                                                   channels-last input, W = [N][K] K-major weights
+//
+// Per CTA: one 128-row x BN-column output tile, accumulators in TMEM (BN fp32 columns).
+//   warp 0    TMA producer: per 32-float k-block one 3-D box of A ([samples][Lout][32 floats], 128B swizzle)
+//             and one 2-D box of W into a STAGES-deep shared-memory ring
+//   warp 1    TMEM allocator + MMA issuer: 3 x tcgen05.mma.kind::tf32 per 8-wide k-step
+//             (lo*hi + hi*lo + hi*hi, fp32 accumulation in TMEM).  The tensor core truncates when it adds
+//             into the fp32 accumulator, which biases a long K loop by ~n_steps * 2^-24 (measured: 4e-5 at
+//             K = 1536); the hi*hi products therefore alternate between two accumulators per k-block and the
+//             small lo terms use a third, and the epilogue adds the three with round-to-nearest.
+//   warps 2-5 split every landed fp32 tile in place into hi = tf32-rounded value and a second buffer
+//             lo = x - hi (exact in fp32), then run the epilogue: TMEM -> registers -> shared staging ->
+//             coalesced global stores, bias / accumulate, BatchNorm (sum, centred M2) partials per column.
+//
+// Replaces the nn.Conv1d forward calls of hippie/backbones.py:11,24,26,31,50,55 and their input gradients.
+#include <cuda.h>
+
+#include "kernels.cuh"
+
+namespace hp {
+
+namespace {
+
+constexpr int TC_BM = 128;
+constexpr int TC_BK = 32;  // floats per k-block = one 128-byte swizzle row
+constexpr int TC_THREADS = 192;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+// shared-memory matrix descriptor: K-major, 128-byte swizzle, 8-row groups 1024 B apart (cute::UMMA::SmemDescriptor)
+__device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);  // start address, 16-byte units
+  d |= (uint64_t)1 << 16;                   // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;         // stride byte offset between 8-row groups
+  d |= (uint64_t)1 << 46;                   // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                   // SWIZZLE_128B
+  return d;
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=tf32, K-major both, M=128, N=BN
+__host__ __device__ constexpr uint32_t umma_idesc_tf32(int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+struct TcConv {
+  float* C;
+  const float* bias;
+  float* part;
+  int B, N, K;        // samples, output channels, k*Cin
+  int Lout, nb;       // logical rows per sample, samples per 128-row tile
+  int out_rows, out_off, out_lstride, accumulate;
+};
+
+template <int BN, int STAGES>
+struct TcSmem {
+  static constexpr int A_BYTES = TC_BM * TC_BK * 4;  // 16 KB
+  static constexpr int B_BYTES = BN * TC_BK * 4;
+  static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+  static constexpr int RING_BYTES = STAGES * STAGE_BYTES;
+  static constexpr int EPI_STRIDE = BN + 4;
+  static_assert(TC_BM * EPI_STRIDE * 4 <= RING_BYTES, "epilogue staging must fit in the ring");
+  static constexpr int TOTAL = RING_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
+  static constexpr int TMEM_COLS = BN == 128 ? 512 : 256;  // 3 accumulators of BN columns, power of two
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+    conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapW, TcConv p) {
+  using S = TcSmem<BN, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ring + S::RING_BYTES);
+  uint64_t* full = bars;                 // [STAGES]  TMA bytes landed
+  uint64_t* conv = bars + STAGES;        // [STAGES]  hi/lo split written
+  uint64_t* empty = bars + 2 * STAGES;   // [STAGES]  MMAs that read the stage retired
+  uint64_t* accum = bars + 3 * STAGES;   // accumulator complete
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b0 = blockIdx.x * p.nb, n0 = blockIdx.y * BN;
+  const int nkb = p.K / TC_BK;
+  const int rows_tile = p.nb * p.Lout;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&mapA);
+    tma_prefetch_desc(&mapW);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&conv[s], 128);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(accum, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(S::TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      const uint32_t tx_bytes = (uint32_t)(rows_tile * TC_BK * 4 + S::B_BYTES);
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
+        mbar_wait(&empty[s], ph ^ 1u);
+        uint8_t* st = ring + s * S::STAGE_BYTES;
+        mbar_expect_tx(&full[s], tx_bytes);
+        tma_load_3d(st, &mapA, &full[s], kb * TC_BK, 0, b0);
+        tma_load_2d(st + 2 * S::A_BYTES, &mapW, &full[s], kb * TC_BK, n0);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_tf32(BN);
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
+        mbar_wait(&full[s], ph);
+        mbar_wait(&conv[s], ph);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t st = smem_u32(ring + s * S::STAGE_BYTES);
+        const uint64_t a_hi = umma_desc_k_sw128(st), a_lo = umma_desc_k_sw128(st + S::A_BYTES);
+        const uint64_t b_hi = umma_desc_k_sw128(st + 2 * S::A_BYTES);
+        const uint64_t b_lo = umma_desc_k_sw128(st + 2 * S::A_BYTES + S::B_BYTES);
+#pragma unroll
+        for (int k8 = 0; k8 < TC_BK / 8; ++k8) {
+          const uint64_t adv = (uint64_t)(k8 * 32 >> 4);  // 8 tf32 = 32 bytes along the swizzled row
+          umma_tf32(tmem_base + 2 * BN, a_lo + adv, b_hi + adv, idesc, (kb | k8) != 0 ? 1u : 0u);
+          umma_tf32(tmem_base + 2 * BN, a_hi + adv, b_lo + adv, idesc, 1u);
+          umma_tf32(tmem_base + (kb & 1) * BN, a_hi + adv, b_hi + adv, idesc, (kb >= 2 || k8 != 0) ? 1u : 0u);
+        }
+        umma_commit(&empty[s]);
+      }
+      umma_commit(accum);
+    }
+  } else {
+    // ===================== split (hi / lo) warps, then epilogue =====================
+    const int t = threadIdx.x - 64;  // 0..127
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int s = kb % STAGES;
+      const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
+      mbar_wait(&full[s], ph);
+      uint8_t* st = ring + s * S::STAGE_BYTES;
+      // A: [hi | lo] at st, st + A_BYTES;  W: [hi | lo] at st + 2*A_BYTES, + B_BYTES.  Element-wise on raw bytes,
+      // so the 128-byte swizzle the TMA applied is preserved.
+#pragma unroll
+      for (int i = 0; i < S::A_BYTES / 16 / 128; ++i) {
+        uint4* ph_ = reinterpret_cast<uint4*>(st) + t + i * 128;
+        uint4 v = *ph_, h;
+        h.x = (v.x + 0x1000u) & 0xFFFFE000u, h.y = (v.y + 0x1000u) & 0xFFFFE000u;
+        h.z = (v.z + 0x1000u) & 0xFFFFE000u, h.w = (v.w + 0x1000u) & 0xFFFFE000u;
+        float4 l;
+        l.x = __uint_as_float(v.x) - __uint_as_float(h.x), l.y = __uint_as_float(v.y) - __uint_as_float(h.y);
+        l.z = __uint_as_float(v.z) - __uint_as_float(h.z), l.w = __uint_as_float(v.w) - __uint_as_float(h.w);
+        *ph_ = h;
+        *reinterpret_cast<float4*>(st + S::A_BYTES + (size_t)(t + i * 128) * 16) = l;
+      }
+#pragma unroll
+      for (int i = 0; i < S::B_BYTES / 16 / 128; ++i) {
+        uint4* ph_ = reinterpret_cast<uint4*>(st + 2 * S::A_BYTES) + t + i * 128;
+        uint4 v = *ph_, h;
+        h.x = (v.x + 0x1000u) & 0xFFFFE000u, h.y = (v.y + 0x1000u) & 0xFFFFE000u;
+        h.z = (v.z + 0x1000u) & 0xFFFFE000u, h.w = (v.w + 0x1000u) & 0xFFFFE000u;
+        float4 l;
+        l.x = __uint_as_float(v.x) - __uint_as_float(h.x), l.y = __uint_as_float(v.y) - __uint_as_float(h.y);
+        l.z = __uint_as_float(v.z) - __uint_as_float(h.z), l.w = __uint_as_float(v.w) - __uint_as_float(h.w);
+        *ph_ = h;
+        *reinterpret_cast<float4*>(st + 2 * S::A_BYTES + S::B_BYTES + (size_t)(t + i * 128) * 16) = l;
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the tensor core
+      mbar_arrive(&conv[s]);
+    }
+
+    // ---- epilogue ----
+    mbar_wait(accum, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    float* stage = reinterpret_cast<float*>(ring);  // [128][BN + 4]; the ring is idle once `accum` has fired
+    const int q = warp & 3;                         // TMEM lane quarter this warp may read
+    const int row = q * 32 + lane;
+#pragma unroll
+    for (int c = 0; c < BN / 32; ++c) {
+      uint32_t r[32], r1[32], r2[32];
+      const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32);
+      tmem_ld32(ta, r);
+      tmem_ld32(ta + BN, r1);
+      tmem_ld32(ta + 2 * BN, r2);
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        r[i] = __float_as_uint((__uint_as_float(r[i]) + __uint_as_float(r1[i])) + __uint_as_float(r2[i]));
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        *reinterpret_cast<uint4*>(&stage[row * S::EPI_STRIDE + c * 32 + i * 4]) =
+            make_uint4(r[i * 4], r[i * 4 + 1], r[i * 4 + 2], r[i * 4 + 3]);
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");  // the four epilogue warps only
+
+    const int nvalid = min(rows_tile, (p.B - b0) * p.Lout);  // rows of this tile that are real outputs
+    {  // coalesced stores: thread -> (row group, fixed column quad)
+      constexpr int QUADS = BN / 4;
+      const int quad = t % QUADS;
+      float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (p.bias) bv = *reinterpret_cast<const float4*>(p.bias + n0 + quad * 4);
+      for (int r = t / QUADS; r < nvalid; r += 128 / QUADS) {
+        const int bs = r / p.Lout, l = r - bs * p.Lout;
+        float4 v = *reinterpret_cast<const float4*>(&stage[r * S::EPI_STRIDE + quad * 4]);
+        v.x += bv.x, v.y += bv.y, v.z += bv.z, v.w += bv.w;
+        float4* dst = reinterpret_cast<float4*>(
+            p.C + ((int64_t)(b0 + bs) * p.out_rows + p.out_off + (int64_t)l * p.out_lstride) * p.N + n0 + quad * 4);
+        if (p.accumulate) {
+          const float4 o = *dst;
+          v.x += o.x, v.y += o.y, v.z += o.z, v.w += o.w;
+        }
+        *dst = v;
+      }
+    }
+    if (p.part && t < BN) {  // BatchNorm statistics of this tile: (sum, centred sum of squares) per column
+      const float bias = p.bias ? p.bias[n0 + t] : 0.f;
+      float s = 0.f;
+      for (int r = 0; r < nvalid; ++r) s += stage[r * S::EPI_STRIDE + t];
+      const float mean = s / (float)nvalid;
+      float m2 = 0.f;
+      for (int r = 0; r < nvalid; ++r) {
+        const float d = stage[r * S::EPI_STRIDE + t] - mean;
+        m2 = fmaf(d, d, m2);
+      }
+      *reinterpret_cast<float2*>(p.part + ((int64_t)blockIdx.x * p.N + n0 + t) * 2) =
+          make_float2(s + bias * (float)nvalid, m2);
+    }
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(S::TMEM_COLS) : "memory");
+  }
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Weight gradient on tcgen05:  dW[m, n] += sum_r dY[r, m] * X[(r + roff) * Cin + n]   (split over row ranges)
+//
+// Both operands are "MN-major" for the tensor core: the reduction index r is the slow (row) index of the
+// channels-last tensors.  A tile = 128 output channels x 32 rows is fetched as 4 groups of [32 rows][32 floats]
+// (one 3-D TMA box, 128-byte swizzle), the canonical UMMA Major-MN SWIZZLE_128B layout; one MMA consumes 8 rows.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t umma_desc_mn(uint32_t saddr, uint32_t lbo, uint32_t sbo, uint32_t ltype) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(lbo >> 4) << 16;  // leading byte offset: next group of 32 MN elements
+  d |= (uint64_t)(sbo >> 4) << 32;  // stride byte offset: next group of K rows
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)ltype << 61;
+  return d;
+}
+__host__ __device__ constexpr uint32_t umma_idesc_tf32_mn(int n) {
+  return umma_idesc_tf32(n) | (1u << 15) | (1u << 16);  // A and B MN-major
+}
+
+struct TcWgrad {
+  float* dW;
+  int M, N;            // Cout, k*Cin
+  int R;               // padded rows to reduce over
+  int rows_per_split;  // multiple of TC_BK
+  uint32_t lbo, sbo, ltype;  // shared-memory descriptor fields of the MN-major operands
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+    wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapDY, const __grid_constant__ CUtensorMap mapX, TcWgrad p) {
+  using S = TcSmem<BN, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ring + S::RING_BYTES);
+  uint64_t* full = bars;
+  uint64_t* conv = bars + STAGES;
+  uint64_t* empty = bars + 2 * STAGES;
+  uint64_t* accum = bars + 3 * STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * BN, m0 = blockIdx.y * TC_BM;
+  const int r_begin = blockIdx.z * p.rows_per_split;
+  const int r_end = min(p.R, r_begin + p.rows_per_split);
+  const int nkb = (r_end - r_begin + TC_BK - 1) / TC_BK;  // >= 1 by construction of the grid
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&mapDY);
+    tma_prefetch_desc(&mapX);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&conv[s], 128);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(accum, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "n"(S::TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
+        mbar_wait(&empty[s], ph ^ 1u);
+        uint8_t* st = ring + s * S::STAGE_BYTES;
+        mbar_expect_tx(&full[s], (uint32_t)(S::A_BYTES + S::B_BYTES));
+        // one [32 rows][32 channels] box per group of 32 channels (groups land 4 KB apart = the descriptor's LBO)
+#pragma unroll
+        for (int g = 0; g < TC_BM / 32; ++g)
+          tma_load_2d(st + g * (TC_BK * 128), &mapDY, &full[s], m0 + g * 32, r_begin + kb * TC_BK);
+#pragma unroll
+        for (int g = 0; g < BN / 32; ++g)
+          tma_load_2d(st + 2 * S::A_BYTES + g * (TC_BK * 128), &mapX, &full[s], n0 + g * 32, r_begin + kb * TC_BK);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_tf32_mn(BN);
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
+        mbar_wait(&full[s], ph);
+        mbar_wait(&conv[s], ph);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t st = smem_u32(ring + s * S::STAGE_BYTES);
+        const uint64_t a_hi = umma_desc_mn(st, p.lbo, p.sbo, p.ltype), a_lo = umma_desc_mn(st + S::A_BYTES, p.lbo, p.sbo, p.ltype);
+        const uint64_t b_hi = umma_desc_mn(st + 2 * S::A_BYTES, p.lbo, p.sbo, p.ltype);
+        const uint64_t b_lo = umma_desc_mn(st + 2 * S::A_BYTES + S::B_BYTES, p.lbo, p.sbo, p.ltype);
+#pragma unroll
+        for (int k8 = 0; k8 < TC_BK / 8; ++k8) {
+          const uint64_t adv = (uint64_t)(k8 * 1024 >> 4);  // 8 reduction rows = 8 x 128 B
+          umma_tf32(tmem_base + 2 * BN, a_lo + adv, b_hi + adv, idesc, (kb | k8) != 0 ? 1u : 0u);
+          umma_tf32(tmem_base + 2 * BN, a_hi + adv, b_lo + adv, idesc, 1u);
+          umma_tf32(tmem_base + (kb & 1) * BN, a_hi + adv, b_hi + adv, idesc, (kb >= 2 || k8 != 0) ? 1u : 0u);
+        }
+        umma_commit(&empty[s]);
+      }
+      umma_commit(accum);
+    }
+  } else {
+    const int t = threadIdx.x - 64;
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int s = kb % STAGES;
+      const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
+      mbar_wait(&full[s], ph);
+      uint8_t* st = ring + s * S::STAGE_BYTES;
+#pragma unroll
+      for (int i = 0; i < S::A_BYTES / 16 / 128; ++i) {
+        uint4* ph_ = reinterpret_cast<uint4*>(st) + t + i * 128;
+        uint4 v = *ph_, h;
+        h.x = (v.x + 0x1000u) & 0xFFFFE000u, h.y = (v.y + 0x1000u) & 0xFFFFE000u;
+        h.z = (v.z + 0x1000u) & 0xFFFFE000u, h.w = (v.w + 0x1000u) & 0xFFFFE000u;
+        float4 l;
+        l.x = __uint_as_float(v.x) - __uint_as_float(h.x), l.y = __uint_as_float(v.y) - __uint_as_float(h.y);
+        l.z = __uint_as_float(v.z) - __uint_as_float(h.z), l.w = __uint_as_float(v.w) - __uint_as_float(h.w);
+        *ph_ = h;
+        *reinterpret_cast<float4*>(st + S::A_BYTES + (size_t)(t + i * 128) * 16) = l;
+      }
+#pragma unroll
+      for (int i = 0; i < S::B_BYTES / 16 / 128; ++i) {
+        uint4* ph_ = reinterpret_cast<uint4*>(st + 2 * S::A_BYTES) + t + i * 128;
+        uint4 v = *ph_, h;
+        h.x = (v.x + 0x1000u) & 0xFFFFE000u, h.y = (v.y + 0x1000u) & 0xFFFFE000u;
+        h.z = (v.z + 0x1000u) & 0xFFFFE000u, h.w = (v.w + 0x1000u) & 0xFFFFE000u;
+        float4 l;
+        l.x = __uint_as_float(v.x) - __uint_as_float(h.x), l.y = __uint_as_float(v.y) - __uint_as_float(h.y);
+        l.z = __uint_as_float(v.z) - __uint_as_float(h.z), l.w = __uint_as_float(v.w) - __uint_as_float(h.w);
+        *ph_ = h;
+        *reinterpret_cast<float4*>(st + 2 * S::A_BYTES + S::B_BYTES + (size_t)(t + i * 128) * 16) = l;
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_arrive(&conv[s]);
+    }
+
+    mbar_wait(accum, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    float* stage = reinterpret_cast<float*>(ring);
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const bool two = nkb >= 2;  // the second hi*hi accumulator is only written when there are two k-blocks
+#pragma unroll
+    for (int c = 0; c < BN / 32; ++c) {
+      uint32_t r[32], r1[32], r2[32];
+      const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32);
+      tmem_ld32(ta, r);
+      tmem_ld32(ta + BN, r1);
+      tmem_ld32(ta + 2 * BN, r2);
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        r[i] = __float_as_uint((__uint_as_float(r[i]) + (two ? __uint_as_float(r1[i]) : 0.f)) + __uint_as_float(r2[i]));
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        *reinterpret_cast<uint4*>(&stage[row * S::EPI_STRIDE + c * 32 + i * 4]) =
+            make_uint4(r[i * 4], r[i * 4 + 1], r[i * 4 + 2], r[i * 4 + 3]);
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    const int mvalid = min(TC_BM, p.M - m0);
+    const int col = t % BN;
+    for (int r = t / BN; r < mvalid; r += 128 / BN)
+      atomicAdd(p.dW + (int64_t)(m0 + r) * p.N + n0 + col, stage[r * S::EPI_STRIDE + col]);
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(S::TMEM_COLS) : "memory");
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn g_encode = nullptr;
+// MN-major fp32/tf32 operands: the tensor core transposes at 32-byte granularity, so the pairing is
+// TMA CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B <-> UMMA layout type SWIZZLE_128B_BASE32B (1), groups of 32 channels
+// 4 KB apart (LBO), groups of 4 reduction rows 512 B apart (SBO).  Found by tools/tc_test's probe on a B200: the
+// plain SWIZZLE_128B pairing (type 2) yields zeros for MN-major tf32.
+uint32_t g_wg_lbo = TC_BK * 128, g_wg_sbo = 512, g_wg_ltype = 1;
+CUtensorMapSwizzle g_wg_swz = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
+
+}  // namespace
+
+bool tc_init(std::string* err) {
+  if (g_encode) return true;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) {
+    if (err) *err = "cuTensorMapEncodeTiled is not available from the driver";
+    return false;
+  }
+  g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+  cudaFuncSetAttribute(conv_gemm_tc_kernel<128, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<128, 3>::TOTAL);
+  cudaFuncSetAttribute(conv_gemm_tc_kernel<64, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<64, 4>::TOTAL);
+  cudaFuncSetAttribute(wgrad_tc_kernel<128, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<128, 3>::TOTAL);
+  cudaFuncSetAttribute(wgrad_tc_kernel<64, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<64, 4>::TOTAL);
+  return cudaGetLastError() == cudaSuccess;
+}
+
+// 3-D map over a padded channels-last tensor: (k within the k*Cin window, logical output row, sample)
+bool tc_make_act_map(TcMap* out, const float* base, int in_C, int K, int Lout, int in_rows, int in_stride, int in_off,
+                     int max_batch) {
+  const int nb = TC_BM / Lout;
+  cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)Lout, (cuuint64_t)max_batch};
+  cuuint64_t strides[2] = {(cuuint64_t)in_stride * in_C * 4, (cuuint64_t)in_rows * in_C * 4};
+  cuuint32_t box[3] = {(cuuint32_t)TC_BK, (cuuint32_t)Lout, (cuuint32_t)nb};
+  cuuint32_t estr[3] = {1, 1, 1};
+  void* gptr = const_cast<float*>(base + (int64_t)in_off * in_C);
+  CUresult r = g_encode(reinterpret_cast<CUtensorMap*>(out->opaque), CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, gptr, dims,
+                        strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+// 2-D map over K-major weights [N][K]; box = 32 floats x bn rows
+bool tc_make_weight_map(TcMap* out, const float* w, int N, int K, int bn) {
+  cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)N};
+  cuuint64_t strides[1] = {(cuuint64_t)K * 4};
+  cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)bn};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode(reinterpret_cast<CUtensorMap*>(out->opaque), CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                        const_cast<float*>(w), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+// 2-D map for the wgrad operands: (channel, reduction row) with box 32 channels x 32 rows.  For the input tensor the
+// "row" is the k*Cin-float window starting at that padded row, so consecutive rows overlap (row pitch = Cin floats).
+bool tc_make_rows_map(TcMap* out, const float* base, int row_floats, int channels, int rows, int /*box_groups*/) {
+  cuuint64_t dims[2] = {(cuuint64_t)channels, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)row_floats * 4};
+  cuuint32_t box[2] = {32, (cuuint32_t)TC_BK};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode(reinterpret_cast<CUtensorMap*>(out->opaque), CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                        const_cast<float*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        g_wg_swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+void tc_debug_wgrad_knobs(uint32_t lbo, uint32_t sbo, uint32_t ltype, int tma_swizzle) {
+  g_wg_lbo = lbo, g_wg_sbo = sbo, g_wg_ltype = ltype, g_wg_swz = (CUtensorMapSwizzle)tma_swizzle;
+}
+
+void launch_wgrad_tc(const WgradGemm& g, const TcMap& mapDY, const TcMap& mapX, int bn, int sm_count, cudaStream_t s) {
+  TcWgrad p{};
+  p.dW = g.dW, p.M = g.M, p.N = g.N, p.R = g.R;
+  p.lbo = g_wg_lbo, p.sbo = g_wg_sbo, p.ltype = g_wg_ltype;
+  const int tiles = ((g.M + TC_BM - 1) / TC_BM) * (g.N / bn);
+  int splits = (2 * sm_count + tiles - 1) / tiles;
+  const int kblocks = (g.R + TC_BK - 1) / TC_BK;
+  if (splits > (kblocks + 3) / 4) splits = (kblocks + 3) / 4;  // at least 4 k-blocks (128 rows) per CTA
+  if (splits < 1) splits = 1;
+  int kb_per = (kblocks + splits - 1) / splits;
+  p.rows_per_split = kb_per * TC_BK;
+  splits = (g.R + p.rows_per_split - 1) / p.rows_per_split;
+  dim3 grid(g.N / bn, (g.M + TC_BM - 1) / TC_BM, splits);
+  const CUtensorMap& a = *reinterpret_cast<const CUtensorMap*>(mapDY.opaque);
+  const CUtensorMap& x = *reinterpret_cast<const CUtensorMap*>(mapX.opaque);
+  if (bn == 128)
+    wgrad_tc_kernel<128, 3><<<grid, TC_THREADS, TcSmem<128, 3>::TOTAL, s>>>(a, x, p);
+  else
+    wgrad_tc_kernel<64, 4><<<grid, TC_THREADS, TcSmem<64, 4>::TOTAL, s>>>(a, x, p);
+}
+
+int tc_pick_bn(int B, int N, int Lout, int sm_count) {
+  if (N % 128 != 0) return 64;
+  const int nb = TC_BM / Lout;
+  const int mtiles = (B + nb - 1) / nb;
+  return (mtiles * (N / 128) * 4 >= sm_count * 3) ? 128 : 64;  // fall back to 64-wide tiles when the grid is too small
+}
+
+// returns the number of logical rows per statistics tile
+int launch_conv_gemm_tc(const ConvGemm& g, const TcMap& mapA, const TcMap& mapW, int bn, int B, cudaStream_t s) {
+  TcConv p{};
+  p.C = g.C, p.bias = g.bias, p.part = g.part, p.B = B, p.N = g.N, p.K = g.K, p.Lout = g.Lout;
+  p.nb = TC_BM / g.Lout;
+  p.out_rows = g.out_rows, p.out_off = g.out_off, p.out_lstride = g.out_lstride, p.accumulate = g.accumulate;
+  dim3 grid((B + p.nb - 1) / p.nb, g.N / bn);
+  const CUtensorMap& a = *reinterpret_cast<const CUtensorMap*>(mapA.opaque);
+  const CUtensorMap& w = *reinterpret_cast<const CUtensorMap*>(mapW.opaque);
+  if (bn == 128)
+    conv_gemm_tc_kernel<128, 3><<<grid, TC_THREADS, TcSmem<128, 3>::TOTAL, s>>>(a, w, p);
+  else
+    conv_gemm_tc_kernel<64, 4><<<grid, TC_THREADS, TcSmem<64, 4>::TOTAL, s>>>(a, w, p);
+  return p.nb * g.Lout;
+}
+
+}  // namespace hp

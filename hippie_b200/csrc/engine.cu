@@ -47,6 +47,12 @@ struct Conv {
   int w = -1, b = -1;
   int cin = 0, cout = 0, k = 3, stride = 1;
   int64_t wt_off = -1;
+  int id = -1;
+};
+struct ConvMaps {  // TMA tensor maps of the tcgen05 path, built at first use after hippie_bind
+  TcMap a_fwd, w64, w128, a_dg, wt64, wt128, wg_dy, wg_x4, wg_x2;
+  bool fwd_ready = false, dg_ready = false;
+  int wg_B = -1;  // the wgrad maps bound the reduction rows, so they depend on the batch size
 };
 struct EncBlock {
   Conv c1, c2, cs;
@@ -114,6 +120,10 @@ struct hippie_engine {
   cudaStream_t side = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   int launches = 0;
+  int n_convs = 0;
+  std::vector<ConvMaps> cmaps;
+  bool use_tc = false;  // tcgen05 3xTF32 implicit GEMM for conv forward / dgrad (conv_path 0); false = FP32 SIMT
+  std::string tc_note;
   // profiling aid (bench.py roofline): CUDA events around every implicit-GEMM launch
   struct ProfRec {
     int kind;
@@ -278,6 +288,7 @@ struct hippie_engine {
     c.w = pidx.at(n + ".weight");
     c.b = bias ? pidx.at(n + ".bias") : -1;
     c.cin = cin, c.cout = cout, c.k = k, c.stride = stride;
+    c.id = n_convs++;
     if (need_wt && !cfg.inference_only) {
       c.wt_off = take((int64_t)cout * cin * k);
       WtEntry e;
@@ -464,7 +475,24 @@ struct hippie_engine {
     g.in_rows = acts[in].L + 2, g.in_stride = cv.stride, g.in_off = cv.k == 3 ? 0 : 1, g.in_C = cv.cin;
     g.out_rows = acts[out].L + 2, g.out_off = 1, g.out_lstride = 1, g.accumulate = 0;
     cudaEvent_t pe = prof_begin(br);
-    const int tile = launch_conv_gemm_simt(g, br.st);
+    int tile;
+    if (use_tc && g.Lout <= 128) {
+      ConvMaps& m = cmaps[cv.id];
+      if (!m.fwd_ready) {
+        bool ok = tc_make_act_map(&m.a_fwd, g.A, g.in_C, g.K, g.Lout, g.in_rows, g.in_stride, g.in_off, cfg.max_batch);
+        ok = ok && tc_make_weight_map(&m.w64, g.W, g.N, g.K, 64);
+        if (g.N % 128 == 0) ok = ok && tc_make_weight_map(&m.w128, g.W, g.N, g.K, 128);
+        if (!ok) err = "cuTensorMapEncodeTiled failed (conv forward)", use_tc = false;
+        m.fwd_ready = ok;
+      }
+    }
+    if (use_tc && g.Lout <= 128) {
+      ConvMaps& m = cmaps[cv.id];
+      const int bn = tc_pick_bn(B, g.N, g.Lout, sm_count);
+      tile = launch_conv_gemm_tc(g, m.a_fwd, bn == 128 ? m.w128 : m.w64, bn, B, br.st);
+    } else {
+      tile = launch_conv_gemm_simt(g, br.st);
+    }
     prof_end(pe, 0, 2.0 * g.M * g.N * g.K, br);
     ++launches;
     if (train && bn >= 0) bn_finalize(bn, br.part, (g.M + tile - 1) / tile, tile, g.M, br);
@@ -494,7 +522,23 @@ struct hippie_engine {
     g.in_rows = acts[dy].L + 2, g.in_stride = 1, g.in_off = cv.k == 3 ? 0 : 1, g.in_C = cv.cout;
     g.out_rows = acts[gx].L + 2, g.out_off = 1, g.out_lstride = 1, g.accumulate = accumulate ? 1 : 0;
     cudaEvent_t pe = prof_begin(br);
-    launch_conv_gemm_simt(g, br.st);
+    if (use_tc && g.Lout <= 128) {
+      ConvMaps& m = cmaps[cv.id];
+      if (!m.dg_ready) {
+        bool ok = tc_make_act_map(&m.a_dg, g.A, g.in_C, g.K, g.Lout, g.in_rows, g.in_stride, g.in_off, cfg.max_batch);
+        ok = ok && tc_make_weight_map(&m.wt64, g.W, g.N, g.K, 64);
+        if (g.N % 128 == 0) ok = ok && tc_make_weight_map(&m.wt128, g.W, g.N, g.K, 128);
+        if (!ok) err = "cuTensorMapEncodeTiled failed (conv dgrad)", use_tc = false;
+        m.dg_ready = ok;
+      }
+    }
+    if (use_tc && g.Lout <= 128) {
+      ConvMaps& m = cmaps[cv.id];
+      const int bn = tc_pick_bn(B, g.N, g.Lout, sm_count);
+      launch_conv_gemm_tc(g, m.a_dg, bn == 128 ? m.wt128 : m.wt64, bn, B, br.st);
+    } else {
+      launch_conv_gemm_simt(g, br.st);
+    }
     prof_end(pe, 1, 2.0 * g.M * g.N * g.K, br);
     ++launches;
   }
@@ -503,7 +547,23 @@ struct hippie_engine {
     g.dY = A(dy), g.X = A(x), g.dW = Gp(cv.w);
     g.M = cv.cout, g.N = cv.k * cv.cin, g.R = B * (acts[dy].L + 2), g.Cin = cv.cin, g.roff = cv.k == 3 ? -1 : 0;
     cudaEvent_t pe = prof_begin(br);
-    launch_wgrad_simt(g, sm_count, br.st);
+    if (use_tc) {
+      ConvMaps& m = cmaps[cv.id];
+      if (m.wg_B != B) {
+        bool ok = tc_make_rows_map(&m.wg_dy, g.dY, g.M, g.M, g.R, 4);
+        ok = ok && tc_make_rows_map(&m.wg_x4, g.X + (int64_t)g.roff * g.Cin, g.Cin, g.N, g.R, 4);
+        ok = ok && tc_make_rows_map(&m.wg_x2, g.X + (int64_t)g.roff * g.Cin, g.Cin, g.N, g.R, 2);
+        if (!ok) err = "cuTensorMapEncodeTiled failed (conv wgrad)", use_tc = false;
+        m.wg_B = ok ? B : -1;
+      }
+    }
+    if (use_tc) {
+      ConvMaps& m = cmaps[cv.id];
+      const int bn = (g.N % 128 == 0) ? 128 : 64;
+      launch_wgrad_tc(g, m.wg_dy, bn == 128 ? m.wg_x4 : m.wg_x2, bn, sm_count, br.st);
+    } else {
+      launch_wgrad_simt(g, sm_count, br.st);
+    }
     // algorithmic FLOPs: only the B*Lout real output rows contribute (pad / dilation rows are zeros)
     prof_end(pe, 2, 2.0 * (double)g.M * g.N * (double)B * acts[dy].L / (cv.stride == 2 ? 2.0 : 1.0), br);
     ++launches;
@@ -822,6 +882,12 @@ int hippie_bind(hippie_handle h, float* params, float* grads, float* exp_avg, fl
     cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming);
   }
   cudaMemsetAsync(workspace, 0, (size_t)h->ws_floats * sizeof(float), st);
+  h->cmaps.assign(h->n_convs, ConvMaps{});
+  h->use_tc = false;
+  if (h->cfg.conv_path != 1) {
+    h->use_tc = tc_init(&h->tc_note);
+    if (!h->use_tc && h->cfg.conv_path == 2) return h->fail(-8, "tcgen05 path requested but unavailable: " + h->tc_note);
+  }
   if (!h->wt_table.empty())
     cudaMemcpyAsync(h->ws + h->wt_table_off, h->wt_table.data(), h->wt_table.size() * sizeof(WtEntry),
                     cudaMemcpyHostToDevice, st);
@@ -907,6 +973,8 @@ int hippie_clip_adamw(hippie_handle h, float lr, float beta1, float beta2, float
 }
 
 int hippie_last_launch_count(hippie_handle h) { return h ? h->launches : -1; }
+
+int hippie_conv_path_in_use(hippie_handle h) { return h ? (h->use_tc ? 2 : 1) : -1; }
 
 int hippie_profile(hippie_handle h, int enable) {
   if (!h) return -1;

@@ -10,6 +10,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <string>
+
 namespace hp {
 
 constexpr float kSlopeBackbone = 0.01f;  // F.leaky_relu default  (reference hippie/backbones.py:37,40,66,69,95)
@@ -39,6 +41,21 @@ struct ConvGemm {
 };
 // returns the number of logical rows per statistics tile (BM) it used
 int launch_conv_gemm_simt(const ConvGemm& g, cudaStream_t s);
+
+// ---- tcgen05 path (conv_tc.cu): TMA tensor maps are built on the host at first use ----------------------
+struct alignas(64) TcMap {
+  unsigned char opaque[128];  // CUtensorMap
+};
+bool tc_init(std::string* err);  // resolves cuTensorMapEncodeTiled through the runtime; sets kernel attributes
+bool tc_make_act_map(TcMap* out, const float* base, int in_C, int K, int Lout, int in_rows, int in_stride, int in_off,
+                     int max_batch);
+bool tc_make_weight_map(TcMap* out, const float* w, int N, int K, int bn);
+int tc_pick_bn(int B, int N, int Lout, int sm_count);
+struct WgradGemm;
+bool tc_make_rows_map(TcMap* out, const float* base, int row_floats, int channels, int rows, int box_groups);
+void tc_debug_wgrad_knobs(uint32_t lbo, uint32_t sbo, uint32_t ltype, int tma_swizzle);  // tools/tc_test only
+void launch_wgrad_tc(const WgradGemm& g, const TcMap& mapDY, const TcMap& mapX, int bn, int sm_count, cudaStream_t s);
+int launch_conv_gemm_tc(const ConvGemm& g, const TcMap& mapA, const TcMap& mapW, int bn, int B, cudaStream_t s);
 
 // ---- weight gradient:  dW[m, n] += sum_r dY[r, m] * X[(r + roff) * Cin + n]  (split-K, atomics) -------
 struct WgradGemm {

@@ -213,6 +213,10 @@ class Engine:
                                               1 if has_cls_grad else 0, _ptr(scalars), self._stream()))
         return scalars
 
+    def conv_path_in_use(self) -> int:
+        """2 = tcgen05 3xTF32 implicit GEMM, 1 = FP32 CUDA-core GEMM (valid after allocate())."""
+        return int(self._L.hippie_conv_path_in_use(self._h))
+
     def last_launch_count(self) -> int:
         return int(self._L.hippie_last_launch_count(self._h))
 

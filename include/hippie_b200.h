@@ -46,7 +46,8 @@ typedef struct hippie_cfg {
   int32_t multimodal; /* 1 = MultiModalCVAE, 0 = hippieUnimodalCVAE                             */
   int32_t max_batch;  /* largest B any call will pass; sizes the workspace                      */
   int32_t inference_only; /* 1 = no gradient tensors in the workspace (embedding engines)      */
-  int32_t conv_path;  /* 0 = auto (tcgen05 where available), 1 = force the FP32 CUDA-core GEMM  */
+  int32_t conv_path;  /* 0 = auto (tcgen05 3xTF32, FP32 CUDA-core GEMM if TMA maps are unavailable),
+                         1 = force the FP32 CUDA-core GEMM, 2 = require tcgen05 (bind fails otherwise)   */
 } hippie_cfg;
 
 /* Layout kinds of a parameter inside the flat buffer. */
@@ -137,6 +138,9 @@ int hippie_embed(hippie_handle h, const float* x1, const float* x2, const int64_
 
 /* Number of kernel launches issued by the most recent call of each kind (bench.py gpu_launches). */
 int hippie_last_launch_count(hippie_handle h);
+
+/* 2 = the tcgen05 3xTF32 implicit GEMM serves conv forward / dgrad, 1 = the FP32 CUDA-core GEMM does. */
+int hippie_conv_path_in_use(hippie_handle h);
 
 /* Measurement aid for bench.py (not part of the reference interface): when enabled, every implicit-GEMM launch
  * (kind 0 = conv forward, 1 = dgrad, 2 = wgrad) of the following calls is bracketed by CUDA events on the stream it

@@ -144,6 +144,7 @@ def run_train_case(cfg, B, labelled, seed=1234, beta=0.5, w1=1.0, w2=1.0, lr=1e-
         e = (grads[n].double() - ref).norm().item()
         r = (g32[n].double() - ref).norm().item()
         gerr[n] = (e, r, ref.norm().item())
+        res.setdefault("grad_dbg", {})[n] = (grads[n].double().norm().item(), (grads[n].double() * ref).sum().item() / (grads[n].double().norm().item() * ref.norm().item() + 1e-300))
         flat_e += e * e
         flat_r += r * r
         flat_n += ref.norm().item() ** 2

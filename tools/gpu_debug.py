@@ -27,6 +27,7 @@ def main():
         cfg, B, lab = CASES[name]
         t0 = time.time()
         res, eng = U.run_train_case(cfg, B, lab, conv_path=int(os.environ.get("CONV_PATH", "0")))
+        print("conv path in use:", eng.conv_path_in_use())
         print(f"=== {name}  ({time.time() - t0:.1f}s)  launches fwd+bwd {res['launches_fwd_bwd']} opt {res['launches_opt']}")
         print("loss eng", res["loss_eng"])
         print("loss f64", res["loss_f64"])
@@ -46,7 +47,7 @@ def main():
                 bad.append((n, e, r, nn))
         print("grad tensors outside 3x oracle-f32 noise:", len(bad), "of", len(res["grad_err"]))
         for n, e, r, nn in bad[:60]:
-            print("   GRAD %-55s err %.3e  f32err %.3e  norm %.3e" % (n, e, r, nn))
+            print("   GRAD %-55s err %.3e  f32err %.3e  norm %.3e  eng_norm %.3e cos %.4f" % ((n, e, r, nn) + res["grad_dbg"][n]))
         print("params with spurious grad:", res["no_grad_params"])
         print("running stats rel err %.2e | grad norm eng %.6f f64 %.6f | clip eng %.6f f64 %.6f" % (
             res["running_err"], res["grad_norm_eng"], res["grad_norm_f64"], res["clip_eng"], res["clip_f64"]))
