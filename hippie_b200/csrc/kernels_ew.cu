@@ -387,21 +387,32 @@ __global__ void __launch_bounds__(128) pool_linear_bwd_x_kernel(const float* __r
   }
 }
 
-// dW[f][c] = sum_b dh[b][f] * pooled[b][c];  db[f] = sum_b dh[b][f].   grid = F, block = 256
+// dW[j][i] = sum_b dy[b][j] * x[b][i];  db[j] = sum_b dy[b][j]   (column i == nin is the bias).
+// 64 outputs per CTA, the batch reduction is split over 4 thread groups and combined in shared memory.
 __global__ void __launch_bounds__(256) linear_wgrad_rows_kernel(const float* __restrict__ dy, int ldy,
                                                                 const float* __restrict__ x, int ldx, int B, int nin,
-                                                                float* __restrict__ dW, float* __restrict__ db) {
-  const int f = blockIdx.x;
-  for (int c = threadIdx.x; c < nin; c += blockDim.x) {
-    float s = 0.f;
-    for (int b = 0; b < B; ++b) s = fmaf(__ldg(dy + (int64_t)b * ldy + f), __ldg(x + (int64_t)b * ldx + c), s);
-    dW[(int64_t)f * nin + c] = s;
+                                                                int nout, float* __restrict__ dW,
+                                                                float* __restrict__ db) {
+  __shared__ float red[4][64];
+  const int o = threadIdx.x & 63, bg = threadIdx.x >> 6;
+  const int idx = blockIdx.x * 64 + o;
+  const int j = idx / (nin + 1), i = idx - j * (nin + 1);
+  float s = 0.f;
+  if (j < nout) {
+    if (i < nin) {
+      for (int b = bg; b < B; b += 4) s = fmaf(__ldg(dy + (int64_t)b * ldy + j), __ldg(x + (int64_t)b * ldx + i), s);
+    } else {
+      for (int b = bg; b < B; b += 4) s += __ldg(dy + (int64_t)b * ldy + j);
+    }
   }
-  if (threadIdx.x < 32 && db) {
-    float s = 0.f;
-    for (int b = threadIdx.x; b < B; b += 32) s += dy[(int64_t)b * ldy + f];
-    s = warp_sum(s);
-    if (threadIdx.x == 0) db[f] = s;
+  red[bg][o] = s;
+  __syncthreads();
+  if (bg == 0 && j < nout) {
+    s = (red[0][o] + red[1][o]) + (red[2][o] + red[3][o]);
+    if (i < nin)
+      dW[(int64_t)j * nin + i] = s;
+    else if (db)
+      db[j] = s;
   }
 }
 
@@ -755,7 +766,7 @@ void launch_pool_linear_fwd(const float* x4, int B, int L, int C, const float* W
 void launch_pool_linear_bwd(const float* dh, const float* pooled, const float* W, int B, int L, int C, int F,
                             float* g_x4, float* dW, float* db, cudaStream_t s) {
   pool_linear_bwd_x_kernel<<<B, 128, F * sizeof(float), s>>>(dh, W, L, C, F, g_x4);
-  linear_wgrad_rows_kernel<<<F, 256, 0, s>>>(dh, F, pooled, C, B, C, dW, db);
+  linear_wgrad_rows_kernel<<<(F * (C + 1) + 63) / 64, 256, 0, s>>>(dh, F, pooled, C, B, C, F, dW, db);
 }
 void launch_dec_linear_fwd(const float* d, int B, int F, const float* W, const float* bias, int C, float* t0,
                            float* /*t0_up*/, cudaStream_t s) {
@@ -765,7 +776,7 @@ void launch_dec_linear_bwd(const float* g_t0, const float* d, const float* W, in
                            float* dd, float* dW, float* db, cudaStream_t s) {
   dec_linear_bwd_x_kernel<<<B, 256, C * sizeof(float), s>>>(g_t0, W, F, C, gx0, dd);
   // dW[c][f] = sum_b gx0[b][c] * d[b][f];  db[c] = sum_b gx0[b][c]
-  linear_wgrad_rows_kernel<<<C, 128, 0, s>>>(gx0, C, d, F, B, F, dW, db);
+  linear_wgrad_rows_kernel<<<(C * (F + 1) + 63) / 64, 256, 0, s>>>(gx0, C, d, F, B, F, C, dW, db);
 }
 static size_t dec_tail_smem(int Lo) { return (size_t)(34 * 65 + Lo * 65 + 64 + ((Lo + 3) & ~3) + 68 + 192) * sizeof(float); }
 int launch_dec_tail(const DecTail& t, cudaStream_t s) {

@@ -268,6 +268,7 @@ def _block_enc(cx: _Ctx, p: str, x, stride):
     out = _conv1d(cx, p + ".conv1", x, stride, 1)
     cx.taps[p + ".conv1"] = out
     out = _lrelu(_bn_apply(cx, p + ".bn1", out), SLOPE_BACKBONE)
+    cx.taps[p + ".a1"] = out
     out = _conv1d(cx, p + ".conv2", out, 1, 1)
     out = _bn_apply(cx, p + ".bn2", out)
     if stride == 1:
@@ -296,6 +297,7 @@ def _block_dec(cx: _Ctx, p: str, x, stride):
     # BasicBlockDec.forward (backbones.py:65-70); ResizeConv1d.forward (:13-16)
     out = _conv1d(cx, p + ".conv2", x, 1, 1)
     out = _lrelu(_bn_apply(cx, p + ".bn2", out), SLOPE_BACKBONE)
+    cx.taps[p + ".a2"] = out
     if stride == 1:
         out = _bn_apply(cx, p + ".bn1", _conv1d(cx, p + ".conv1", out, 1, 1))
         sc = x

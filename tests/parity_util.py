@@ -120,6 +120,15 @@ def run_train_case(cfg, B, labelled, seed=1234, beta=0.5, w1=1.0, w2=1.0, lr=1e-
             tap_err[name] = ((got.double() - ref).abs().max().item() / scale,
                              (taps32[name].double() - ref).abs().max().item() / scale)
     res["tap_err"] = tap_err
+    # LeakyReLU sites whose sign differs from the fp64 oracle: each such element changes its local derivative by a
+    # factor of 100, so gradients are only comparable tightly when there is none
+    flips_eng = flips_f32 = 0
+    for name, ref in taps64.items():
+        if name in tap_names and ref.dim() == 3 and not name.endswith(".conv1") and not name.endswith(".linear"):
+            got = eng.tensor_view(name, B).detach().cpu()
+            flips_eng += int(((got > 0) != (ref > 0)).sum())
+            flips_f32 += int(((taps32[name] > 0) != (ref > 0)).sum())
+    res["flips_eng"], res["flips_f32"] = flips_eng, flips_f32
     out_err = {}
     for k in ("enc", "mu", "logvar", "dec1", "dec2"):
         if k in info64["out"]:

@@ -27,7 +27,7 @@ def oracle_tap_grads(cfg, st, x1, x2, labels, eps, dt, beta=0.5):
 
 
 def main():
-    cfg = O.CVAEConfig(z_dim=10)
+    cfg = O.CVAEConfig(z_dim=int(os.environ.get("Z", "10")))
     B = int(os.environ.get("B", "48"))
     x1, x2, labels, eps = U.case_inputs(cfg, B, False)
     st = U.perturbed_state(cfg)
@@ -51,6 +51,20 @@ def main():
                 e = (got - ref).norm().item() / (ref.norm().item() + 1e-300)
                 r = (g32[k].double() - ref).norm().item() / (ref.norm().item() + 1e-300)
                 print("%-45s %10.3e %10.3e %10.3e" % (pref + k, e, r, ref.norm().item()))
+    # LeakyReLU mask flips: elements whose sign differs between the engine and the fp64 oracle
+    print("---- sign mismatches (engine vs f64 / f32 vs f64): count, max |ref| at a mismatch")
+    tot_e = tot_r = 0
+    for k, ref in t64.items():
+        if ref.dim() == 3 and k in names and not k.endswith("conv1") and not k.endswith("linear"):
+            got = eng.tensor_view(k, B).detach().cpu().double()
+            mm = (got > 0) != (ref.detach() > 0)
+            mr = (t32[k].detach() > 0) != (ref.detach() > 0)
+            tot_e += int(mm.sum()); tot_r += int(mr.sum())
+            if mm.any() or mr.any():
+                print("%-40s eng %3d (max|ref| %.2e)   f32 %3d (max|ref| %.2e)  of %d" % (
+                    k, int(mm.sum()), ref.detach().abs()[mm].max().item() if mm.any() else 0.0, int(mr.sum()),
+                    ref.detach().abs()[mr].max().item() if mr.any() else 0.0, ref.numel()))
+    print("total sign mismatches: engine %d, oracle-f32 %d" % (tot_e, tot_r))
     # forward taps, relative L2
     print("---- forward taps rel L2 (eng, f32)")
     for k, ref in t64.items():
