@@ -122,24 +122,30 @@ struct TcConv {
   int B, N, K;        // samples, output channels, k*Cin
   int Lout, nb;       // logical rows per sample, samples per 128-row tile
   int out_rows, out_off, out_lstride, accumulate;
+  int dbg;  // tools/tc_test timing experiments: 1 = skip the hi/lo split, 2 = hi*hi MMA only
 };
 
-template <int BN, int STAGES>
+// PASSES = 3: fp32-accurate 3xTF32 (stage = A_hi | A_lo | W_hi | W_lo);  PASSES = 1: single tf32 pass with
+// round-to-nearest operands (stage = A | W), used for the backward GEMMs in the fast-backward mode.
+template <int BN, int STAGES, int PASSES>
 struct TcSmem {
   static constexpr int A_BYTES = TC_BM * TC_BK * 4;  // 16 KB
   static constexpr int B_BYTES = BN * TC_BK * 4;
-  static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+  static constexpr int A_LO = A_BYTES;                             // offset of A_lo (3-pass only)
+  static constexpr int B_OFF = PASSES == 3 ? 2 * A_BYTES : A_BYTES;  // offset of W (hi)
+  static constexpr int B_LO = B_OFF + B_BYTES;                     // offset of W_lo (3-pass only)
+  static constexpr int STAGE_BYTES = PASSES == 3 ? 2 * A_BYTES + 2 * B_BYTES : A_BYTES + B_BYTES;
   static constexpr int RING_BYTES = STAGES * STAGE_BYTES;
   static constexpr int EPI_STRIDE = BN + 4;
   static_assert(TC_BM * EPI_STRIDE * 4 <= RING_BYTES, "epilogue staging must fit in the ring");
   static constexpr int TOTAL = RING_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
-  static constexpr int TMEM_COLS = BN == 128 ? 512 : 256;  // 3 accumulators of BN columns, power of two
+  static constexpr int TMEM_COLS = PASSES == 3 ? (BN == 128 ? 512 : 256) : 2 * BN;  // 3 (or 2) accumulators
 };
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int PASSES>
 __global__ void __launch_bounds__(TC_THREADS, 1)
     conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapW, TcConv p) {
-  using S = TcSmem<BN, STAGES>;
+  using S = TcSmem<BN, STAGES, PASSES>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = reinterpret_cast<uint64_t*>(ring + S::RING_BYTES);
@@ -186,7 +192,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         uint8_t* st = ring + s * S::STAGE_BYTES;
         mbar_expect_tx(&full[s], tx_bytes);
         tma_load_3d(st, &mapA, &full[s], kb * TC_BK, 0, b0);
-        tma_load_2d(st + 2 * S::A_BYTES, &mapW, &full[s], kb * TC_BK, n0);
+        tma_load_2d(st + S::B_OFF, &mapW, &full[s], kb * TC_BK, n0);
       }
     }
   } else if (warp == 1) {
@@ -200,14 +206,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         mbar_wait(&conv[s], ph);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t st = smem_u32(ring + s * S::STAGE_BYTES);
-        const uint64_t a_hi = umma_desc_k_sw128(st), a_lo = umma_desc_k_sw128(st + S::A_BYTES);
-        const uint64_t b_hi = umma_desc_k_sw128(st + 2 * S::A_BYTES);
-        const uint64_t b_lo = umma_desc_k_sw128(st + 2 * S::A_BYTES + S::B_BYTES);
+        const uint64_t a_hi = umma_desc_k_sw128(st), a_lo = umma_desc_k_sw128(st + S::A_LO);
+        const uint64_t b_hi = umma_desc_k_sw128(st + S::B_OFF), b_lo = umma_desc_k_sw128(st + S::B_LO);
 #pragma unroll
         for (int k8 = 0; k8 < TC_BK / 8; ++k8) {
           const uint64_t adv = (uint64_t)(k8 * 32 >> 4);  // 8 tf32 = 32 bytes along the swizzled row
-          umma_tf32(tmem_base + 2 * BN, a_lo + adv, b_hi + adv, idesc, (kb | k8) != 0 ? 1u : 0u);
-          umma_tf32(tmem_base + 2 * BN, a_hi + adv, b_lo + adv, idesc, 1u);
+          if (PASSES == 3 && !(p.dbg & 2)) {
+            umma_tf32(tmem_base + 2 * BN, a_lo + adv, b_hi + adv, idesc, (kb | k8) != 0 ? 1u : 0u);
+            umma_tf32(tmem_base + 2 * BN, a_hi + adv, b_lo + adv, idesc, 1u);
+          }
           umma_tf32(tmem_base + (kb & 1) * BN, a_hi + adv, b_hi + adv, idesc, (kb >= 2 || k8 != 0) ? 1u : 0u);
         }
         umma_commit(&empty[s]);
@@ -224,29 +231,35 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       uint8_t* st = ring + s * S::STAGE_BYTES;
       // A: [hi | lo] at st, st + A_BYTES;  W: [hi | lo] at st + 2*A_BYTES, + B_BYTES.  Element-wise on raw bytes,
       // so the 128-byte swizzle the TMA applied is preserved.
+      if (p.dbg & 1) {
+        mbar_arrive(&conv[s]);
+        continue;
+      }
 #pragma unroll
       for (int i = 0; i < S::A_BYTES / 16 / 128; ++i) {
         uint4* ph_ = reinterpret_cast<uint4*>(st) + t + i * 128;
         uint4 v = *ph_, h;
-        h.x = (v.x + 0x1000u) & 0xFFFFE000u, h.y = (v.y + 0x1000u) & 0xFFFFE000u;
-        h.z = (v.z + 0x1000u) & 0xFFFFE000u, h.w = (v.w + 0x1000u) & 0xFFFFE000u;
+        const uint32_t rb = (p.dbg & 4) ? 0u : 0x1000u;  // dbg 4: truncate and leave the raw value as hi
+        h.x = (v.x + rb) & 0xFFFFE000u, h.y = (v.y + rb) & 0xFFFFE000u;
+        h.z = (v.z + rb) & 0xFFFFE000u, h.w = (v.w + rb) & 0xFFFFE000u;
         float4 l;
         l.x = __uint_as_float(v.x) - __uint_as_float(h.x), l.y = __uint_as_float(v.y) - __uint_as_float(h.y);
         l.z = __uint_as_float(v.z) - __uint_as_float(h.z), l.w = __uint_as_float(v.w) - __uint_as_float(h.w);
-        *ph_ = h;
-        *reinterpret_cast<float4*>(st + S::A_BYTES + (size_t)(t + i * 128) * 16) = l;
+        if (!(p.dbg & 4)) *ph_ = h;
+        if (PASSES == 3) *reinterpret_cast<float4*>(st + S::A_LO + (size_t)(t + i * 128) * 16) = l;
       }
 #pragma unroll
       for (int i = 0; i < S::B_BYTES / 16 / 128; ++i) {
-        uint4* ph_ = reinterpret_cast<uint4*>(st + 2 * S::A_BYTES) + t + i * 128;
+        uint4* ph_ = reinterpret_cast<uint4*>(st + S::B_OFF) + t + i * 128;
         uint4 v = *ph_, h;
-        h.x = (v.x + 0x1000u) & 0xFFFFE000u, h.y = (v.y + 0x1000u) & 0xFFFFE000u;
-        h.z = (v.z + 0x1000u) & 0xFFFFE000u, h.w = (v.w + 0x1000u) & 0xFFFFE000u;
+        const uint32_t rb = (p.dbg & 4) ? 0u : 0x1000u;
+        h.x = (v.x + rb) & 0xFFFFE000u, h.y = (v.y + rb) & 0xFFFFE000u;
+        h.z = (v.z + rb) & 0xFFFFE000u, h.w = (v.w + rb) & 0xFFFFE000u;
         float4 l;
         l.x = __uint_as_float(v.x) - __uint_as_float(h.x), l.y = __uint_as_float(v.y) - __uint_as_float(h.y);
         l.z = __uint_as_float(v.z) - __uint_as_float(h.z), l.w = __uint_as_float(v.w) - __uint_as_float(h.w);
-        *ph_ = h;
-        *reinterpret_cast<float4*>(st + 2 * S::A_BYTES + S::B_BYTES + (size_t)(t + i * 128) * 16) = l;
+        if (!(p.dbg & 4)) *ph_ = h;
+        if (PASSES == 3) *reinterpret_cast<float4*>(st + S::B_LO + (size_t)(t + i * 128) * 16) = l;
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the tensor core
       mbar_arrive(&conv[s]);
@@ -264,7 +277,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32);
       tmem_ld32(ta, r);
       tmem_ld32(ta + BN, r1);
-      tmem_ld32(ta + 2 * BN, r2);
+      if (PASSES == 3) {
+        tmem_ld32(ta + 2 * BN, r2);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) r2[i] = 0u;
+      }
 #pragma unroll
       for (int i = 0; i < 32; ++i)
         r[i] = __float_as_uint((__uint_as_float(r[i]) + __uint_as_float(r1[i])) + __uint_as_float(r2[i]));
@@ -296,14 +314,28 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     }
     if (p.part && t < BN) {  // BatchNorm statistics of this tile: (sum, centred sum of squares) per column
       const float bias = p.bias ? p.bias[n0 + t] : 0.f;
-      float s = 0.f;
-      for (int r = 0; r < nvalid; ++r) s += stage[r * S::EPI_STRIDE + t];
-      const float mean = s / (float)nvalid;
-      float m2 = 0.f;
-      for (int r = 0; r < nvalid; ++r) {
-        const float d = stage[r * S::EPI_STRIDE + t] - mean;
-        m2 = fmaf(d, d, m2);
+      // four independent partial sums keep the shared-memory loads in flight (a single dependent chain of
+      // 128 adds costs ~4 us per tile)
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+      int r = 0;
+      for (; r + 4 <= nvalid; r += 4) {
+        s0 += stage[(r + 0) * S::EPI_STRIDE + t], s1 += stage[(r + 1) * S::EPI_STRIDE + t];
+        s2 += stage[(r + 2) * S::EPI_STRIDE + t], s3 += stage[(r + 3) * S::EPI_STRIDE + t];
       }
+      for (; r < nvalid; ++r) s0 += stage[r * S::EPI_STRIDE + t];
+      const float s = (s0 + s1) + (s2 + s3);
+      const float mean = s / (float)nvalid;
+      float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
+      for (r = 0; r + 4 <= nvalid; r += 4) {
+        const float d0 = stage[(r + 0) * S::EPI_STRIDE + t] - mean, d1 = stage[(r + 1) * S::EPI_STRIDE + t] - mean;
+        const float d2 = stage[(r + 2) * S::EPI_STRIDE + t] - mean, d3 = stage[(r + 3) * S::EPI_STRIDE + t] - mean;
+        q0 = fmaf(d0, d0, q0), q1 = fmaf(d1, d1, q1), q2 = fmaf(d2, d2, q2), q3 = fmaf(d3, d3, q3);
+      }
+      for (; r < nvalid; ++r) {
+        const float d = stage[r * S::EPI_STRIDE + t] - mean;
+        q0 = fmaf(d, d, q0);
+      }
+      const float m2 = (q0 + q1) + (q2 + q3);
       *reinterpret_cast<float2*>(p.part + ((int64_t)blockIdx.x * p.N + n0 + t) * 2) =
           make_float2(s + bias * (float)nvalid, m2);
     }
@@ -345,10 +377,10 @@ struct TcWgrad {
   uint32_t lbo, sbo, ltype;  // shared-memory descriptor fields of the MN-major operands
 };
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int PASSES>
 __global__ void __launch_bounds__(TC_THREADS, 1)
     wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapDY, const __grid_constant__ CUtensorMap mapX, TcWgrad p) {
-  using S = TcSmem<BN, STAGES>;
+  using S = TcSmem<BN, STAGES, PASSES>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = reinterpret_cast<uint64_t*>(ring + S::RING_BYTES);
@@ -400,7 +432,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
           tma_load_2d(st + g * (TC_BK * 128), &mapDY, &full[s], m0 + g * 32, r_begin + kb * TC_BK);
 #pragma unroll
         for (int g = 0; g < BN / 32; ++g)
-          tma_load_2d(st + 2 * S::A_BYTES + g * (TC_BK * 128), &mapX, &full[s], n0 + g * 32, r_begin + kb * TC_BK);
+          tma_load_2d(st + S::B_OFF + g * (TC_BK * 128), &mapX, &full[s], n0 + g * 32, r_begin + kb * TC_BK);
       }
     }
   } else if (warp == 1) {
@@ -413,14 +445,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         mbar_wait(&conv[s], ph);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t st = smem_u32(ring + s * S::STAGE_BYTES);
-        const uint64_t a_hi = umma_desc_mn(st, p.lbo, p.sbo, p.ltype), a_lo = umma_desc_mn(st + S::A_BYTES, p.lbo, p.sbo, p.ltype);
-        const uint64_t b_hi = umma_desc_mn(st + 2 * S::A_BYTES, p.lbo, p.sbo, p.ltype);
-        const uint64_t b_lo = umma_desc_mn(st + 2 * S::A_BYTES + S::B_BYTES, p.lbo, p.sbo, p.ltype);
+        const uint64_t a_hi = umma_desc_mn(st, p.lbo, p.sbo, p.ltype), a_lo = umma_desc_mn(st + S::A_LO, p.lbo, p.sbo, p.ltype);
+        const uint64_t b_hi = umma_desc_mn(st + S::B_OFF, p.lbo, p.sbo, p.ltype);
+        const uint64_t b_lo = umma_desc_mn(st + S::B_LO, p.lbo, p.sbo, p.ltype);
 #pragma unroll
         for (int k8 = 0; k8 < TC_BK / 8; ++k8) {
           const uint64_t adv = (uint64_t)(k8 * 1024 >> 4);  // 8 reduction rows = 8 x 128 B
-          umma_tf32(tmem_base + 2 * BN, a_lo + adv, b_hi + adv, idesc, (kb | k8) != 0 ? 1u : 0u);
-          umma_tf32(tmem_base + 2 * BN, a_hi + adv, b_lo + adv, idesc, 1u);
+          if (PASSES == 3) {
+            umma_tf32(tmem_base + 2 * BN, a_lo + adv, b_hi + adv, idesc, (kb | k8) != 0 ? 1u : 0u);
+            umma_tf32(tmem_base + 2 * BN, a_hi + adv, b_lo + adv, idesc, 1u);
+          }
           umma_tf32(tmem_base + (kb & 1) * BN, a_hi + adv, b_hi + adv, idesc, (kb >= 2 || k8 != 0) ? 1u : 0u);
         }
         umma_commit(&empty[s]);
@@ -444,11 +478,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         l.x = __uint_as_float(v.x) - __uint_as_float(h.x), l.y = __uint_as_float(v.y) - __uint_as_float(h.y);
         l.z = __uint_as_float(v.z) - __uint_as_float(h.z), l.w = __uint_as_float(v.w) - __uint_as_float(h.w);
         *ph_ = h;
-        *reinterpret_cast<float4*>(st + S::A_BYTES + (size_t)(t + i * 128) * 16) = l;
+        if (PASSES == 3) *reinterpret_cast<float4*>(st + S::A_LO + (size_t)(t + i * 128) * 16) = l;
       }
 #pragma unroll
       for (int i = 0; i < S::B_BYTES / 16 / 128; ++i) {
-        uint4* ph_ = reinterpret_cast<uint4*>(st + 2 * S::A_BYTES) + t + i * 128;
+        uint4* ph_ = reinterpret_cast<uint4*>(st + S::B_OFF) + t + i * 128;
         uint4 v = *ph_, h;
         h.x = (v.x + 0x1000u) & 0xFFFFE000u, h.y = (v.y + 0x1000u) & 0xFFFFE000u;
         h.z = (v.z + 0x1000u) & 0xFFFFE000u, h.w = (v.w + 0x1000u) & 0xFFFFE000u;
@@ -456,7 +490,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         l.x = __uint_as_float(v.x) - __uint_as_float(h.x), l.y = __uint_as_float(v.y) - __uint_as_float(h.y);
         l.z = __uint_as_float(v.z) - __uint_as_float(h.z), l.w = __uint_as_float(v.w) - __uint_as_float(h.w);
         *ph_ = h;
-        *reinterpret_cast<float4*>(st + 2 * S::A_BYTES + S::B_BYTES + (size_t)(t + i * 128) * 16) = l;
+        if (PASSES == 3) *reinterpret_cast<float4*>(st + S::B_LO + (size_t)(t + i * 128) * 16) = l;
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       mbar_arrive(&conv[s]);
@@ -474,7 +508,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32);
       tmem_ld32(ta, r);
       tmem_ld32(ta + BN, r1);
-      tmem_ld32(ta + 2 * BN, r2);
+      if (PASSES == 3) {
+        tmem_ld32(ta + 2 * BN, r2);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) r2[i] = 0u;
+      }
 #pragma unroll
       for (int i = 0; i < 32; ++i)
         r[i] = __float_as_uint((__uint_as_float(r[i]) + (two ? __uint_as_float(r1[i]) : 0.f)) + __uint_as_float(r2[i]));
@@ -501,6 +540,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 EncodeTiledFn g_encode = nullptr;
+int g_conv_dbg = 0;
 // MN-major fp32/tf32 operands: the tensor core transposes at 32-byte granularity, so the pairing is
 // TMA CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B <-> UMMA layout type SWIZZLE_128B_BASE32B (1), groups of 32 channels
 // 4 KB apart (LBO), groups of 4 reduction rows 512 B apart (SBO).  Found by tools/tc_test's probe on a B200: the
@@ -520,10 +560,13 @@ bool tc_init(std::string* err) {
     return false;
   }
   g_encode = reinterpret_cast<EncodeTiledFn>(fn);
-  cudaFuncSetAttribute(conv_gemm_tc_kernel<128, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<128, 3>::TOTAL);
-  cudaFuncSetAttribute(conv_gemm_tc_kernel<64, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<64, 4>::TOTAL);
-  cudaFuncSetAttribute(wgrad_tc_kernel<128, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<128, 3>::TOTAL);
-  cudaFuncSetAttribute(wgrad_tc_kernel<64, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<64, 4>::TOTAL);
+#define HP_SET_SMEM(kern, BN, ST, PS) \
+  cudaFuncSetAttribute(kern<BN, ST, PS>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<BN, ST, PS>::TOTAL)
+  HP_SET_SMEM(conv_gemm_tc_kernel, 128, 3, 3), HP_SET_SMEM(conv_gemm_tc_kernel, 64, 4, 3);
+  HP_SET_SMEM(conv_gemm_tc_kernel, 128, 6, 1), HP_SET_SMEM(conv_gemm_tc_kernel, 64, 8, 1);
+  HP_SET_SMEM(wgrad_tc_kernel, 128, 3, 3), HP_SET_SMEM(wgrad_tc_kernel, 64, 4, 3);
+  HP_SET_SMEM(wgrad_tc_kernel, 128, 6, 1), HP_SET_SMEM(wgrad_tc_kernel, 64, 8, 1);
+#undef HP_SET_SMEM
   return cudaGetLastError() == cudaSuccess;
 }
 
@@ -567,18 +610,22 @@ bool tc_make_rows_map(TcMap* out, const float* base, int row_floats, int channel
   return r == CUDA_SUCCESS;
 }
 
+void tc_debug_conv(int dbg) { g_conv_dbg = dbg; }
+
 void tc_debug_wgrad_knobs(uint32_t lbo, uint32_t sbo, uint32_t ltype, int tma_swizzle) {
   g_wg_lbo = lbo, g_wg_sbo = sbo, g_wg_ltype = ltype, g_wg_swz = (CUtensorMapSwizzle)tma_swizzle;
 }
 
-void launch_wgrad_tc(const WgradGemm& g, const TcMap& mapDY, const TcMap& mapX, int bn, int sm_count, cudaStream_t s) {
+void launch_wgrad_tc(const WgradGemm& g, const TcMap& mapDY, const TcMap& mapX, int bn, int sm_count, int passes,
+                     cudaStream_t s) {
   TcWgrad p{};
   p.dW = g.dW, p.M = g.M, p.N = g.N, p.R = g.R;
   p.lbo = g_wg_lbo, p.sbo = g_wg_sbo, p.ltype = g_wg_ltype;
   const int tiles = ((g.M + TC_BM - 1) / TC_BM) * (g.N / bn);
-  int splits = (2 * sm_count + tiles - 1) / tiles;
+  // one wave: every CTA pays ~6-9 us of prologue + epilogue, so fewer, longer CTAs beat more splits
+  int splits = sm_count / tiles;
   const int kblocks = (g.R + TC_BK - 1) / TC_BK;
-  if (splits > (kblocks + 3) / 4) splits = (kblocks + 3) / 4;  // at least 4 k-blocks (128 rows) per CTA
+  if (splits > (kblocks + 7) / 8) splits = (kblocks + 7) / 8;  // at least 8 k-blocks (256 rows) per CTA
   if (splits < 1) splits = 1;
   int kb_per = (kblocks + splits - 1) / splits;
   p.rows_per_split = kb_per * TC_BK;
@@ -586,10 +633,17 @@ void launch_wgrad_tc(const WgradGemm& g, const TcMap& mapDY, const TcMap& mapX, 
   dim3 grid(g.N / bn, (g.M + TC_BM - 1) / TC_BM, splits);
   const CUtensorMap& a = *reinterpret_cast<const CUtensorMap*>(mapDY.opaque);
   const CUtensorMap& x = *reinterpret_cast<const CUtensorMap*>(mapX.opaque);
-  if (bn == 128)
-    wgrad_tc_kernel<128, 3><<<grid, TC_THREADS, TcSmem<128, 3>::TOTAL, s>>>(a, x, p);
-  else
-    wgrad_tc_kernel<64, 4><<<grid, TC_THREADS, TcSmem<64, 4>::TOTAL, s>>>(a, x, p);
+  if (passes == 3) {
+    if (bn == 128)
+      wgrad_tc_kernel<128, 3, 3><<<grid, TC_THREADS, TcSmem<128, 3, 3>::TOTAL, s>>>(a, x, p);
+    else
+      wgrad_tc_kernel<64, 4, 3><<<grid, TC_THREADS, TcSmem<64, 4, 3>::TOTAL, s>>>(a, x, p);
+  } else {
+    if (bn == 128)
+      wgrad_tc_kernel<128, 6, 1><<<grid, TC_THREADS, TcSmem<128, 6, 1>::TOTAL, s>>>(a, x, p);
+    else
+      wgrad_tc_kernel<64, 8, 1><<<grid, TC_THREADS, TcSmem<64, 8, 1>::TOTAL, s>>>(a, x, p);
+  }
 }
 
 int tc_pick_bn(int B, int N, int Lout, int sm_count) {
@@ -600,18 +654,27 @@ int tc_pick_bn(int B, int N, int Lout, int sm_count) {
 }
 
 // returns the number of logical rows per statistics tile
-int launch_conv_gemm_tc(const ConvGemm& g, const TcMap& mapA, const TcMap& mapW, int bn, int B, cudaStream_t s) {
+int launch_conv_gemm_tc(const ConvGemm& g, const TcMap& mapA, const TcMap& mapW, int bn, int B, int passes,
+                        cudaStream_t s) {
   TcConv p{};
   p.C = g.C, p.bias = g.bias, p.part = g.part, p.B = B, p.N = g.N, p.K = g.K, p.Lout = g.Lout;
   p.nb = TC_BM / g.Lout;
   p.out_rows = g.out_rows, p.out_off = g.out_off, p.out_lstride = g.out_lstride, p.accumulate = g.accumulate;
+  p.dbg = g_conv_dbg;
   dim3 grid((B + p.nb - 1) / p.nb, g.N / bn);
   const CUtensorMap& a = *reinterpret_cast<const CUtensorMap*>(mapA.opaque);
   const CUtensorMap& w = *reinterpret_cast<const CUtensorMap*>(mapW.opaque);
-  if (bn == 128)
-    conv_gemm_tc_kernel<128, 3><<<grid, TC_THREADS, TcSmem<128, 3>::TOTAL, s>>>(a, w, p);
-  else
-    conv_gemm_tc_kernel<64, 4><<<grid, TC_THREADS, TcSmem<64, 4>::TOTAL, s>>>(a, w, p);
+  if (passes == 3) {
+    if (bn == 128)
+      conv_gemm_tc_kernel<128, 3, 3><<<grid, TC_THREADS, TcSmem<128, 3, 3>::TOTAL, s>>>(a, w, p);
+    else
+      conv_gemm_tc_kernel<64, 4, 3><<<grid, TC_THREADS, TcSmem<64, 4, 3>::TOTAL, s>>>(a, w, p);
+  } else {
+    if (bn == 128)
+      conv_gemm_tc_kernel<128, 6, 1><<<grid, TC_THREADS, TcSmem<128, 6, 1>::TOTAL, s>>>(a, w, p);
+    else
+      conv_gemm_tc_kernel<64, 8, 1><<<grid, TC_THREADS, TcSmem<64, 8, 1>::TOTAL, s>>>(a, w, p);
+  }
   return p.nb * g.Lout;
 }
 

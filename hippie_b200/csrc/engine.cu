@@ -87,6 +87,7 @@ struct Branch {
   cudaStream_t st = nullptr;
   float* part = nullptr;   // BatchNorm statistics / stem / tail partials
   float* bpart = nullptr;  // BatchNorm backward partials
+  cudaStream_t wst = nullptr;  // weight gradients are off the critical path: they run here, behind an event
 };
 
 }  // namespace
@@ -118,12 +119,17 @@ struct hippie_engine {
   float* ws = nullptr;
   bool bound = false;
   cudaStream_t side = nullptr;
+  cudaStream_t wside[2] = {nullptr, nullptr};
+  std::vector<cudaEvent_t> ev_pool;
+  size_t ev_next = 0;
+  cudaEvent_t next_event() { return ev_pool[ev_next++ % ev_pool.size()]; }
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   int launches = 0;
   int n_convs = 0;
   std::vector<ConvMaps> cmaps;
   bool use_tc = false;  // tcgen05 3xTF32 implicit GEMM for conv forward / dgrad (conv_path 0); false = FP32 SIMT
   std::string tc_note;
+  int bwd_passes = 3;  // conv_path 3: dgrad / wgrad run one tf32 pass (round-to-nearest operands)
   // profiling aid (bench.py roofline): CUDA events around every implicit-GEMM launch
   struct ProfRec {
     int kind;
@@ -441,7 +447,7 @@ struct hippie_engine {
       H.dbn_run[m] = bns[bidx.at(d + ".3")].run_off, H.dbn_cnt[m] = bidx.at(d + ".3");
     }
     head_scratch = take(head_scratch_floats(z, cfg.class_hidden_dim, cfg.max_batch));
-    scal_off = take(64);
+    scal_off = take(64 + kHeadMaxCtas);  // [0],[1] squared-error sums, [64..) KL partials per head CTA
     // partial-sum buffers.  BatchNorm statistics: [tiles of >= 64 logical rows][C][2]; the stem's weight-gradient
     // partials ([tiles of 128 rows][192]) also fit.  BatchNorm backward: at most kBnBwdMaxChunks chunks x C x 3.
     part_floats = 4096;
@@ -489,7 +495,7 @@ struct hippie_engine {
     if (use_tc && g.Lout <= 128) {
       ConvMaps& m = cmaps[cv.id];
       const int bn = tc_pick_bn(B, g.N, g.Lout, sm_count);
-      tile = launch_conv_gemm_tc(g, m.a_fwd, bn == 128 ? m.w128 : m.w64, bn, B, br.st);
+      tile = launch_conv_gemm_tc(g, m.a_fwd, bn == 128 ? m.w128 : m.w64, bn, B, 3, br.st);
     } else {
       tile = launch_conv_gemm_simt(g, br.st);
     }
@@ -535,7 +541,7 @@ struct hippie_engine {
     if (use_tc && g.Lout <= 128) {
       ConvMaps& m = cmaps[cv.id];
       const int bn = tc_pick_bn(B, g.N, g.Lout, sm_count);
-      launch_conv_gemm_tc(g, m.a_dg, bn == 128 ? m.wt128 : m.wt64, bn, B, br.st);
+      launch_conv_gemm_tc(g, m.a_dg, bn == 128 ? m.wt128 : m.wt64, bn, B, bwd_passes, br.st);
     } else {
       launch_conv_gemm_simt(g, br.st);
     }
@@ -546,6 +552,12 @@ struct hippie_engine {
     WgradGemm g{};
     g.dY = A(dy), g.X = A(x), g.dW = Gp(cv.w);
     g.M = cv.cout, g.N = cv.k * cv.cin, g.R = B * (acts[dy].L + 2), g.Cin = cv.cin, g.roff = cv.k == 3 ? -1 : 0;
+    cudaStream_t wst = br.wst ? br.wst : br.st;
+    if (wst != br.st) {  // dY is final once the stream reaches this point; everything the wgrad reads stays untouched
+      cudaEvent_t e = next_event();
+      cudaEventRecord(e, br.st);
+      cudaStreamWaitEvent(wst, e, 0);
+    }
     cudaEvent_t pe = prof_begin(br);
     if (use_tc) {
       ConvMaps& m = cmaps[cv.id];
@@ -560,9 +572,9 @@ struct hippie_engine {
     if (use_tc) {
       ConvMaps& m = cmaps[cv.id];
       const int bn = (g.N % 128 == 0) ? 128 : 64;
-      launch_wgrad_tc(g, m.wg_dy, bn == 128 ? m.wg_x4 : m.wg_x2, bn, sm_count, br.st);
+      launch_wgrad_tc(g, m.wg_dy, bn == 128 ? m.wg_x4 : m.wg_x2, bn, sm_count, bwd_passes, wst);
     } else {
-      launch_wgrad_simt(g, sm_count, br.st);
+      launch_wgrad_simt(g, sm_count, wst);
     }
     // algorithmic FLOPs: only the B*Lout real output rows contribute (pad / dilation rows are zeros)
     prof_end(pe, 2, 2.0 * (double)g.M * g.N * (double)B * acts[dy].L / (cv.stride == 2 ? 2.0 : 1.0), br);
@@ -706,7 +718,7 @@ struct hippie_engine {
     for (int m = 0; m < n_dec; ++m) a.dout[m] = ws + dec[m].d, a.dd[m] = ws + dec[m].dd;
     a.src = src, a.cls = cls, a.eps = eps, a.scratch = ws + head_scratch;
     a.out_enc = out_enc, a.out_mu = out_mu, a.out_logvar = out_logvar;
-    a.kl_sum = ws + scal_off + 2, a.train = train ? 1 : 0, a.decode = decode ? 1 : 0, a.zscore_ddof = zscore;
+    a.kl_sum = ws + scal_off + 64, a.train = train ? 1 : 0, a.decode = decode ? 1 : 0, a.zscore_ddof = zscore;
     a.beta = beta;
     return a;
   }
@@ -741,6 +753,7 @@ struct hippie_engine {
           float* out_logvar, float* out_dec1, float* out_dec2, cudaStream_t main) {
     launches = 0;
     Branch b0{main, ws + part_off[0], ws + bpart_off[0]}, b1{profiling ? main : side, ws + part_off[1], ws + bpart_off[1]};
+    if (backward && !profiling) b0.wst = wside[0], b1.wst = wside[1];
     const float* xin[2] = {x1, x2};
     float* dec_out[2] = {out_dec1, out_dec2};
     const float lw[2] = {cfg.multimodal ? w1 : 1.f, w2};
@@ -763,7 +776,7 @@ struct hippie_engine {
       join(main);
     }
     HeadArgs ha = head_args(B, src, cls, eps, train, true, out_enc, out_mu, out_logvar, beta, -1);
-    launch_head_fwd(ha, main);
+    const int n_kl = launch_head_fwd(ha, main);
     ++launches;
     if (two) fork(main);
     for (int m = 0; m < n_dec; ++m) {
@@ -774,7 +787,7 @@ struct hippie_engine {
     }
     if (two) join(main);
     if (scalars_out) {
-      launch_loss_finalize(ws + scal_off + 0, ws + scal_off + 1, ws + scal_off + 2, B, dec[0].Lo,
+      launch_loss_finalize(ws + scal_off + 0, ws + scal_off + 1, ws + scal_off + 64, n_kl, B, dec[0].Lo,
                            cfg.multimodal ? dec[1].Lo : 1, beta, w1, w2, cfg.multimodal, scalars_out, main);
       ++launches;
     }
@@ -787,6 +800,12 @@ struct hippie_engine {
         encoder_bwd(enc[1], xin[1], B, b1);
         join(main);
       }
+      for (int i = 0; i < 2; ++i)
+        if (!profiling) {  // the weight-gradient streams rejoin the caller's stream
+          cudaEvent_t e = next_event();
+          cudaEventRecord(e, wside[i]);
+          cudaStreamWaitEvent(main, e, 0);
+        }
     }
     return check(train ? "train_fwd_bwd" : "eval_forward");
   }
@@ -815,6 +834,9 @@ int hippie_create(const hippie_cfg* cfg, hippie_handle* out) {
 void hippie_destroy(hippie_handle h) {
   if (!h) return;
   if (h->side) cudaStreamDestroy(h->side);
+  for (auto e : h->ev_pool) cudaEventDestroy(e);
+  for (int i = 0; i < 2; ++i)
+    if (h->wside[i]) cudaStreamDestroy(h->wside[i]);
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   if (h->ev_join) cudaEventDestroy(h->ev_join);
   delete h;
@@ -879,6 +901,9 @@ int hippie_bind(hippie_handle h, float* params, float* grads, float* exp_avg, fl
   if (!h->side) {
     cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking);
     cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
+    for (int i = 0; i < 2; ++i) cudaStreamCreateWithFlags(&h->wside[i], cudaStreamNonBlocking);
+    h->ev_pool.resize(512);
+    for (auto& e : h->ev_pool) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming);
   }
   cudaMemsetAsync(workspace, 0, (size_t)h->ws_floats * sizeof(float), st);
@@ -886,7 +911,8 @@ int hippie_bind(hippie_handle h, float* params, float* grads, float* exp_avg, fl
   h->use_tc = false;
   if (h->cfg.conv_path != 1) {
     h->use_tc = tc_init(&h->tc_note);
-    if (!h->use_tc && h->cfg.conv_path == 2) return h->fail(-8, "tcgen05 path requested but unavailable: " + h->tc_note);
+    h->bwd_passes = h->cfg.conv_path == 3 ? 1 : 3;
+    if (!h->use_tc && h->cfg.conv_path >= 2) return h->fail(-8, "tcgen05 path requested but unavailable: " + h->tc_note);
   }
   if (!h->wt_table.empty())
     cudaMemcpyAsync(h->ws + h->wt_table_off, h->wt_table.data(), h->wt_table.size() * sizeof(WtEntry),

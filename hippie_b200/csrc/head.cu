@@ -267,10 +267,10 @@ __global__ void __launch_bounds__(256) head_fwd_kernel(HeadArgs a) {
   klp = warp_sum(klp);
   if ((threadIdx.x & 31) == 0) sred[threadIdx.x >> 5] = klp;
   __syncthreads();
-  if (threadIdx.x == 0 && a.kl_sum) {
+  if (threadIdx.x == 0 && a.kl_sum) {  // per-CTA partial; loss_finalize adds them in a fixed order (deterministic)
     float s = 0.f;
     for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += sred[w];
-    atomicAdd(a.kl_sum, s);
+    a.kl_sum[blockIdx.x] = s;
   }
   if (!a.decode) return;
 
@@ -403,16 +403,18 @@ static int head_grid(int B, int z) {
   return g;
 }
 
-void launch_head_fwd(const HeadArgs& a, cudaStream_t s) {
+int launch_head_fwd(const HeadArgs& a, cudaStream_t s) {
   if (a.train) {
     void* args[] = {const_cast<HeadArgs*>(&a)};
-    cudaLaunchCooperativeKernel((const void*)head_fwd_kernel, dim3(head_grid(a.B, a.z)), dim3(256), args, 0, s);
-  } else {
-    int grid = (a.B + 63) / 64;
-    if (grid > 592) grid = 592;
-    if (grid < 1) grid = 1;
-    head_fwd_kernel<<<grid, 256, 0, s>>>(a);
+    const int grid = head_grid(a.B, a.z);
+    cudaLaunchCooperativeKernel((const void*)head_fwd_kernel, dim3(grid), dim3(256), args, 0, s);
+    return grid;
   }
+  int grid = (a.B + 63) / 64;
+  if (grid > kHeadMaxCtas) grid = kHeadMaxCtas;
+  if (grid < 1) grid = 1;
+  head_fwd_kernel<<<grid, 256, 0, s>>>(a);
+  return grid;
 }
 void launch_head_bwd(const HeadArgs& a, cudaStream_t s) {
   void* args[] = {const_cast<HeadArgs*>(&a)};

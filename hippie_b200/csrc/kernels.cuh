@@ -53,9 +53,13 @@ bool tc_make_weight_map(TcMap* out, const float* w, int N, int K, int bn);
 int tc_pick_bn(int B, int N, int Lout, int sm_count);
 struct WgradGemm;
 bool tc_make_rows_map(TcMap* out, const float* base, int row_floats, int channels, int rows, int box_groups);
+void tc_debug_conv(int dbg);  // tools/tc_test only
 void tc_debug_wgrad_knobs(uint32_t lbo, uint32_t sbo, uint32_t ltype, int tma_swizzle);  // tools/tc_test only
-void launch_wgrad_tc(const WgradGemm& g, const TcMap& mapDY, const TcMap& mapX, int bn, int sm_count, cudaStream_t s);
-int launch_conv_gemm_tc(const ConvGemm& g, const TcMap& mapA, const TcMap& mapW, int bn, int B, cudaStream_t s);
+void launch_wgrad_tc(const WgradGemm& g, const TcMap& mapDY, const TcMap& mapX, int bn, int sm_count, int passes,
+                     cudaStream_t s);
+// passes = 3: fp32-accurate 3xTF32; passes = 1: one tf32 pass with round-to-nearest operands
+int launch_conv_gemm_tc(const ConvGemm& g, const TcMap& mapA, const TcMap& mapW, int bn, int B, int passes,
+                        cudaStream_t s);
 
 // ---- weight gradient:  dW[m, n] += sum_r dY[r, m] * X[(r + roff) * Cin + n]  (split-K, atomics) -------
 struct WgradGemm {
@@ -213,7 +217,7 @@ struct HeadArgs {
   float* out_enc;
   float* out_mu;
   float* out_logvar;  // optional user outputs [B][z]
-  float* kl_sum;      // scalar: sum_b kl_b
+  float* kl_sum;      // [number of CTAs] partial sums of kl_b (added in order by launch_loss_finalize)
   int train;          // batch statistics + running update
   int decode;         // 0 = stop after mu/logvar (embedding pass)
   int zscore_ddof;    // -1 none; else z-score out_enc rows in place
@@ -223,11 +227,12 @@ struct HeadArgs {
   float beta;
 };
 int64_t head_scratch_floats(int z, int h, int B);
-void launch_head_fwd(const HeadArgs& a, cudaStream_t s);
+constexpr int kHeadMaxCtas = 592;
+int launch_head_fwd(const HeadArgs& a, cudaStream_t s);  // returns the number of CTAs (= KL partials written)
 void launch_head_bwd(const HeadArgs& a, cudaStream_t s);
 
 // ---- loss scalars: total = w1*mse1 + w2*mse2 + beta*kl ---------------------------------------------------
-void launch_loss_finalize(const float* sse1, const float* sse2, const float* kl_sum, int B, int Lo1, int Lo2,
+void launch_loss_finalize(const float* sse1, const float* sse2, const float* kl_parts, int n_kl, int B, int Lo1, int Lo2,
                           float beta, float w1, float w2, int multimodal, float* scalars, cudaStream_t s);
 
 // ---- gradient clipping + AdamW over the flat buffers ----------------------------------------------------

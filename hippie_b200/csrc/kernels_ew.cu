@@ -609,11 +609,14 @@ __global__ void __launch_bounds__(256) dec_tail_reduce_kernel(DecTail t, int nct
   }
 }
 
-__global__ void loss_finalize_kernel(const float* sse1, const float* sse2, const float* kl_sum, int B, int Lo1, int Lo2,
+__global__ void loss_finalize_kernel(const float* sse1, const float* sse2, const float* kl_parts, int n_kl, int B, int Lo1,
+                                     int Lo2,
                                      float beta, float w1, float w2, int multimodal, float* scalars) {
   const float mse1 = *sse1 / ((float)B * (float)Lo1);
   const float mse2 = multimodal ? *sse2 / ((float)B * (float)Lo2) : 0.f;
-  const float kl = *kl_sum / (float)B;
+  float kl_sum = 0.f;
+  for (int i = 0; i < n_kl; ++i) kl_sum += kl_parts[i];
+  const float kl = kl_sum / (float)B;
   const float mse = multimodal ? w1 * mse1 + w2 * mse2 : mse1;
   scalars[0] = mse + beta * kl;
   scalars[1] = mse1;
@@ -794,9 +797,9 @@ void launch_dec_tail_reduce(const DecTail& t, int ncta, float* dwc, float* dbc, 
                             cudaStream_t s) {
   dec_tail_reduce_kernel<<<t.Lo + 1, 256, 0, s>>>(t, ncta, dwc, dbc, dWo, dbo, sse);
 }
-void launch_loss_finalize(const float* sse1, const float* sse2, const float* kl_sum, int B, int Lo1, int Lo2,
+void launch_loss_finalize(const float* sse1, const float* sse2, const float* kl_parts, int n_kl, int B, int Lo1, int Lo2,
                           float beta, float w1, float w2, int multimodal, float* scalars, cudaStream_t s) {
-  loss_finalize_kernel<<<1, 1, 0, s>>>(sse1, sse2, kl_sum, B, Lo1, Lo2, beta, w1, w2, multimodal, scalars);
+  loss_finalize_kernel<<<1, 1, 0, s>>>(sse1, sse2, kl_parts, n_kl, B, Lo1, Lo2, beta, w1, w2, multimodal, scalars);
 }
 void launch_clip_adamw(const AdamArgs& a, cudaStream_t s) {
   const int nblk = 1024;

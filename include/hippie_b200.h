@@ -47,7 +47,9 @@ typedef struct hippie_cfg {
   int32_t max_batch;  /* largest B any call will pass; sizes the workspace                      */
   int32_t inference_only; /* 1 = no gradient tensors in the workspace (embedding engines)      */
   int32_t conv_path;  /* 0 = auto (tcgen05 3xTF32, FP32 CUDA-core GEMM if TMA maps are unavailable),
-                         1 = force the FP32 CUDA-core GEMM, 2 = require tcgen05 (bind fails otherwise)   */
+                         1 = force the FP32 CUDA-core GEMM, 2 = require tcgen05 (bind fails otherwise),
+                         3 = tcgen05 with fast backward: forward stays 3xTF32 (loss / embedding parity),
+                             dgrad and wgrad run ONE tf32 pass with round-to-nearest operands          */
 } hippie_cfg;
 
 /* Layout kinds of a parameter inside the flat buffer. */

@@ -22,6 +22,8 @@ static inline int ck_(cudaError_t e, const char* f, int l) {
 }
 #define CK(x) ck_((x), __FILE__, __LINE__)
 
+static int g_passes = 3;
+
 static void fill(std::vector<float>& v, unsigned seed, float scale) {
   unsigned s = seed * 2654435761u + 12345u;
   for (auto& x : v) {
@@ -75,7 +77,7 @@ static void test_conv(int B, int L, int Cin, int Cout, int k, int stride, bool b
   g.in_rows = L + 2, g.in_stride = stride, g.in_off = k == 3 ? 0 : 1, g.in_C = Cin;
   g.out_rows = Lout + 2, g.out_off = 1, g.out_lstride = 1, g.accumulate = acc ? 1 : 0;
   ConvGemm g1 = g, g2 = g;
-  g1.C = dc1 + Cout, g1.part = dp1, g2.C = dc2 + Cout, g2.part = dp2;
+  g1.C = dc1 + Cout, g1.part = getenv("TC_NOSTATS") ? nullptr : dp1, g2.C = dc2 + Cout, g2.part = getenv("TC_NOSTATS") ? nullptr : dp2;
   launch_conv_gemm_simt(g1, 0);
   TcMap ma, mw;
   const int bn = tc_pick_bn(B, Cout, Lout, 148);
@@ -84,7 +86,7 @@ static void test_conv(int B, int L, int Cin, int Cout, int k, int stride, bool b
     printf("conv  B=%d L=%d %d->%d k%d s%d: tensor map creation FAILED\n", B, L, Cin, Cout, k, stride);
     return;
   }
-  launch_conv_gemm_tc(g2, ma, mw, bn, B, 0);
+  launch_conv_gemm_tc(g2, ma, mw, bn, B, g_passes, 0);
   CK(cudaDeviceSynchronize());
   std::vector<float> r1(out_floats), r2(out_floats);
   CK(cudaMemcpy(r1.data(), dc1, out_floats * 4, cudaMemcpyDeviceToHost));
@@ -92,7 +94,7 @@ static void test_conv(int B, int L, int Cin, int Cout, int k, int stride, bool b
   double mr, md = compare(r2, r1, &mr);
   g1.accumulate = g2.accumulate = 0;
   const float t1 = time_ms([&] { launch_conv_gemm_simt(g1, 0); }, 20);
-  const float t2 = time_ms([&] { launch_conv_gemm_tc(g2, ma, mw, bn, B, 0); }, 20);
+  const float t2 = time_ms([&] { launch_conv_gemm_tc(g2, ma, mw, bn, B, g_passes, 0); }, 20);
   const double fl = 2.0 * g.M * g.N * g.K;
   printf("conv  B=%4d L=%3d %3d->%3d k%d s%d bias%d acc%d bn%3d | rel err %.2e | simt %7.1f us %6.1f TF | tc %7.1f us %6.1f TF\n", B,
          L, Cin, Cout, k, stride, bias, acc, bn, md / mr, t1 * 1e3, fl / t1 / 1e9, t2 * 1e3, fl / t2 / 1e9);
@@ -121,14 +123,14 @@ static void test_wgrad(int B, int L, int Cin, int Cout, int k) {
     printf("wgrad B=%d L=%d %d->%d k%d: tensor map creation FAILED\n", B, L, Cin, Cout, k);
     return;
   }
-  launch_wgrad_tc(g2, my, mx, bn, 148, 0);
+  launch_wgrad_tc(g2, my, mx, bn, 148, g_passes, 0);
   CK(cudaDeviceSynchronize());
   std::vector<float> r1((size_t)Cout * N), r2((size_t)Cout * N);
   CK(cudaMemcpy(r1.data(), dw1, r1.size() * 4, cudaMemcpyDeviceToHost));
   CK(cudaMemcpy(r2.data(), dw2, r2.size() * 4, cudaMemcpyDeviceToHost));
   double mr, md = compare(r2, r1, &mr);
   const float t1 = time_ms([&] { launch_wgrad_simt(g1, 148, 0); }, 20);
-  const float t2 = time_ms([&] { launch_wgrad_tc(g2, my, mx, bn, 148, 0); }, 20);
+  const float t2 = time_ms([&] { launch_wgrad_tc(g2, my, mx, bn, 148, g_passes, 0); }, 20);
   const double fl = 2.0 * Cout * (double)N * R;
   printf("wgrad B=%4d L=%3d %3d->%3d k%d bn%3d | rel err %.2e (tc[0..3] %.4f %.4f %.4f %.4f simt %.4f %.4f %.4f %.4f) | simt %7.1f us %6.1f TF | tc %7.1f us %6.1f TF\n",
          B, L, Cin, Cout, k, bn, md / mr, r2[0], r2[1], r2[2], r2[3], r1[0], r1[1], r1[2], r1[3], t1 * 1e3, fl / t1 / 1e9,
@@ -143,6 +145,7 @@ int main(int argc, char** argv) {
     return 1;
   }
   const int B = argc > 1 ? atoi(argv[1]) : 512;
+  if (getenv("TC_PASSES")) g_passes = atoi(getenv("TC_PASSES"));
   if (argc > 2) {  // probe the MN-major descriptor / TMA swizzle pairing
     const int swz[] = {3 /*128B*/, 4 /*128B_ATOM_32B*/, 5 /*ATOM_32B_FLIP_8B*/, 6 /*ATOM_64B*/};
     const unsigned lt[] = {2, 1};
@@ -156,6 +159,18 @@ int main(int argc, char** argv) {
             printf("swz %d ltype %u lbo %4u sbo %4u : ", sw, l, lbo, sbo);
             test_wgrad(8, 4, 128, 128, 3);
           }
+    return 0;
+  }
+  if (getenv("TC_DBG")) {  // where does the time go?  0 = full, 1 = no hi/lo split, 2 = one MMA pass, 3 = both
+    for (int dbg : {0, 4, 1, 2, 3}) {
+      tc_debug_conv(dbg);
+      printf("dbg %d: ", dbg);
+      test_conv(B, 7, 512, 512, 3, 1, false, false);
+      printf("dbg %d: ", dbg);
+      test_conv(B, 4, 512, 512, 3, 1, false, false);
+      printf("dbg %d: ", dbg);
+      test_conv(B, 16, 128, 128, 3, 1, false, false);
+    }
     return 0;
   }
   test_wgrad(8, 4, 64, 64, 3);
