@@ -1,0 +1,560 @@
+// tcgen05 implicit-GEMM conv1d (forward, dgrad) and weight gradient over 16-bit PAIR PLANES.
+//
+// Every GEMM operand lives in HBM as two 16-bit planes (hi, lo) with  x ~= hi + lo :
+//   forward   activations fp16 pair (scale 1), weights fp16 pair (scale 2^8)          -> ~22 mantissa bits
+//   backward  output gradients bf16 pair (no range issue), weights / activations as in the forward
+// and one product is three tensor-core MMAs  hi*hi + hi*lo + lo*hi  (kind::f16, K = 16, fp32 accumulation in TMEM).
+// tools/pair_precision.py shows the fp16 pair matches fp32 operands on the loss / embedding bounds (like 3xTF32),
+// at HALF the tensor time and ~1/3 of the shared-memory traffic of an in-kernel 3xTF32 split: the kernels below are
+// pure TMA -> MMA pipelines, the producers of the tensors write the planes (kernels_ew.cu).
+//
+//   C[m, n] (+)= scale * sum_k A[row(m), k] * B[n, k]
+//     A rows  = contiguous k*Cin windows of the padded channels-last pair tensor (3-D TMA box per plane)
+//     B       = K-major weight planes [N][K] (forward), or the SAME planes read MN-major as [ci][(t, co)] (dgrad:
+//               no transposed weight copy exists)
+//
+// Per CTA (192 threads): warp 0 TMA producer, warp 1 TMEM allocator + MMA issuer, warps 2-5 epilogue
+// (TMEM -> registers -> shared staging -> coalesced stores, bias, BatchNorm (sum, centred M2) partials).
+// The tensor core truncates when it adds into the fp32 accumulator; to keep that bias below the parity bound the
+// hi*hi products alternate between two accumulators and the small cross terms use a third (summed with
+// round-to-nearest in the epilogue).
+//
+// Replaces the nn.Conv1d forward calls of hippie/backbones.py:11,24,26,31,50,55 and their autograd backward.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+#include <cstdio>
+
+#include "kernels.cuh"
+#include "pair_fmt.cuh"
+#include "tc_common.cuh"
+
+namespace hp {
+
+namespace {
+
+using namespace tc;
+
+constexpr int PK = 64;  // K elements per k-block = one 128-byte swizzle row of 16-bit values
+
+struct PairConv {
+  float* C;
+  const float* bias;
+  float* part;
+  int B, N, K;
+  int Lout, nb;
+  int out_rows, out_off, out_lstride, accumulate;
+  float out_scale;
+  uint32_t idesc;
+  int b_mn;        // 1: B tiles are MN-major boxes of the forward weight planes [co][t][ci]
+  int kb_per_tap;  // b_mn: k-blocks per tap (= Cout / 64)
+  int taps;        // b_mn: kernel size (3 or 1); tap of k-block kb = taps - 1 - kb / kb_per_tap
+  const float* dyn_scale;  // optional device scalar multiplied into out_scale
+};
+
+template <int BN, int STAGES>
+struct PairSmem {
+  static constexpr int A_PLANE = TC_BM * 128;  // 16 KB: 128 rows x 64 halfs
+  static constexpr int B_PLANE = BN * 128;
+  static constexpr int A_LO = A_PLANE;
+  static constexpr int B_OFF = 2 * A_PLANE;
+  static constexpr int B_LO = B_OFF + B_PLANE;
+  static constexpr int STAGE_BYTES = 2 * A_PLANE + 2 * B_PLANE;
+  static constexpr int RING_BYTES = STAGES * STAGE_BYTES;
+  static constexpr int EPI_STRIDE = BN + 4;
+  static_assert(TC_BM * EPI_STRIDE * 4 <= RING_BYTES, "epilogue staging must fit in the ring");
+  static constexpr int TOTAL = RING_BYTES + 1024 + 256;
+  static constexpr int TMEM_COLS = BN == 128 ? 512 : 256;  // three accumulators of BN columns
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+    conv_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, PairConv p) {
+  using S = PairSmem<BN, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ring + S::RING_BYTES);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + STAGES;
+  uint64_t* accum = bars + 2 * STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b0 = blockIdx.x * p.nb, n0 = blockIdx.y * BN;
+  const int nkb = p.K / PK;
+  const int rows_tile = p.nb * p.Lout;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&mapA);
+    tma_prefetch_desc(&mapB);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(accum, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "n"(S::TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      const uint32_t tx_bytes = (uint32_t)(2 * rows_tile * 128 + 2 * S::B_PLANE);
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
+        mbar_wait(&empty[s], ph ^ 1u);
+        uint8_t* st = ring + s * S::STAGE_BYTES;
+        mbar_expect_tx(&full[s], tx_bytes);
+        tma_load_4d(st, &mapA, &full[s], kb * PK, 0, b0, 0);
+        tma_load_4d(st + S::A_LO, &mapA, &full[s], kb * PK, 0, b0, 1);
+        if (!p.b_mn) {
+          tma_load_3d(st + S::B_OFF, &mapB, &full[s], kb * PK, n0, 0);
+          tma_load_3d(st + S::B_LO, &mapB, &full[s], kb * PK, n0, 1);
+        } else {
+          const int u = kb / p.kb_per_tap, cob = kb - u * p.kb_per_tap;
+          const int tap = p.taps - 1 - u;
+#pragma unroll
+          for (int g = 0; g < BN / 64; ++g) {  // one [64 co][64 ci] box per group of 64 output columns
+            tma_load_4d(st + S::B_OFF + g * 8192, &mapB, &full[s], n0 + g * 64, tap, cob * 64, 0);
+            tma_load_4d(st + S::B_LO + g * 8192, &mapB, &full[s], n0 + g * 64, tap, cob * 64, 1);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
+        mbar_wait(&full[s], ph);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t st = smem_u32(ring + s * S::STAGE_BYTES);
+        const uint64_t a_hi = umma_desc(st, 16, 1024, 2), a_lo = umma_desc(st + S::A_LO, 16, 1024, 2);
+        uint64_t b_hi, b_lo, badv;
+        if (!p.b_mn) {  // K-major: 8-row groups 1024 B apart, 16 halfs = 32 B along the swizzled row per step
+          b_hi = umma_desc(st + S::B_OFF, 16, 1024, 2), b_lo = umma_desc(st + S::B_LO, 16, 1024, 2);
+          badv = 32 >> 4;
+        } else {  // MN-major: groups of 64 columns 8 KB apart (LBO), 8 k-rows 1024 B apart (SBO), 16 k-rows per step
+          b_hi = umma_desc(st + S::B_OFF, 8192, 1024, 2), b_lo = umma_desc(st + S::B_LO, 8192, 1024, 2);
+          badv = 2048 >> 4;
+        }
+#pragma unroll
+        for (int k16 = 0; k16 < PK / 16; ++k16) {
+          const uint64_t aadv = (uint64_t)(k16 * 32 >> 4), bad = (uint64_t)k16 * badv;
+          const int step = kb * (PK / 16) + k16;
+          umma_f16(tmem_base + 2 * BN, a_lo + aadv, b_hi + bad, p.idesc, step != 0 ? 1u : 0u);
+          umma_f16(tmem_base + 2 * BN, a_hi + aadv, b_lo + bad, p.idesc, 1u);
+          umma_f16(tmem_base + (step & 1) * BN, a_hi + aadv, b_hi + bad, p.idesc, step >= 2 ? 1u : 0u);
+        }
+        umma_commit(&empty[s]);
+      }
+      umma_commit(accum);
+    }
+  } else {
+    // ===================== epilogue =====================
+    const int t = threadIdx.x - 64;  // 0..127
+    mbar_wait(accum, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    float* stage = reinterpret_cast<float*>(ring);  // [128][BN + 4]; the ring is idle once `accum` has fired
+    const int q = warp & 3;                         // TMEM lane quarter this warp may read
+    const int row = q * 32 + lane;
+    const float sc = p.dyn_scale ? p.out_scale * __ldg(p.dyn_scale) : p.out_scale;
+#pragma unroll
+    for (int c = 0; c < BN / 32; ++c) {
+      uint32_t r[32], r1[32], r2[32];
+      const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32);
+      tmem_ld32(ta, r);
+      tmem_ld32(ta + BN, r1);
+      tmem_ld32(ta + 2 * BN, r2);
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        r[i] = __float_as_uint(((__uint_as_float(r[i]) + __uint_as_float(r1[i])) + __uint_as_float(r2[i])) * sc);
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        *reinterpret_cast<uint4*>(&stage[row * S::EPI_STRIDE + c * 32 + i * 4]) =
+            make_uint4(r[i * 4], r[i * 4 + 1], r[i * 4 + 2], r[i * 4 + 3]);
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");  // the four epilogue warps only
+
+    const int nvalid = min(rows_tile, (p.B - b0) * p.Lout);  // rows of this tile that are real outputs
+    {  // coalesced stores: thread -> (row group, fixed column quad)
+      constexpr int QUADS = BN / 4;
+      const int quad = t % QUADS;
+      float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (p.bias) bv = *reinterpret_cast<const float4*>(p.bias + n0 + quad * 4);
+      for (int r = t / QUADS; r < nvalid; r += 128 / QUADS) {
+        const int bs = r / p.Lout, l = r - bs * p.Lout;
+        float4 v = *reinterpret_cast<const float4*>(&stage[r * S::EPI_STRIDE + quad * 4]);
+        v.x += bv.x, v.y += bv.y, v.z += bv.z, v.w += bv.w;
+        float4* dst = reinterpret_cast<float4*>(
+            p.C + ((int64_t)(b0 + bs) * p.out_rows + p.out_off + (int64_t)l * p.out_lstride) * p.N + n0 + quad * 4);
+        if (p.accumulate) {
+          const float4 o = *dst;
+          v.x += o.x, v.y += o.y, v.z += o.z, v.w += o.w;
+        }
+        *dst = v;
+      }
+    }
+    if (p.part) {  // BatchNorm statistics of this tile: (sum, centred sum of squares) per column
+      // BN == 64: two threads per column (rows split in halves, combined with Chan's formula through shared memory)
+      constexpr int TPC = 128 / BN;  // threads per column
+      const int col = t % BN, part_id = t / BN;
+      const int r_lo = (nvalid * part_id) / TPC, r_hi = (nvalid * (part_id + 1)) / TPC;
+      const int cnt = r_hi - r_lo;
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+      int r = r_lo;
+      for (; r + 4 <= r_hi; r += 4) {
+        s0 += stage[(r + 0) * S::EPI_STRIDE + col], s1 += stage[(r + 1) * S::EPI_STRIDE + col];
+        s2 += stage[(r + 2) * S::EPI_STRIDE + col], s3 += stage[(r + 3) * S::EPI_STRIDE + col];
+      }
+      for (; r < r_hi; ++r) s0 += stage[r * S::EPI_STRIDE + col];
+      const float s = (s0 + s1) + (s2 + s3);
+      const float mean = cnt > 0 ? s / (float)cnt : 0.f;
+      float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
+      for (r = r_lo; r + 4 <= r_hi; r += 4) {
+        const float d0 = stage[(r + 0) * S::EPI_STRIDE + col] - mean, d1 = stage[(r + 1) * S::EPI_STRIDE + col] - mean;
+        const float d2 = stage[(r + 2) * S::EPI_STRIDE + col] - mean, d3 = stage[(r + 3) * S::EPI_STRIDE + col] - mean;
+        q0 = fmaf(d0, d0, q0), q1 = fmaf(d1, d1, q1), q2 = fmaf(d2, d2, q2), q3 = fmaf(d3, d3, q3);
+      }
+      for (; r < r_hi; ++r) {
+        const float d = stage[r * S::EPI_STRIDE + col] - mean;
+        q0 = fmaf(d, d, q0);
+      }
+      float m2 = (q0 + q1) + (q2 + q3);
+      float sum = s;
+      if (TPC == 2) {
+        asm volatile("bar.sync 1, 128;" ::: "memory");  // every thread is done reading its rows' staging columns
+        float* xch = stage;                              // reuse: [64][2] exchange
+        if (part_id == 1) xch[col * 2] = s, xch[col * 2 + 1] = m2;
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (part_id == 0) {
+          const float sb = xch[col * 2], m2b = xch[col * 2 + 1];
+          const int cb = nvalid - cnt;
+          if (cb > 0) {
+            const float mb = sb / (float)cb;
+            const float delta = mb - mean;
+            m2 = m2 + m2b + delta * delta * ((float)cnt * (float)cb / (float)nvalid);
+            sum = s + sb;
+          }
+        }
+      }
+      if (part_id == 0) {
+        const float bias = p.bias ? p.bias[n0 + col] : 0.f;
+        *reinterpret_cast<float2*>(p.part + ((int64_t)blockIdx.x * p.N + n0 + col) * 2) =
+            make_float2(sum + bias * (float)nvalid, m2);
+      }
+    }
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(S::TMEM_COLS) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Weight gradient:  dW[m, n] += scale * sum_r dY[r, m] * X[(r + roff) * Cin + n]   (split over row ranges, atomics)
+// Both operands are MN-major: the reduction index r is the row index of the channels-last pair tensors.  A k-block is
+// 64 rows; a tile of 128 (BN) channels arrives as 2 (BN / 64) boxes of [64 rows][64 channels] (128-byte swizzle).
+// ------------------------------------------------------------------------------------------------
+struct PairWgrad {
+  float* dW;
+  int M, N;
+  int R;
+  int rows_per_split;  // multiple of PK
+  float out_scale;
+  const float* dyn_scale;
+  uint32_t idesc;
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+    wgrad_pair_kernel(const __grid_constant__ CUtensorMap mapDY, const __grid_constant__ CUtensorMap mapX, PairWgrad p) {
+  using S = PairSmem<BN, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ring + S::RING_BYTES);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + STAGES;
+  uint64_t* accum = bars + 2 * STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * BN, m0 = blockIdx.y * TC_BM;
+  const int r_begin = blockIdx.z * p.rows_per_split;
+  const int r_end = min(p.R, r_begin + p.rows_per_split);
+  const int nkb = (r_end - r_begin + PK - 1) / PK;  // >= 1 by construction of the grid
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&mapDY);
+    tma_prefetch_desc(&mapX);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(accum, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "n"(S::TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
+        mbar_wait(&empty[s], ph ^ 1u);
+        uint8_t* st = ring + s * S::STAGE_BYTES;
+        mbar_expect_tx(&full[s], (uint32_t)S::STAGE_BYTES);
+        const int r0 = r_begin + kb * PK;
+#pragma unroll
+        for (int g = 0; g < TC_BM / 64; ++g) {
+          tma_load_3d(st + g * 8192, &mapDY, &full[s], m0 + g * 64, r0, 0);
+          tma_load_3d(st + S::A_LO + g * 8192, &mapDY, &full[s], m0 + g * 64, r0, 1);
+        }
+#pragma unroll
+        for (int g = 0; g < BN / 64; ++g) {
+          tma_load_3d(st + S::B_OFF + g * 8192, &mapX, &full[s], n0 + g * 64, r0, 0);
+          tma_load_3d(st + S::B_LO + g * 8192, &mapX, &full[s], n0 + g * 64, r0, 1);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
+        mbar_wait(&full[s], ph);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t st = smem_u32(ring + s * S::STAGE_BYTES);
+        const uint64_t a_hi = umma_desc(st, 8192, 1024, 2), a_lo = umma_desc(st + S::A_LO, 8192, 1024, 2);
+        const uint64_t b_hi = umma_desc(st + S::B_OFF, 8192, 1024, 2), b_lo = umma_desc(st + S::B_LO, 8192, 1024, 2);
+#pragma unroll
+        for (int k16 = 0; k16 < PK / 16; ++k16) {
+          const uint64_t adv = (uint64_t)(k16 * 2048 >> 4);  // 16 reduction rows = 16 x 128 B
+          const int step = kb * (PK / 16) + k16;
+          umma_f16(tmem_base + 2 * BN, a_lo + adv, b_hi + adv, p.idesc, step != 0 ? 1u : 0u);
+          umma_f16(tmem_base + 2 * BN, a_hi + adv, b_lo + adv, p.idesc, 1u);
+          umma_f16(tmem_base + (step & 1) * BN, a_hi + adv, b_hi + adv, p.idesc, step >= 2 ? 1u : 0u);
+        }
+        umma_commit(&empty[s]);
+      }
+      umma_commit(accum);
+    }
+  } else {
+    const int t = threadIdx.x - 64;
+    mbar_wait(accum, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    float* stage = reinterpret_cast<float*>(ring);
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const float sc = p.dyn_scale ? p.out_scale * __ldg(p.dyn_scale) : p.out_scale;
+#pragma unroll
+    for (int c = 0; c < BN / 32; ++c) {
+      uint32_t r[32], r1[32], r2[32];
+      const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32);
+      tmem_ld32(ta, r);
+      tmem_ld32(ta + BN, r1);
+      tmem_ld32(ta + 2 * BN, r2);
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        r[i] = __float_as_uint(((__uint_as_float(r[i]) + __uint_as_float(r1[i])) + __uint_as_float(r2[i])) * sc);
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        *reinterpret_cast<uint4*>(&stage[row * S::EPI_STRIDE + c * 32 + i * 4]) =
+            make_uint4(r[i * 4], r[i * 4 + 1], r[i * 4 + 2], r[i * 4 + 3]);
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    const int mvalid = min(TC_BM, p.M - m0);
+    const int col = t % BN;
+    for (int r = t / BN; r < mvalid; r += 128 / BN)
+      atomicAdd(p.dW + (int64_t)(m0 + r) * p.N + n0 + col, stage[r * S::EPI_STRIDE + col]);
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(S::TMEM_COLS) : "memory");
+  }
+}
+
+// fp32 -> pair planes (tools/pair_test and the weight refresh)
+template <int FMT>
+__global__ void to_pair_kernel(const float* __restrict__ src, uint16_t* __restrict__ hi, uint16_t* __restrict__ lo,
+                               int64_t n, float scale) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    uint16_t h, l;
+    pair_split<FMT>(src[i] * scale, h, l);
+    hi[i] = h, lo[i] = l;
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn g_enc = nullptr;
+
+bool encode(TcMap* out, int fmt, int rank, const void* base, const cuuint64_t* dims, const cuuint64_t* strides,
+            const cuuint32_t* box, CUtensorMapL2promotion promo) {
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = g_enc(reinterpret_cast<CUtensorMap*>(out->opaque),
+                     fmt == kPairBF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank,
+                     const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    fprintf(stderr, "hippie_b200: cuTensorMapEncodeTiled -> %d (rank %d, base %p, dims", (int)r, rank, base);
+    for (int i = 0; i < rank; ++i) fprintf(stderr, " %llu", (unsigned long long)dims[i]);
+    fprintf(stderr, ", strides");
+    for (int i = 0; i + 1 < rank; ++i) fprintf(stderr, " %llu", (unsigned long long)strides[i]);
+    fprintf(stderr, ", box");
+    for (int i = 0; i < rank; ++i) fprintf(stderr, " %u", box[i]);
+    fprintf(stderr, ")\n");
+  }
+  return r == CUDA_SUCCESS;
+}
+
+}  // namespace
+
+bool pair_init(std::string* err) {
+  if (g_enc) return true;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) {
+    if (err) *err = "cuTensorMapEncodeTiled is not available from the driver";
+    return false;
+  }
+  g_enc = reinterpret_cast<EncodeTiledFn>(fn);
+  cudaFuncSetAttribute(conv_pair_kernel<128, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, PairSmem<128, 3>::TOTAL);
+  cudaFuncSetAttribute(conv_pair_kernel<64, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, PairSmem<64, 4>::TOTAL);
+  cudaFuncSetAttribute(wgrad_pair_kernel<128, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, PairSmem<128, 3>::TOTAL);
+  cudaFuncSetAttribute(wgrad_pair_kernel<64, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, PairSmem<64, 4>::TOTAL);
+  if (cudaGetLastError() != cudaSuccess) {
+    if (err) *err = "cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed";
+    g_enc = nullptr;
+    return false;
+  }
+  return true;
+}
+
+// (k within the k*Cin window, logical output row, sample, plane)
+bool pair_make_act_map(TcMap* out, const void* planes, int64_t plane_stride, int fmt, int in_C, int K, int Lout,
+                       int in_rows, int in_stride, int in_off, int max_batch) {
+  const int nb = TC_BM / Lout;
+  cuuint64_t dims[4] = {(cuuint64_t)K, (cuuint64_t)Lout, (cuuint64_t)max_batch, 2};
+  cuuint64_t strides[3] = {(cuuint64_t)in_stride * in_C * 2, (cuuint64_t)in_rows * in_C * 2, (cuuint64_t)plane_stride * 2};
+  cuuint32_t box[4] = {(cuuint32_t)PK, (cuuint32_t)Lout, (cuuint32_t)nb, 1};
+  const uint16_t* base = static_cast<const uint16_t*>(planes) + (int64_t)in_off * in_C;
+  return encode(out, fmt, 4, base, dims, strides, box, CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
+}
+
+// K-major weight planes [N][K]: (k, n, plane), box 64 x bn x 1
+bool pair_make_w_map(TcMap* out, const void* planes, int64_t plane_stride, int fmt, int N, int K, int bn) {
+  cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)N, 2};
+  cuuint64_t strides[2] = {(cuuint64_t)K * 2, (cuuint64_t)plane_stride * 2};
+  cuuint32_t box[3] = {(cuuint32_t)PK, (cuuint32_t)bn, 1};
+  return encode(out, fmt, 3, planes, dims, strides, box, CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
+}
+
+// the same planes [co][t][ci] read MN-major for dgrad: (ci, t, co, plane), box 64 x 1 x 64 x 1
+bool pair_make_wmn_map(TcMap* out, const void* planes, int64_t plane_stride, int fmt, int Cout, int Cin, int k) {
+  cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)k, (cuuint64_t)Cout, 2};
+  cuuint64_t strides[3] = {(cuuint64_t)Cin * 2, (cuuint64_t)k * Cin * 2, (cuuint64_t)plane_stride * 2};
+  cuuint32_t box[4] = {64, 1, 64, 1};
+  return encode(out, fmt, 4, planes, dims, strides, box, CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
+}
+
+// wgrad operands: (channel, reduction row, plane), box 64 x 64 x 1; row pitch `row_elems` (rows may overlap)
+bool pair_make_rows_map(TcMap* out, const void* planes, int64_t plane_stride, int fmt, int64_t row_elems, int channels,
+                        int rows) {
+  cuuint64_t dims[3] = {(cuuint64_t)channels, (cuuint64_t)rows, 2};
+  cuuint64_t strides[2] = {(cuuint64_t)row_elems * 2, (cuuint64_t)plane_stride * 2};
+  cuuint32_t box[3] = {64, (cuuint32_t)PK, 1};
+  return encode(out, fmt, 3, planes, dims, strides, box, CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
+}
+
+int pair_pick_bn(int B, int N, int Lout, int sm_count) {
+  if (N % 128 != 0) return 64;
+  const int nb = TC_BM / Lout;
+  const int mtiles = (B + nb - 1) / nb;
+  return (mtiles * (N / 128) * 4 >= sm_count * 3) ? 128 : 64;
+}
+
+int launch_conv_pair(const ConvGemm& g, const TcMap& mapA, const TcMap& mapB, int bn, int B, const PairOpts& o,
+                     cudaStream_t s) {
+  PairConv p{};
+  p.C = g.C, p.bias = g.bias, p.part = g.part, p.B = B, p.N = g.N, p.K = g.K, p.Lout = g.Lout;
+  p.nb = TC_BM / g.Lout;
+  p.out_rows = g.out_rows, p.out_off = g.out_off, p.out_lstride = g.out_lstride, p.accumulate = g.accumulate;
+  p.out_scale = o.out_scale;
+  p.idesc = umma_idesc_16(bn, o.a_fmt, o.b_fmt, 0, o.b_mn ? 1 : 0);
+  p.b_mn = o.b_mn, p.taps = o.taps, p.kb_per_tap = o.taps > 0 ? (g.K / o.taps) / PK : 1;
+  p.dyn_scale = o.dyn_scale;
+  dim3 grid((B + p.nb - 1) / p.nb, g.N / bn);
+
+  const CUtensorMap& a = *reinterpret_cast<const CUtensorMap*>(mapA.opaque);
+  const CUtensorMap& w = *reinterpret_cast<const CUtensorMap*>(mapB.opaque);
+  if (bn == 128)
+    conv_pair_kernel<128, 3><<<grid, TC_THREADS, PairSmem<128, 3>::TOTAL, s>>>(a, w, p);
+  else
+    conv_pair_kernel<64, 4><<<grid, TC_THREADS, PairSmem<64, 4>::TOTAL, s>>>(a, w, p);
+  return p.nb * g.Lout;
+}
+
+void launch_wgrad_pair(const WgradGemm& g, const TcMap& mapDY, const TcMap& mapX, int bn, int sm_count, const PairOpts& o,
+                       cudaStream_t s) {
+  PairWgrad p{};
+  p.dW = g.dW, p.M = g.M, p.N = g.N, p.R = g.R;
+  p.out_scale = o.out_scale, p.dyn_scale = o.dyn_scale;
+  p.idesc = umma_idesc_16(bn, o.a_fmt, o.b_fmt, 1, 1);
+  const int tiles = ((g.M + TC_BM - 1) / TC_BM) * (g.N / bn);
+  int splits = sm_count / tiles;
+  const int kblocks = (g.R + PK - 1) / PK;
+  if (splits > (kblocks + 3) / 4) splits = (kblocks + 3) / 4;  // at least 4 k-blocks (256 rows) per CTA
+  if (splits < 1) splits = 1;
+  const int kb_per = (kblocks + splits - 1) / splits;
+  p.rows_per_split = kb_per * PK;
+  splits = (g.R + p.rows_per_split - 1) / p.rows_per_split;
+  dim3 grid(g.N / bn, (g.M + TC_BM - 1) / TC_BM, splits);
+  const CUtensorMap& a = *reinterpret_cast<const CUtensorMap*>(mapDY.opaque);
+  const CUtensorMap& x = *reinterpret_cast<const CUtensorMap*>(mapX.opaque);
+  if (bn == 128)
+    wgrad_pair_kernel<128, 3><<<grid, TC_THREADS, PairSmem<128, 3>::TOTAL, s>>>(a, x, p);
+  else
+    wgrad_pair_kernel<64, 4><<<grid, TC_THREADS, PairSmem<64, 4>::TOTAL, s>>>(a, x, p);
+}
+
+void launch_to_pair(const float* src, void* planes, int64_t plane_stride, int64_t n, float scale, int fmt,
+                    cudaStream_t s) {
+  uint16_t* hi = static_cast<uint16_t*>(planes);
+  int blocks = (int)((n + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (blocks < 1) blocks = 1;
+  if (fmt == kPairBF16)
+    to_pair_kernel<kPairBF16><<<blocks, 256, 0, s>>>(src, hi, hi + plane_stride, n, scale);
+  else
+    to_pair_kernel<kPairF16><<<blocks, 256, 0, s>>>(src, hi, hi + plane_stride, n, scale);
+}
+
+}  // namespace hp

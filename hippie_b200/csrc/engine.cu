@@ -19,6 +19,7 @@
 
 #include "../../include/hippie_b200.h"
 #include "kernels.cuh"
+#include "pair_fmt.cuh"
 
 using namespace hp;
 
@@ -37,12 +38,18 @@ struct BNInfo {
   int gamma = -1, beta = -1;  // param indices
   int64_t run_off = 0;        // offset into bn_mean / bn_var
   int64_t coef_off = 0;       // workspace offset of the 8*C coefficient block
+  int64_t part_off = -1;      // workspace offset of this BatchNorm's statistics partials [tiles][C][2]
+  int ntiles = 0, tile_rows = 0, M = 0;  // shape of the partials the producing conv left (set at launch time)
 };
 struct Act {
   std::string name;
   int L = 0, C = 0;
-  int64_t off = 0;  // workspace float offset of padded row 0
+  int64_t off = -1;   // workspace float offset of padded row 0 of the fp32 tensor (-1: no fp32 copy)
+  int64_t poff = -1;  // workspace float offset of padded row 0 of the fp16 hi plane (-1: no pair planes)
+  int64_t pstride = 0;  // elements between the hi and the lo plane
+  int64_t slot = -1;  // gradient pair tensors: workspace offset of (bound, scale, 1 / scale)
 };
+enum { kF32 = 1, kPlanes = 2, kSlot = 4 };
 struct Conv {
   int w = -1, b = -1;
   int cin = 0, cout = 0, k = 3, stride = 1;
@@ -50,7 +57,7 @@ struct Conv {
   int id = -1;
 };
 struct ConvMaps {  // TMA tensor maps of the tcgen05 path, built at first use after hippie_bind
-  TcMap a_fwd, w64, w128, a_dg, wt64, wt128, wg_dy, wg_x4, wg_x2;
+  TcMap a_fwd, w64, w128, a_dg, w_mn, wg_dy, wg_x;
   bool fwd_ready = false, dg_ready = false;
   int wg_B = -1;  // the wgrad maps bound the reduction rows, so they depend on the batch size
 };
@@ -126,10 +133,14 @@ struct hippie_engine {
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   int launches = 0;
   int n_convs = 0;
+  bool failed = false;  // a tensor-map encode failed while launching (reported by the entry point)
   std::vector<ConvMaps> cmaps;
-  bool use_tc = false;  // tcgen05 3xTF32 implicit GEMM for conv forward / dgrad (conv_path 0); false = FP32 SIMT
+  bool use_tc = false;  // tcgen05 implicit GEMMs over fp16 pair planes (conv_path 0); false = FP32 CUDA-core GEMMs
   std::string tc_note;
-  int bwd_passes = 3;  // conv_path 3: dgrad / wgrad run one tf32 pass (round-to-nearest operands)
+  int64_t wp_off = 0;     // weight pair planes: hi plane at ws + wp_off (as halfs), lo plane param_floats elements later
+  int64_t slots_off = 0;  // (max|g|, max|xhat|, max|k|, 1/scale) per gradient pair tensor, zeroed once per step
+  int n_slots = 0;
+  static constexpr int kMaxSlots = 256;
   // profiling aid (bench.py roofline): CUDA events around every implicit-GEMM launch
   struct ProfRec {
     int kind;
@@ -164,7 +175,7 @@ struct hippie_engine {
     p.name = name, p.ndim = ndim, p.shape[0] = s0, p.shape[1] = s1, p.shape[2] = s2, p.layout = layout;
     p.numel = s0 * (ndim > 1 ? s1 : 1) * (ndim > 2 ? s2 : 1);
     p.off = param_floats;
-    param_floats += (p.numel + 3) & ~(int64_t)3;
+    param_floats += (p.numel + 7) & ~(int64_t)7;  // 16-byte aligned in the fp16 pair planes too
     pidx[name] = (int)params.size();
     params.push_back(p);
     return (int)params.size() - 1;
@@ -272,13 +283,26 @@ struct hippie_engine {
     param_floats = (param_floats + 63) & ~(int64_t)63;
   }
 
-  int act(const std::string& name, int L, int C) {
+  bool pair_mode() const { return cfg.conv_path != 1; }
+  // kinds: kF32 = fp32 tensor, kPlanes = fp16 pair planes (only materialised on the tcgen05 path), kSlot = scale slot
+  int act(const std::string& name, int L, int C, int kinds = kF32) {
     Act a;
     a.name = name, a.L = L, a.C = C;
     const int64_t rows = (int64_t)cfg.max_batch * (L + 2) + 2;  // + one finite guard row on either side
-    a.off = take(rows * C) + C;
+    if (!pair_mode()) kinds = kF32;
+    if (kinds & kF32) a.off = take(rows * C) + C;
+    if (kinds & kPlanes) {
+      a.pstride = rows * C;
+      a.poff = take(rows * C) + C / 2;  // 2 planes x 2 bytes = rows * C floats; row 0 starts C halfs in
+    }
+    if (kinds & kSlot) a.slot = slots_off + 4 * (n_slots++);
     acts.push_back(a);
     return (int)acts.size() - 1;
+  }
+  uint16_t* PL(int i) { return reinterpret_cast<uint16_t*>(ws + acts[i].poff); }
+  // statistics partials of the BatchNorm that follows conv output `a`: tiles of >= 64 logical rows
+  void bn_attach(int bn, int a) {
+    bns[bn].part_off = take((((int64_t)cfg.max_batch * acts[a].L + 63) / 64 + 1) * acts[a].C * 2);
   }
   int grad_of(int a) {
     if (cfg.inference_only) return -1;
@@ -295,7 +319,7 @@ struct hippie_engine {
     c.b = bias ? pidx.at(n + ".bias") : -1;
     c.cin = cin, c.cout = cout, c.k = k, c.stride = stride;
     c.id = n_convs++;
-    if (need_wt && !cfg.inference_only) {
+    if (need_wt && !cfg.inference_only && !pair_mode()) {
       c.wt_off = take((int64_t)cout * cin * k);
       WtEntry e;
       e.w_off = params[c.w].off, e.wt_off = c.wt_off, e.cout = cout, e.cin = cin, e.k = k;
@@ -311,7 +335,8 @@ struct hippie_engine {
     E.stem_w = pidx.at(p + ".conv1.weight");
     E.bn0 = bidx.at(p + ".bn1");
     E.c0 = act(p + ".conv1", E.L0, 64);
-    E.a0 = act(p + ".stem", E.L0, 64);
+    bn_attach(E.bn0, E.c0);
+    E.a0 = act(p + ".stem", E.L0, 64, kF32 | kPlanes);
     if (train_tensors) E.dc0 = gact_or(E.c0);
     int x = E.a0, L = E.L0, in_planes = 64;
     const int planes[4] = {64, 128, 256, 512}, strides[4] = {1, 2, 2, 2};
@@ -327,22 +352,25 @@ struct hippie_engine {
         b.bn1 = bidx.at(q + ".bn1"), b.bn2 = bidx.at(q + ".bn2");
         b.x = x;
         b.c1o = act(q + ".conv1", Lout, out);
-        b.a1 = act(q + ".a1", Lout, out);
+        b.a1 = act(q + ".a1", Lout, out, kF32 | kPlanes);
         b.c2o = act(q + ".conv2", Lout, out);
         if (b.down) {
           b.cs = mkconv(q + ".shortcut.0", out, in_planes, 1, s, false, true);
           b.bns = bidx.at(q + ".shortcut.1");
           b.cso = act(q + ".shortcut", Lout, out);
         }
-        b.out = act(q, Lout, out);
+        b.out = act(q, Lout, out, (li * 2 + bi) < 7 ? (kF32 | kPlanes) : kF32);  // the last block feeds the pooling only
+        bn_attach(b.bn1, b.c1o), bn_attach(b.bn2, b.c2o);
+        if (b.down) bn_attach(b.bns, b.cso);
         if (train_tensors) {
           grad_of(b.x), grad_of(b.out);
           b.g_a1 = act("g:" + q + ".a1", Lout, out);
-          b.dc2 = act("d:" + q + ".conv2", Lout, out);
+          // gradients w.r.t. conv outputs are GEMM operands only: scaled fp16 pair planes on the tcgen05 path
+          b.dc2 = act("d:" + q + ".conv2", Lout, out, kPlanes | kSlot);
           // gradients of stride-2 convs are stored zero-dilated at the INPUT resolution, so their
           // dgrad / wgrad run as stride-1 problems (DESIGN.md "Backward of strided convs")
-          b.dc1 = act("d:" + q + ".conv1", b.down ? L : Lout, out);
-          if (b.down) b.dcs = act("d:" + q + ".shortcut", L, out);
+          b.dc1 = act("d:" + q + ".conv1", b.down ? L : Lout, out, kPlanes | kSlot);
+          if (b.down) b.dcs = act("d:" + q + ".shortcut", L, out, kPlanes | kSlot);
         }
         x = b.out, L = Lout, in_planes = planes[li];
       }
@@ -356,7 +384,7 @@ struct hippie_engine {
     const int z = cfg.z_dim;
     D.prefix = p, D.Lo = Lo;
     D.lin_w = pidx.at(p + ".linear.weight"), D.lin_b = pidx.at(p + ".linear.bias");
-    D.t0 = act(p + ".linear", 4, 512);
+    D.t0 = act(p + ".linear", 4, 512, kF32 | kPlanes);
     int x = D.t0, L = 4, in_planes = 512;
     const int lis[4] = {4, 3, 2, 1}, planes[4] = {256, 128, 64, 64}, strides[4] = {2, 2, 2, 1};
     for (int i = 0; i < 4; ++i) {
@@ -370,25 +398,28 @@ struct hippie_engine {
         b.c2 = mkconv(q + ".conv2", in_planes, in_planes, 3, 1, false, true);
         b.bn2 = bidx.at(q + ".bn2"), b.bn1 = bidx.at(q + ".bn1");
         b.c2o = act(q + ".conv2", L, in_planes);
-        b.a2 = act(q + ".a2", L, in_planes);
+        b.a2 = act(q + ".a2", L, in_planes, b.up ? kF32 : (kF32 | kPlanes));
         if (b.up) {
           b.c1 = mkconv(q + ".conv1.conv", out, in_planes, 3, 1, true, true);
           b.cs = mkconv(q + ".shortcut.0.conv", out, in_planes, 3, 1, true, true);
           b.bns = bidx.at(q + ".shortcut.1");
-          b.a2_up = act(q + ".a2_up", Lout, in_planes);
-          b.x_up = act(q + ".x_up", Lout, in_planes);
+          // the up-sampled copies are conv inputs only: pair planes, no fp32 tensor, on the tcgen05 path
+          b.a2_up = act(q + ".a2_up", Lout, in_planes, kPlanes);
+          b.x_up = act(q + ".x_up", Lout, in_planes, kPlanes);
           b.cso = act(q + ".shortcut", Lout, out);
         } else {
           b.c1 = mkconv(q + ".conv1", out, in_planes, 3, 1, false, true);
         }
         b.c1o = act(q + ".conv1", Lout, out);
-        b.out = act(q, Lout, out);
+        b.out = act(q, Lout, out, (i * 2 + bi) < 7 ? (kF32 | kPlanes) : kF32);  // the last block feeds the tail kernel
+        bn_attach(b.bn2, b.c2o), bn_attach(b.bn1, b.c1o);
+        if (b.up) bn_attach(b.bns, b.cso);
         if (train_tensors) {
           grad_of(b.x), grad_of(b.out);
-          b.dc2 = act("d:" + q + ".conv2", L, in_planes);
-          b.dc1 = act("d:" + q + ".conv1", Lout, out);
+          b.dc2 = act("d:" + q + ".conv2", L, in_planes, kPlanes | kSlot);
+          b.dc1 = act("d:" + q + ".conv1", Lout, out, kPlanes | kSlot);
           if (b.up) {
-            b.dcs = act("d:" + q + ".shortcut", Lout, out);
+            b.dcs = act("d:" + q + ".shortcut", Lout, out, kPlanes | kSlot);
             b.g_a2_up = act("g:" + q + ".a2_up", Lout, in_planes);
             b.g_x_up = act("g:" + q + ".x_up", Lout, in_planes);
           } else {
@@ -412,6 +443,7 @@ struct hippie_engine {
   int64_t off_of(const std::string& n) { return params[pidx.at(n)].off; }
   void build() {
     build_spec();
+    slots_off = take(4 * kMaxSlots);
     const bool tr = !cfg.inference_only;
     const int z = cfg.z_dim;
     n_enc = cfg.multimodal ? 2 : 1, n_dec = n_enc;
@@ -453,9 +485,12 @@ struct hippie_engine {
     part_floats = 4096;
     for (auto& a : acts)
       part_floats = std::max<int64_t>(part_floats, (((int64_t)cfg.max_batch * a.L + 63) / 64 + 1) * a.C * 2);
-    bpart_floats = (int64_t)(kBnBwdMaxChunks + 1) * 512 * 3;
+    bpart_floats = (int64_t)(kBnBwdMaxChunks + 1) * 512 * 6;
     for (int i = 0; i < 2; ++i) part_off[i] = take(part_floats), bpart_off[i] = take(bpart_floats);
     adam_part = take(1024);
+    if (pair_mode()) {
+      wp_off = take(param_floats);  // 2 planes x 2 bytes per parameter
+    }
     for (auto& b : bns) {
       b.coef_off = take(8 * (int64_t)b.C);
       BnEvalEntry e;
@@ -468,7 +503,9 @@ struct hippie_engine {
   }
 
   // ---- helpers ---------------------------------------------------------------------------------
-  float* A(int i) { return ws + acts[i].off; }
+  float* A(int i) { return acts[i].off >= 0 ? ws + acts[i].off : nullptr; }
+  uint16_t* WP() { return reinterpret_cast<uint16_t*>(ws + wp_off); }
+  float* slot(int i) { return ws + acts[i].slot; }
   float* coef(int bn) { return ws + bns[bn].coef_off; }
   float* Pp(int p) { return P + params[p].off; }
   float* Gp(int p) { return G + params[p].off; }
@@ -476,72 +513,81 @@ struct hippie_engine {
   void conv_fwd(const Conv& cv, int in, int out, int bn, int B, bool train, Branch& br) {
     ConvGemm g{};
     g.A = A(in), g.W = Pp(cv.w), g.bias = cv.b >= 0 ? Pp(cv.b) : nullptr, g.C = A(out);
-    g.part = (train && bn >= 0) ? br.part : nullptr;
+    g.part = (train && bn >= 0) ? ws + bns[bn].part_off : nullptr;
     g.M = B * acts[out].L, g.N = cv.cout, g.K = cv.k * cv.cin, g.Lout = acts[out].L;
     g.in_rows = acts[in].L + 2, g.in_stride = cv.stride, g.in_off = cv.k == 3 ? 0 : 1, g.in_C = cv.cin;
     g.out_rows = acts[out].L + 2, g.out_off = 1, g.out_lstride = 1, g.accumulate = 0;
     cudaEvent_t pe = prof_begin(br);
     int tile;
-    if (use_tc && g.Lout <= 128) {
+    if (use_tc) {
       ConvMaps& m = cmaps[cv.id];
+      const uint16_t* wpl = WP() + params[cv.w].off;
       if (!m.fwd_ready) {
-        bool ok = tc_make_act_map(&m.a_fwd, g.A, g.in_C, g.K, g.Lout, g.in_rows, g.in_stride, g.in_off, cfg.max_batch);
-        ok = ok && tc_make_weight_map(&m.w64, g.W, g.N, g.K, 64);
-        if (g.N % 128 == 0) ok = ok && tc_make_weight_map(&m.w128, g.W, g.N, g.K, 128);
-        if (!ok) err = "cuTensorMapEncodeTiled failed (conv forward)", use_tc = false;
-        m.fwd_ready = ok;
+        bool ok = pair_make_act_map(&m.a_fwd, PL(in), acts[in].pstride, kPairF16, g.in_C, g.K, g.Lout, g.in_rows,
+                                    g.in_stride, g.in_off, cfg.max_batch);
+        ok = ok && pair_make_w_map(&m.w64, wpl, param_floats, kPairF16, g.N, g.K, 64);
+        if (g.N % 128 == 0) ok = ok && pair_make_w_map(&m.w128, wpl, param_floats, kPairF16, g.N, g.K, 128);
+        if (!ok) return (void)(err = "cuTensorMapEncodeTiled failed (conv forward)", failed = true);
+        m.fwd_ready = true;
       }
-    }
-    if (use_tc && g.Lout <= 128) {
-      ConvMaps& m = cmaps[cv.id];
-      const int bn = tc_pick_bn(B, g.N, g.Lout, sm_count);
-      tile = launch_conv_gemm_tc(g, m.a_fwd, bn == 128 ? m.w128 : m.w64, bn, B, 3, br.st);
+      const int bn_tile = pair_pick_bn(B, g.N, g.Lout, sm_count);
+      PairOpts o{1.f / kWeightPairScale, kPairF16, kPairF16, 0, cv.k};
+      tile = launch_conv_pair(g, m.a_fwd, bn_tile == 128 ? m.w128 : m.w64, bn_tile, B, o, br.st);
     } else {
       tile = launch_conv_gemm_simt(g, br.st);
     }
     prof_end(pe, 0, 2.0 * g.M * g.N * g.K, br);
     ++launches;
-    if (train && bn >= 0) bn_finalize(bn, br.part, (g.M + tile - 1) / tile, tile, g.M, br);
+    if (train && bn >= 0) bns[bn].ntiles = (g.M + tile - 1) / tile, bns[bn].tile_rows = tile, bns[bn].M = g.M;
   }
-  void bn_finalize(int bn, const float* part, int ntiles, int tile, int M, Branch& br) {
+  // the apply kernel turns the partials the conv left into coefficients (and running statistics) itself
+  BnFinalize finalize_args(int bn) {
     BnFinalize f{};
-    f.part = part, f.ntiles = ntiles, f.tile_rows = tile, f.M = M, f.C = bns[bn].C;
+    f.part = ws + bns[bn].part_off, f.ntiles = bns[bn].ntiles, f.tile_rows = bns[bn].tile_rows, f.M = bns[bn].M;
+    f.C = bns[bn].C;
     f.gamma = Pp(bns[bn].gamma), f.beta = Pp(bns[bn].beta);
     f.run_mean = bn_mean + bns[bn].run_off, f.run_var = bn_var + bns[bn].run_off, f.run_count = bn_count + bn;
     f.coef = coef(bn);
-    launch_bn_finalize_train(f, br.st);
-    ++launches;
+    return f;
   }
-  void apply(int c, int bn, int r, int rbn, int out, int out_up, int B, Branch& br) {
+  void apply(int c, int bn, int r, int rbn, int out, int out_up, int B, bool train, Branch& br) {
     BnApply a{};
+    a.train = train ? 1 : 0;
+    if (train) {
+      a.fin = finalize_args(bn);
+      if (rbn >= 0) a.rfin = finalize_args(rbn);
+    }
     a.c = A(c), a.coef = coef(bn), a.r = r >= 0 ? A(r) : nullptr, a.rcoef = rbn >= 0 ? coef(rbn) : nullptr;
     a.out = A(out), a.out_up = out_up >= 0 ? A(out_up) : nullptr;
     a.B = B, a.L = acts[c].L, a.C = acts[c].C, a.slope = kSlopeBackbone;
-    launch_bn_apply(a, br.st);
+    if (use_tc) {
+      if (acts[out].poff >= 0) a.out_p = PL(out), a.out_ps = acts[out].pstride;
+      if (out_up >= 0 && acts[out_up].poff >= 0) a.up_p = PL(out_up), a.up_ps = acts[out_up].pstride;
+    }
+    launch_bn_apply(a, sm_count, br.st);
     ++launches;
   }
   // dgrad as a stride-1 convolution of the (dilated) output gradient with the transposed weights
   void dgrad(const Conv& cv, int dy, int gx, bool accumulate, int B, Branch& br) {
     ConvGemm g{};
-    g.A = A(dy), g.W = ws + cv.wt_off, g.bias = nullptr, g.C = A(gx), g.part = nullptr;
+    g.A = A(dy), g.W = cv.wt_off >= 0 ? ws + cv.wt_off : nullptr, g.bias = nullptr, g.C = A(gx), g.part = nullptr;
     g.M = B * acts[gx].L, g.N = cv.cin, g.K = cv.k * cv.cout, g.Lout = acts[gx].L;
     g.in_rows = acts[dy].L + 2, g.in_stride = 1, g.in_off = cv.k == 3 ? 0 : 1, g.in_C = cv.cout;
     g.out_rows = acts[gx].L + 2, g.out_off = 1, g.out_lstride = 1, g.accumulate = accumulate ? 1 : 0;
     cudaEvent_t pe = prof_begin(br);
-    if (use_tc && g.Lout <= 128) {
+    if (use_tc) {
       ConvMaps& m = cmaps[cv.id];
       if (!m.dg_ready) {
-        bool ok = tc_make_act_map(&m.a_dg, g.A, g.in_C, g.K, g.Lout, g.in_rows, g.in_stride, g.in_off, cfg.max_batch);
-        ok = ok && tc_make_weight_map(&m.wt64, g.W, g.N, g.K, 64);
-        if (g.N % 128 == 0) ok = ok && tc_make_weight_map(&m.wt128, g.W, g.N, g.K, 128);
-        if (!ok) err = "cuTensorMapEncodeTiled failed (conv dgrad)", use_tc = false;
-        m.dg_ready = ok;
+        bool ok = pair_make_act_map(&m.a_dg, PL(dy), acts[dy].pstride, kPairF16, g.in_C, g.K, g.Lout, g.in_rows, 1,
+                                    g.in_off, cfg.max_batch);
+        ok = ok && pair_make_wmn_map(&m.w_mn, WP() + params[cv.w].off, param_floats, kPairF16, cv.cout, cv.cin, cv.k);
+        if (!ok) return (void)(err = "cuTensorMapEncodeTiled failed (conv dgrad)", failed = true);
+        m.dg_ready = true;
       }
-    }
-    if (use_tc && g.Lout <= 128) {
-      ConvMaps& m = cmaps[cv.id];
-      const int bn = tc_pick_bn(B, g.N, g.Lout, sm_count);
-      launch_conv_gemm_tc(g, m.a_dg, bn == 128 ? m.wt128 : m.wt64, bn, B, bwd_passes, br.st);
+      const int bn_tile = pair_pick_bn(B, g.N, g.Lout, sm_count);
+      PairOpts o{1.f / kWeightPairScale, kPairF16, kPairF16, 1, cv.k};
+      o.dyn_scale = slot(dy) + 3;
+      launch_conv_pair(g, m.a_dg, m.w_mn, bn_tile, B, o, br.st);
     } else {
       launch_conv_gemm_simt(g, br.st);
     }
@@ -562,17 +608,14 @@ struct hippie_engine {
     if (use_tc) {
       ConvMaps& m = cmaps[cv.id];
       if (m.wg_B != B) {
-        bool ok = tc_make_rows_map(&m.wg_dy, g.dY, g.M, g.M, g.R, 4);
-        ok = ok && tc_make_rows_map(&m.wg_x4, g.X + (int64_t)g.roff * g.Cin, g.Cin, g.N, g.R, 4);
-        ok = ok && tc_make_rows_map(&m.wg_x2, g.X + (int64_t)g.roff * g.Cin, g.Cin, g.N, g.R, 2);
-        if (!ok) err = "cuTensorMapEncodeTiled failed (conv wgrad)", use_tc = false;
-        m.wg_B = ok ? B : -1;
+        bool ok = pair_make_rows_map(&m.wg_dy, PL(dy), acts[dy].pstride, kPairF16, g.M, g.M, g.R);
+        ok = ok && pair_make_rows_map(&m.wg_x, PL(x) + (int64_t)g.roff * g.Cin, acts[x].pstride, kPairF16, g.Cin, g.N, g.R);
+        if (!ok) return (void)(err = "cuTensorMapEncodeTiled failed (conv wgrad)", failed = true);
+        m.wg_B = B;
       }
-    }
-    if (use_tc) {
-      ConvMaps& m = cmaps[cv.id];
-      const int bn = (g.N % 128 == 0) ? 128 : 64;
-      launch_wgrad_tc(g, m.wg_dy, bn == 128 ? m.wg_x4 : m.wg_x2, bn, sm_count, bwd_passes, wst);
+      PairOpts o{1.f, kPairF16, kPairF16, 1, cv.k};
+      o.dyn_scale = slot(dy) + 3;
+      launch_wgrad_pair(g, m.wg_dy, m.wg_x, (g.N % 128 == 0) ? 128 : 64, sm_count, o, wst);
     } else {
       launch_wgrad_simt(g, sm_count, wst);
     }
@@ -590,26 +633,28 @@ struct hippie_engine {
     if (cs >= 0) a.gamma_s = Pp(bns[bnsi].gamma), a.dgamma_s = Gp(bns[bnsi].gamma), a.dbeta_s = Gp(bns[bnsi].beta);
     a.dc = A(dc), a.dil = dil, a.Ld = acts[dc].L;
     if (cs >= 0) a.dcs = A(dcs), a.dil_s = dil_s, a.Ld_s = acts[dcs].L;
+    if (use_tc && acts[dc].poff >= 0) a.dc_p = PL(dc), a.dc_ps = acts[dc].pstride, a.dc_slot = slot(dc);
+    if (use_tc && cs >= 0 && acts[dcs].poff >= 0) a.dcs_p = PL(dcs), a.dcs_ps = acts[dcs].pstride, a.dcs_slot = slot(dcs);
     a.gres = gres >= 0 ? A(gres) : nullptr;
     launch_bn_bwd(a, sm_count, br.st);
     launches += kBnBwdLaunches;
   }
 
   void encoder_fwd(Encoder& E, const float* x, int B, bool train, Branch& br) {
-    launch_stem_fwd(x, Pp(E.stem_w), A(E.c0), train ? br.part : nullptr, B, E.Lin, E.L0, br.st);
+    launch_stem_fwd(x, Pp(E.stem_w), A(E.c0), train ? ws + bns[E.bn0].part_off : nullptr, B, E.Lin, E.L0, br.st);
     ++launches;
-    if (train) bn_finalize(E.bn0, br.part, (B * E.L0 + 127) / 128, 128, B * E.L0, br);
-    apply(E.c0, E.bn0, -1, -1, E.a0, -1, B, br);
+    if (train) bns[E.bn0].ntiles = (B * E.L0 + 127) / 128, bns[E.bn0].tile_rows = 128, bns[E.bn0].M = B * E.L0;
+    apply(E.c0, E.bn0, -1, -1, E.a0, -1, B, train, br);
     for (int i = 0; i < 8; ++i) {
       EncBlock& b = E.blk[i];
       conv_fwd(b.c1, b.x, b.c1o, b.bn1, B, train, br);
-      apply(b.c1o, b.bn1, -1, -1, b.a1, -1, B, br);
+      apply(b.c1o, b.bn1, -1, -1, b.a1, -1, B, train, br);
       conv_fwd(b.c2, b.a1, b.c2o, b.bn2, B, train, br);
       if (b.down) {
         conv_fwd(b.cs, b.x, b.cso, b.bns, B, train, br);
-        apply(b.c2o, b.bn2, b.cso, b.bns, b.out, -1, B, br);
+        apply(b.c2o, b.bn2, b.cso, b.bns, b.out, -1, B, train, br);
       } else {
-        apply(b.c2o, b.bn2, b.x, -1, b.out, -1, B, br);
+        apply(b.c2o, b.bn2, b.x, -1, b.out, -1, B, train, br);
       }
     }
     const int last = E.blk[7].out;
@@ -643,19 +688,20 @@ struct hippie_engine {
   }
 
   void decoder_fwd(Decoder& D, int B, bool train, Branch& br) {
-    launch_dec_linear_fwd(ws + D.d, B, 2 * cfg.z_dim, Pp(D.lin_w), Pp(D.lin_b), 512, A(D.t0), nullptr, br.st);
+    launch_dec_linear_fwd(ws + D.d, B, 2 * cfg.z_dim, Pp(D.lin_w), Pp(D.lin_b), 512, A(D.t0),
+                          use_tc ? PL(D.t0) : nullptr, acts[D.t0].pstride, br.st);
     ++launches;
     for (int i = 0; i < 8; ++i) {
       DecBlock& b = D.blk[i];
       conv_fwd(b.c2, b.x, b.c2o, b.bn2, B, train, br);
-      apply(b.c2o, b.bn2, -1, -1, b.a2, b.a2_up, B, br);
+      apply(b.c2o, b.bn2, -1, -1, b.a2, b.a2_up, B, train, br);
       if (b.up) {
         conv_fwd(b.c1, b.a2_up, b.c1o, b.bn1, B, train, br);
         conv_fwd(b.cs, b.x_up, b.cso, b.bns, B, train, br);
-        apply(b.c1o, b.bn1, b.cso, b.bns, b.out, b.out_up, B, br);
+        apply(b.c1o, b.bn1, b.cso, b.bns, b.out, b.out_up, B, train, br);
       } else {
         conv_fwd(b.c1, b.a2, b.c1o, b.bn1, B, train, br);
-        apply(b.c1o, b.bn1, b.x, -1, b.out, b.out_up, B, br);
+        apply(b.c1o, b.bn1, b.x, -1, b.out, b.out_up, B, train, br);
       }
     }
   }
@@ -723,6 +769,17 @@ struct hippie_engine {
     return a;
   }
 
+  // tcgen05 path: fp16 pair planes of the whole parameter buffer (scaled 2^8), used K-major by the forward convs and
+  // MN-major by dgrad.  FP32 path: transposed + tap-flipped copies for dgrad.
+  void refresh_weights(bool backward, cudaStream_t main) {
+    if (use_tc) {
+      launch_to_pair(P, WP(), param_floats, param_floats, kWeightPairScale, kPairF16, main);
+      ++launches;
+    } else if (backward && !wt_table.empty()) {
+      launch_refresh_wt(reinterpret_cast<const WtEntry*>(ws + wt_table_off), (int)wt_table.size(), P, ws, main);
+      ++launches;
+    }
+  }
   void fork(cudaStream_t main) {
     cudaEventRecord(ev_fork, main);
     cudaStreamWaitEvent(side, ev_fork, 0);
@@ -760,9 +817,9 @@ struct hippie_engine {
     cudaMemsetAsync(ws + scal_off, 0, 64 * sizeof(float), main);
     if (backward) {
       cudaMemsetAsync(G, 0, param_floats * sizeof(float), main);
-      launch_refresh_wt(reinterpret_cast<const WtEntry*>(ws + wt_table_off), (int)wt_table.size(), P, ws, main);
-      ++launches;
+      if (use_tc) cudaMemsetAsync(ws + slots_off, 0, 4 * kMaxSlots * sizeof(float), main);
     }
+    refresh_weights(backward, main);
     if (!train) {
       launch_bn_eval_coefs(reinterpret_cast<const BnEvalEntry*>(ws + bn_table_off), (int)bn_table.size(), P, bn_mean,
                            bn_var, ws, main);
@@ -807,6 +864,7 @@ struct hippie_engine {
           cudaStreamWaitEvent(main, e, 0);
         }
     }
+    if (failed) return fail(-9, err);
     return check(train ? "train_fwd_bwd" : "eval_forward");
   }
 };
@@ -869,7 +927,7 @@ int hippie_bn_info(hippie_handle h, int idx, char* name, int name_cap, int64_t* 
   return 0;
 }
 size_t hippie_workspace_bytes(hippie_handle h) { return h ? (size_t)h->ws_floats * sizeof(float) : 0; }
-int hippie_num_tensors(hippie_handle h) { return h ? (int)h->acts.size() : -1; }
+int hippie_num_tensors(hippie_handle h) { return h ? (int)h->acts.size() : -1; }  // offset -1: no fp32 copy exists
 int hippie_tensor_info(hippie_handle h, int idx, char* name, int name_cap, int64_t* offset, int32_t* L, int32_t* C,
                        int32_t* pad) {
   if (!h || idx < 0 || idx >= (int)h->acts.size()) return -1;
@@ -908,11 +966,10 @@ int hippie_bind(hippie_handle h, float* params, float* grads, float* exp_avg, fl
   }
   cudaMemsetAsync(workspace, 0, (size_t)h->ws_floats * sizeof(float), st);
   h->cmaps.assign(h->n_convs, ConvMaps{});
-  h->use_tc = false;
-  if (h->cfg.conv_path != 1) {
-    h->use_tc = tc_init(&h->tc_note);
-    h->bwd_passes = h->cfg.conv_path == 3 ? 1 : 3;
-    if (!h->use_tc && h->cfg.conv_path >= 2) return h->fail(-8, "tcgen05 path requested but unavailable: " + h->tc_note);
+  h->use_tc = false, h->failed = false;
+  if (h->pair_mode()) {
+    h->use_tc = pair_init(&h->tc_note);
+    if (!h->use_tc) return h->fail(-8, "tcgen05 path unavailable: " + h->tc_note);
   }
   if (!h->wt_table.empty())
     cudaMemcpyAsync(h->ws + h->wt_table_off, h->wt_table.data(), h->wt_table.size() * sizeof(WtEntry),
@@ -965,6 +1022,7 @@ int hippie_embed(hippie_handle h, const float* x1, const float* x2, const int64_
   launch_bn_eval_coefs(reinterpret_cast<const BnEvalEntry*>(h->ws + h->bn_table_off), (int)h->bn_table.size(), h->P,
                        h->bn_mean, h->bn_var, h->ws, main);
   ++h->launches;
+  h->refresh_weights(false, main);
   const bool two = h->n_enc == 2;
   if (two) h->fork(main);
   h->encoder_fwd(h->enc[0], x1, B, false, b0);
@@ -976,6 +1034,7 @@ int hippie_embed(hippie_handle h, const float* x1, const float* x2, const int64_
   ha.kl_sum = nullptr;
   launch_head_fwd(ha, main);
   ++h->launches;
+  if (h->failed) return h->fail(-9, h->err);
   return h->check("hippie_embed");
 }
 

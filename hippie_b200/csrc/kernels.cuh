@@ -72,6 +72,30 @@ struct WgradGemm {
 };
 void launch_wgrad_simt(const WgradGemm& g, int sm_count, cudaStream_t s);
 
+// ---- 16-bit pair planes (conv_pair.cu): operands are (hi, lo) planes written by the producing kernels ----
+struct PairOpts {
+  float out_scale;   // applied to the accumulator sum in the epilogue (2^-8 when B holds scaled weights)
+  int a_fmt, b_fmt;  // kPairF16 / kPairBF16 (pair_fmt.cuh)
+  int b_mn;          // conv: 1 = B tiles read MN-major from the forward weight planes [co][t][ci] (dgrad)
+  int taps;          // conv, b_mn = 1: kernel size of the layer
+  const float* dyn_scale = nullptr;  // device float multiplied into out_scale (1 / scale of a gradient pair tensor)
+};
+bool pair_init(std::string* err);
+bool pair_make_act_map(TcMap* out, const void* planes, int64_t plane_stride, int fmt, int in_C, int K, int Lout,
+                       int in_rows, int in_stride, int in_off, int max_batch);
+bool pair_make_w_map(TcMap* out, const void* planes, int64_t plane_stride, int fmt, int N, int K, int bn);
+bool pair_make_wmn_map(TcMap* out, const void* planes, int64_t plane_stride, int fmt, int Cout, int Cin, int k);
+bool pair_make_rows_map(TcMap* out, const void* planes, int64_t plane_stride, int fmt, int64_t row_elems, int channels,
+                        int rows);
+int pair_pick_bn(int B, int N, int Lout, int sm_count);
+int launch_conv_pair(const ConvGemm& g, const TcMap& mapA, const TcMap& mapB, int bn, int B, const PairOpts& o,
+                     cudaStream_t s);
+void launch_wgrad_pair(const WgradGemm& g, const TcMap& mapDY, const TcMap& mapX, int bn, int sm_count, const PairOpts& o,
+                       cudaStream_t s);
+// planes[0 .. n) = hi(src * scale), planes[plane_stride .. plane_stride + n) = lo
+void launch_to_pair(const float* src, void* planes, int64_t plane_stride, int64_t n, float scale, int fmt, cudaStream_t s);
+
+
 // ---- stem conv (Cin = 1, k3, s2, p1)  reference hippie/backbones.py:78,95 -----------------------------
 void launch_stem_fwd(const float* x, const float* w /*[64][3]*/, float* c0, float* part, int B, int Lin, int Lout,
                      cudaStream_t s);
@@ -93,7 +117,6 @@ struct BnFinalize {
   int64_t* run_count;
   float* coef;
 };
-void launch_bn_finalize_train(const BnFinalize& f, cudaStream_t s);
 // eval mode, all BatchNorms of the model in one launch: scale/shift from the running statistics
 struct BnEvalEntry {
   int64_t gamma_off, beta_off, run_off, coef_off;
@@ -112,8 +135,18 @@ struct BnApply {
   float* out_up;  // [B][2L+2][C] or null
   int B, L, C;
   float slope;
+  // train = 1: (scale, shift) come from the conv's statistics partials (fin / rfin: coef, running buffers, part,
+  // ntiles, tile_rows, M, C filled in); train = 0: from coef / rcoef (eval mode: bn_eval_coefs)
+  int train = 0;
+  BnFinalize fin{};
+  BnFinalize rfin{};
+  // fp16 pair planes of `out` / of the up-sampled copy (row 0 of the hi plane; lo plane `*_ps` elements later), or null
+  uint16_t* out_p = nullptr;
+  int64_t out_ps = 0;
+  uint16_t* up_p = nullptr;
+  int64_t up_ps = 0;
 };
-void launch_bn_apply(const BnApply& a, cudaStream_t s);
+void launch_bn_apply(const BnApply& a, int sm_count, cudaStream_t s);
 
 // backward of  out = lrelu(bn(c) + [bn_s(cs) | identity]) :
 //   g_pre = g * (out > 0 ? 1 : slope);  per channel S1 = sum g_pre, S2 = sum g_pre * xhat, S2s likewise for cs
@@ -125,7 +158,7 @@ struct BnBwd {
   float* coef;
   const float* cs;  // shortcut conv output or null
   float* coef_s;
-  float* part;  // [nchunks][C][3]
+  float* part;  // [nchunks][C][3] = (S1, S2, S2s)
   int B, L, C;
   float slope;
   // finalize: parameter gradients
@@ -141,10 +174,19 @@ struct BnBwd {
   float* dcs;
   int dil_s, Ld_s;
   float* gres;  // if non-null: g_pre is written here (identity shortcut), same layout as out
+  // pair path: dc / dcs may be null; the gradients go to fp16 pair planes scaled by a power of two chosen from an upper
+  // bound of max|dc|.  slot = (max|g_pre|, max|xhat|, max|gamma*invstd|, 1 / scale): [0..2] are atomicMax targets that
+  // the engine zeroes once per step, [3] is read by the dgrad / wgrad epilogues
+  uint16_t* dc_p = nullptr;
+  int64_t dc_ps = 0;
+  float* dc_slot = nullptr;
+  uint16_t* dcs_p = nullptr;
+  int64_t dcs_ps = 0;
+  float* dcs_slot = nullptr;
 };
-void launch_bn_bwd(const BnBwd& a, int sm_count, cudaStream_t s);  // reduce + finalize + apply (3 launches)
-constexpr int kBnBwdLaunches = 3;
-constexpr int kBnBwdMaxChunks = 444;  // 3 CTAs per SM on 148 SMs
+void launch_bn_bwd(const BnBwd& a, int sm_count, cudaStream_t s);  // reduce + apply (2 launches)
+constexpr int kBnBwdLaunches = 2;
+constexpr int kBnBwdMaxChunks = 128;  // every apply CTA re-sums the partials of its 32 channels
 
 // dst[b,l,c] += src[b,2l,c] + src[b,2l+1,c]     (backward of nearest x2 up-sampling)
 void launch_pairsum_acc(const float* src, float* dst, int B, int L, int C, cudaStream_t s);
@@ -159,7 +201,7 @@ constexpr int kPoolLinearBwdLaunches = 2;
 
 // ---- decoder head: Linear(F -> 512) + unsqueeze + nearest x4   reference hippie/backbones.py:129-131 ---
 void launch_dec_linear_fwd(const float* d, int B, int F, const float* W, const float* bias, int C, float* t0,
-                           float* t0_up /*unused*/, cudaStream_t s);
+                           uint16_t* t0_p /*fp16 pair planes or null*/, int64_t t0_ps, cudaStream_t s);
 void launch_dec_linear_bwd(const float* g_t0, const float* d, const float* W, int B, int F, int C, float* gx0,
                            float* dd, float* dW, float* db, cudaStream_t s);
 constexpr int kDecLinearBwdLaunches = 2;

@@ -2,12 +2,32 @@
 // linear tails, decoder head and tail (+ MSE), gradient clipping + AdamW.  All tensors are
 // channels-last padded rows (kernels.cuh).  Reference anchors are given per kernel.
 #include "kernels.cuh"
+#include "pair_fmt.cuh"
 
 namespace hp {
 
 namespace {
 
 __device__ __forceinline__ float lrelu(float x, float slope) { return x > 0.f ? x : x * slope; }
+// 4 consecutive channels -> fp16 pair planes (hi at p, lo at p + ps), 8 bytes per plane
+__device__ __forceinline__ void store_pair4(uint16_t* p, int64_t ps, int64_t idx, float4 v) {
+  uint16_t h0, h1, h2, h3, l0, l1, l2, l3;
+  pair_split<kPairF16>(v.x, h0, l0), pair_split<kPairF16>(v.y, h1, l1);
+  pair_split<kPairF16>(v.z, h2, l2), pair_split<kPairF16>(v.w, h3, l3);
+  *reinterpret_cast<uint2*>(p + idx) = make_uint2((uint32_t)h0 | ((uint32_t)h1 << 16), (uint32_t)h2 | ((uint32_t)h3 << 16));
+  *reinterpret_cast<uint2*>(p + ps + idx) = make_uint2((uint32_t)l0 | ((uint32_t)l1 << 16), (uint32_t)l2 | ((uint32_t)l3 << 16));
+}
+// power of two s with bound * s in [2^13, 2^14): the scale of a gradient pair tensor whose |values| <= bound
+__device__ __forceinline__ float pair_scale_from_bound(float bound) {
+  if (!(bound > 0.f) || bound > 3.0e38f) return 1.f;
+  const int e = (int)((__float_as_uint(bound) >> 23) & 0xFFu) - 127;
+  int se = 13 - e;
+  se = se < -126 ? -126 : (se > 126 ? 126 : se);
+  return __uint_as_float((uint32_t)(se + 127) << 23);
+}
+__device__ __forceinline__ float4 fmax4abs(float4 m, float4 v) {
+  return make_float4(fmaxf(m.x, fabsf(v.x)), fmaxf(m.y, fabsf(v.y)), fmaxf(m.z, fabsf(v.z)), fmaxf(m.w, fabsf(v.w)));
+}
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -105,38 +125,57 @@ __global__ void reduce_partials_kernel(const float* __restrict__ part, int npart
 }
 
 // ------------------------------------------------------------------------------------------------
-// BatchNorm1d, training statistics (nn.BatchNorm1d defaults: eps 1e-5, momentum 0.1, biased variance
-// to normalise, unbiased into running_var).  One warp per channel, Chan's parallel combination of
-// the per-tile (sum, centred M2) partials in double.
+// BatchNorm1d (nn.BatchNorm1d defaults: eps 1e-5, momentum 0.1, biased variance to normalise, unbiased into
+// running_var).  The producing conv leaves per-tile (sum, centred M2) partials; every CTA of the apply kernel owns a
+// slab of 32 channels and first turns the partials of ITS channels into (scale, shift) -- Chan's parallel combination
+// in double, fixed order -- so there is no separate finalize launch.  CTAs with blockIdx.y == 0 also publish the
+// coefficients (mean / invstd are needed by the backward pass) and update the running statistics.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) bn_finalize_train_kernel(BnFinalize f) {
-  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (c >= f.C) return;
-  double S = 0.0;
-  for (int t = lane; t < f.ntiles; t += 32) S += (double)f.part[((int64_t)t * f.C + c) * 2];
-  S = warp_sum_d(S);
-  const double mean = S / (double)f.M;
-  double M2 = 0.0;
-  for (int t = lane; t < f.ntiles; t += 32) {
-    int nt = min(f.tile_rows, f.M - t * f.tile_rows);
-    double st = (double)f.part[((int64_t)t * f.C + c) * 2], m2 = (double)f.part[((int64_t)t * f.C + c) * 2 + 1];
-    double d = st / (double)nt - mean;
-    M2 += m2 + (double)nt * d * d;
+constexpr int kSlab = 32;  // channels per CTA: 128-byte row segments
+
+struct ChanAcc {
+  double n, mean, m2;
+};
+__device__ __forceinline__ void chan_merge(ChanAcc& a, double nb, double mean_b, double m2_b) {
+  if (nb <= 0.0) return;
+  const double n = a.n + nb, delta = mean_b - a.mean;
+  a.mean += delta * (nb / n);
+  a.m2 += m2_b + delta * delta * (a.n * nb / n);
+  a.n = n;
+}
+
+// 256 threads.  Results for the slab's channels land in shared arrays sc / sh / mu (scale, shift = beta, mean).
+__device__ __forceinline__ void bn_finalize_slab(const BnFinalize& f, int c0, bool publish, float* sc, float* sh,
+                                                 float* mu, ChanAcc (*acc)[kSlab]) {
+  const int c = threadIdx.x & (kSlab - 1), slice = threadIdx.x >> 5;  // 8 slices of tiles
+  ChanAcc a{0.0, 0.0, 0.0};
+  for (int t = slice; t < f.ntiles; t += 8) {
+    const float2 p = __ldcg(reinterpret_cast<const float2*>(f.part + ((int64_t)t * f.C + c0 + c) * 2));
+    const int nt = min(f.tile_rows, f.M - t * f.tile_rows);
+    chan_merge(a, (double)nt, (double)p.x / (double)nt, (double)p.y);
   }
-  M2 = warp_sum_d(M2);
-  if (lane == 0) {
-    const double var_b = M2 / (double)f.M;
+  acc[slice][c] = a;
+  __syncthreads();
+  if (slice == 0) {
+    for (int k = 1; k < 8; ++k) chan_merge(a, acc[k][c].n, acc[k][c].mean, acc[k][c].m2);
+    const double var_b = a.m2 / (double)f.M;
     const float invstd = (float)(1.0 / sqrt(var_b + (double)kBnEps));
-    const float meanf = (float)mean;
-    f.coef[0 * f.C + c] = f.gamma[c] * invstd;
-    f.coef[1 * f.C + c] = f.beta[c];
-    f.coef[2 * f.C + c] = meanf;
-    f.coef[3 * f.C + c] = invstd;
-    const float var_u = (float)(M2 / (double)max(f.M - 1, 1));
-    f.run_mean[c] = (1.f - kBnMomentum) * f.run_mean[c] + kBnMomentum * meanf;
-    f.run_var[c] = (1.f - kBnMomentum) * f.run_var[c] + kBnMomentum * var_u;
-    if (c == 0) *f.run_count += 1;
+    const float meanf = (float)a.mean;
+    const int cc = c0 + c;
+    const float scale = f.gamma[cc] * invstd, beta = f.beta[cc];
+    sc[c] = scale, sh[c] = beta, mu[c] = meanf;
+    if (publish) {
+      f.coef[0 * f.C + cc] = scale;
+      f.coef[1 * f.C + cc] = beta;
+      f.coef[2 * f.C + cc] = meanf;
+      f.coef[3 * f.C + cc] = invstd;
+      const float var_u = (float)(a.m2 / (double)max(f.M - 1, 1));
+      f.run_mean[cc] = (1.f - kBnMomentum) * f.run_mean[cc] + kBnMomentum * meanf;
+      f.run_var[cc] = (1.f - kBnMomentum) * f.run_var[cc] + kBnMomentum * var_u;
+      if (cc == 0) *f.run_count += 1;
+    }
   }
+  __syncthreads();
 }
 
 __global__ void bn_eval_coefs_kernel(const BnEvalEntry* __restrict__ tab, const float* __restrict__ params,
@@ -154,89 +193,148 @@ __global__ void bn_eval_coefs_kernel(const BnEvalEntry* __restrict__ tab, const 
 }
 
 // out = lrelu((c - mean)*scale + beta + residual)   reference hippie/backbones.py:37-40,66-69,95
+// grid = (C / 32, row chunks); thread = (channel quad of the slab, row lane)
 template <int RES>  // 0 none, 1 identity, 2 BatchNorm'd shortcut
 __global__ void __launch_bounds__(256) bn_apply_kernel(BnApply a) {
-  const int C4 = a.C >> 2;
-  const int64_t total = (int64_t)a.B * a.L * C4;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int cq = (int)(i % C4);
-    const int64_t m = i / C4;
-    const int b = (int)(m / a.L), l = (int)(m - (int64_t)b * a.L);
+  __shared__ float s_sc[kSlab], s_sh[kSlab], s_mu[kSlab], r_sc[kSlab], r_sh[kSlab], r_mu[kSlab];
+  __shared__ ChanAcc s_acc[8][kSlab];
+  const int c0 = blockIdx.x * kSlab;
+  if (a.train) {
+    bn_finalize_slab(a.fin, c0, blockIdx.y == 0, s_sc, s_sh, s_mu, s_acc);
+    if (RES == 2) bn_finalize_slab(a.rfin, c0, blockIdx.y == 0, r_sc, r_sh, r_mu, s_acc);
+  } else {
+    if (threadIdx.x < kSlab) {
+      const int cc = c0 + threadIdx.x;
+      s_sc[threadIdx.x] = a.coef[0 * a.C + cc], s_sh[threadIdx.x] = a.coef[1 * a.C + cc];
+      s_mu[threadIdx.x] = a.coef[2 * a.C + cc];
+      if (RES == 2) {
+        r_sc[threadIdx.x] = a.rcoef[0 * a.C + cc], r_sh[threadIdx.x] = a.rcoef[1 * a.C + cc];
+        r_mu[threadIdx.x] = a.rcoef[2 * a.C + cc];
+      }
+    }
+    __syncthreads();
+  }
+  const int q = threadIdx.x & 7, rl = threadIdx.x >> 3;
+  const float4 sc = *reinterpret_cast<const float4*>(s_sc + q * 4), be = *reinterpret_cast<const float4*>(s_sh + q * 4);
+  const float4 mu = *reinterpret_cast<const float4*>(s_mu + q * 4);
+  float4 rs = sc, rb = be, rm = mu;
+  if (RES == 2) {
+    rs = *reinterpret_cast<const float4*>(r_sc + q * 4), rb = *reinterpret_cast<const float4*>(r_sh + q * 4);
+    rm = *reinterpret_cast<const float4*>(r_mu + q * 4);
+  }
+  const int M = a.B * a.L;
+  const int rows_per = (M + gridDim.y - 1) / gridDim.y;
+  const int m_end = min(M, (int)(blockIdx.y + 1) * rows_per);
+  const int col = c0 + q * 4;
+  for (int m = blockIdx.y * rows_per + rl; m < m_end; m += 32) {
+    const int b = m / a.L, l = m - b * a.L;
     const int64_t row = (int64_t)b * (a.L + 2) + 1 + l;
-    const float4 x = *reinterpret_cast<const float4*>(a.c + row * a.C + cq * 4);
-    const float4 sc = *reinterpret_cast<const float4*>(a.coef + 0 * a.C + cq * 4);
-    const float4 be = *reinterpret_cast<const float4*>(a.coef + 1 * a.C + cq * 4);
-    const float4 mu = *reinterpret_cast<const float4*>(a.coef + 2 * a.C + cq * 4);
+    const float4 x = *reinterpret_cast<const float4*>(a.c + row * a.C + col);
     float4 y;
     y.x = fmaf(x.x - mu.x, sc.x, be.x), y.y = fmaf(x.y - mu.y, sc.y, be.y);
     y.z = fmaf(x.z - mu.z, sc.z, be.z), y.w = fmaf(x.w - mu.w, sc.w, be.w);
     if (RES == 1) {
-      const float4 r = *reinterpret_cast<const float4*>(a.r + row * a.C + cq * 4);
+      const float4 r = *reinterpret_cast<const float4*>(a.r + row * a.C + col);
       y.x += r.x, y.y += r.y, y.z += r.z, y.w += r.w;
     } else if (RES == 2) {
-      const float4 r = *reinterpret_cast<const float4*>(a.r + row * a.C + cq * 4);
-      const float4 rs = *reinterpret_cast<const float4*>(a.rcoef + 0 * a.C + cq * 4);
-      const float4 rb = *reinterpret_cast<const float4*>(a.rcoef + 1 * a.C + cq * 4);
-      const float4 rm = *reinterpret_cast<const float4*>(a.rcoef + 2 * a.C + cq * 4);
+      const float4 r = *reinterpret_cast<const float4*>(a.r + row * a.C + col);
       y.x += fmaf(r.x - rm.x, rs.x, rb.x), y.y += fmaf(r.y - rm.y, rs.y, rb.y);
       y.z += fmaf(r.z - rm.z, rs.z, rb.z), y.w += fmaf(r.w - rm.w, rs.w, rb.w);
     }
     y.x = lrelu(y.x, a.slope), y.y = lrelu(y.y, a.slope), y.z = lrelu(y.z, a.slope), y.w = lrelu(y.w, a.slope);
-    *reinterpret_cast<float4*>(a.out + row * a.C + cq * 4) = y;
+    *reinterpret_cast<float4*>(a.out + row * a.C + col) = y;
+    if (a.out_p) store_pair4(a.out_p, a.out_ps, row * a.C + col, y);
+    const int64_t ru = (int64_t)b * (2 * a.L + 2) + 1 + 2 * l;
     if (a.out_up) {
-      const int64_t ru = (int64_t)b * (2 * a.L + 2) + 1 + 2 * l;
-      *reinterpret_cast<float4*>(a.out_up + ru * a.C + cq * 4) = y;
-      *reinterpret_cast<float4*>(a.out_up + (ru + 1) * a.C + cq * 4) = y;
+      *reinterpret_cast<float4*>(a.out_up + ru * a.C + col) = y;
+      *reinterpret_cast<float4*>(a.out_up + (ru + 1) * a.C + col) = y;
+    }
+    if (a.up_p) {
+      store_pair4(a.up_p, a.up_ps, ru * a.C + col, y);
+      store_pair4(a.up_p, a.up_ps, (ru + 1) * a.C + col, y);
     }
   }
 }
 
 // ------------------------------------------------------------------------------------------------
 // BatchNorm backward (train mode), fused with the LeakyReLU backward and the residual split.
+//   g_pre = g * (out > 0 ? 1 : slope);  S1 = sum g_pre, S2 = sum g_pre * xhat (per channel)
+//   dc    = gamma * invstd * (g_pre - S1/n - xhat * S2/n)
+// Two launches: the reduce kernel leaves per-chunk partials and the maxima that bound |dc|; every CTA of the apply
+// kernel sums the partials of its 32-channel slab itself.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ float4 load_g(const BnBwd& a, int b, int l, int cq) {
+__device__ __forceinline__ float4 load_g(const BnBwd& a, int b, int l, int col) {
   if (a.g_up) {
     const int64_t ru = (int64_t)b * (2 * a.L + 2) + 1 + 2 * l;
-    const float4 g0 = *reinterpret_cast<const float4*>(a.g + ru * a.C + cq * 4);
-    const float4 g1 = *reinterpret_cast<const float4*>(a.g + (ru + 1) * a.C + cq * 4);
+    const float4 g0 = *reinterpret_cast<const float4*>(a.g + ru * a.C + col);
+    const float4 g1 = *reinterpret_cast<const float4*>(a.g + (ru + 1) * a.C + col);
     return make_float4(g0.x + g1.x, g0.y + g1.y, g0.z + g1.z, g0.w + g1.w);
   }
   const int64_t row = (int64_t)b * (a.L + 2) + 1 + l;
-  return *reinterpret_cast<const float4*>(a.g + row * a.C + cq * 4);
+  return *reinterpret_cast<const float4*>(a.g + row * a.C + col);
+}
+__device__ __forceinline__ float max4(float4 v) { return fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)); }
+__device__ __forceinline__ float block_max(float v, float* red) {  // 256 threads
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  v = red[0];
+#pragma unroll
+  for (int w = 1; w < 8; ++w) v = fmaxf(v, red[w]);
+  __syncthreads();
+  return v;
 }
 
-// part[chunk][C][3] = (S1, S2, S2s)
+// part[chunk][C][3] = (S1, S2, S2s);  slot = (max|g_pre|, max|xhat|, max|gamma*invstd|, 1/scale) as atomicMax targets
+// (non-negative floats order like their bit patterns; the slots are zeroed once per step by the engine)
 __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(BnBwd a, int rows_per_cta) {
   __shared__ float4 red[3][256];
+  __shared__ float mred[8];
   const int C4 = a.C >> 2;
   const int RL = 256 / C4;  // row lanes
   const int cq = threadIdx.x % C4, rl = threadIdx.x / C4;
   const int M = a.B * a.L;
   const int m_begin = blockIdx.x * rows_per_cta, m_end = min(M, m_begin + rows_per_cta);
-  float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1, s3 = s1;
+  float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1, s3 = s1, gm = s1, xm = s1, xsm = s1;
+  float km = 0.f, ksm = 0.f;
   if (rl < RL) {
     const float4 mu = *reinterpret_cast<const float4*>(a.coef + 2 * a.C + cq * 4);
     const float4 is = *reinterpret_cast<const float4*>(a.coef + 3 * a.C + cq * 4);
     float4 mus = mu, iss = is;
+    if (a.dc_slot) {
+      const float4 ga = *reinterpret_cast<const float4*>(a.gamma + cq * 4);
+      km = max4(fmax4abs(make_float4(0.f, 0.f, 0.f, 0.f), make_float4(ga.x * is.x, ga.y * is.y, ga.z * is.z, ga.w * is.w)));
+    }
     if (a.cs) {
       mus = *reinterpret_cast<const float4*>(a.coef_s + 2 * a.C + cq * 4);
       iss = *reinterpret_cast<const float4*>(a.coef_s + 3 * a.C + cq * 4);
+      if (a.dcs_slot) {
+        const float4 ga = *reinterpret_cast<const float4*>(a.gamma_s + cq * 4);
+        ksm = max4(fmax4abs(make_float4(0.f, 0.f, 0.f, 0.f),
+                            make_float4(ga.x * iss.x, ga.y * iss.y, ga.z * iss.z, ga.w * iss.w)));
+      }
     }
     for (int m = m_begin + rl; m < m_end; m += RL) {
       const int b = m / a.L, l = m - b * a.L;
       const int64_t row = (int64_t)b * (a.L + 2) + 1 + l;
-      float4 g = load_g(a, b, l, cq);
+      float4 g = load_g(a, b, l, cq * 4);
       const float4 o = *reinterpret_cast<const float4*>(a.out + row * a.C + cq * 4);
       g.x *= o.x > 0.f ? 1.f : a.slope, g.y *= o.y > 0.f ? 1.f : a.slope;
       g.z *= o.z > 0.f ? 1.f : a.slope, g.w *= o.w > 0.f ? 1.f : a.slope;
       const float4 x = *reinterpret_cast<const float4*>(a.c + row * a.C + cq * 4);
       s1.x += g.x, s1.y += g.y, s1.z += g.z, s1.w += g.w;
-      s2.x = fmaf(g.x, (x.x - mu.x) * is.x, s2.x), s2.y = fmaf(g.y, (x.y - mu.y) * is.y, s2.y);
-      s2.z = fmaf(g.z, (x.z - mu.z) * is.z, s2.z), s2.w = fmaf(g.w, (x.w - mu.w) * is.w, s2.w);
+      const float4 xh = make_float4((x.x - mu.x) * is.x, (x.y - mu.y) * is.y, (x.z - mu.z) * is.z, (x.w - mu.w) * is.w);
+      s2.x = fmaf(g.x, xh.x, s2.x), s2.y = fmaf(g.y, xh.y, s2.y);
+      s2.z = fmaf(g.z, xh.z, s2.z), s2.w = fmaf(g.w, xh.w, s2.w);
+      gm = fmax4abs(gm, g), xm = fmax4abs(xm, xh);
       if (a.cs) {
         const float4 xs = *reinterpret_cast<const float4*>(a.cs + row * a.C + cq * 4);
-        s3.x = fmaf(g.x, (xs.x - mus.x) * iss.x, s3.x), s3.y = fmaf(g.y, (xs.y - mus.y) * iss.y, s3.y);
-        s3.z = fmaf(g.z, (xs.z - mus.z) * iss.z, s3.z), s3.w = fmaf(g.w, (xs.w - mus.w) * iss.w, s3.w);
+        const float4 xsh = make_float4((xs.x - mus.x) * iss.x, (xs.y - mus.y) * iss.y, (xs.z - mus.z) * iss.z,
+                                       (xs.w - mus.w) * iss.w);
+        s3.x = fmaf(g.x, xsh.x, s3.x), s3.y = fmaf(g.y, xsh.y, s3.y);
+        s3.z = fmaf(g.z, xsh.z, s3.z), s3.w = fmaf(g.w, xsh.w, s3.w);
+        xsm = fmax4abs(xsm, xsh);
       }
     }
   }
@@ -253,31 +351,19 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(BnBwd a, int rows_pe
       dst[0 * 3 + k] = t.x, dst[1 * 3 + k] = t.y, dst[2 * 3 + k] = t.z, dst[3 * 3 + k] = t.w;
     }
   }
-}
-
-// coef[4]=k=gamma*invstd, [5]=m1=S1/n, [6]=m2=S2/n ; dgamma=S2, dbeta=S1
-__global__ void __launch_bounds__(256) bn_bwd_finalize_kernel(BnBwd a, int nchunks) {
-  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (c >= a.C) return;
-  double s1 = 0.0, s2 = 0.0, s3 = 0.0;
-  for (int t = lane; t < nchunks; t += 32) {
-    const float* p = a.part + ((int64_t)t * a.C + c) * 3;
-    s1 += (double)p[0], s2 += (double)p[1], s3 += (double)p[2];
-  }
-  s1 = warp_sum_d(s1), s2 = warp_sum_d(s2), s3 = warp_sum_d(s3);
-  if (lane == 0) {
-    const double n = (double)a.B * a.L;
-    a.coef[4 * a.C + c] = a.gamma[c] * a.coef[3 * a.C + c];
-    a.coef[5 * a.C + c] = (float)(s1 / n);
-    a.coef[6 * a.C + c] = (float)(s2 / n);
-    a.dgamma[c] = (float)s2;
-    a.dbeta[c] = (float)s1;
-    if (a.cs) {
-      a.coef_s[4 * a.C + c] = a.gamma_s[c] * a.coef_s[3 * a.C + c];
-      a.coef_s[5 * a.C + c] = (float)(s1 / n);
-      a.coef_s[6 * a.C + c] = (float)(s3 / n);
-      a.dgamma_s[c] = (float)s3;
-      a.dbeta_s[c] = (float)s1;
+  if (a.dc_slot) {  // uniform branch
+    const float g_all = block_max(max4(gm), mred), x_all = block_max(max4(xm), mred), k_all = block_max(km, mred);
+    float xs_all = 0.f, ks_all = 0.f;
+    if (a.dcs_slot) xs_all = block_max(max4(xsm), mred), ks_all = block_max(ksm, mred);
+    if (threadIdx.x == 0) {
+      unsigned int* s = reinterpret_cast<unsigned int*>(a.dc_slot);
+      atomicMax(s + 0, __float_as_uint(g_all)), atomicMax(s + 1, __float_as_uint(x_all));
+      atomicMax(s + 2, __float_as_uint(k_all));
+      if (a.dcs_slot) {
+        unsigned int* ss = reinterpret_cast<unsigned int*>(a.dcs_slot);
+        atomicMax(ss + 0, __float_as_uint(g_all)), atomicMax(ss + 1, __float_as_uint(xs_all));
+        atomicMax(ss + 2, __float_as_uint(ks_all));
+      }
     }
   }
 }
@@ -290,39 +376,85 @@ __device__ __forceinline__ float4 bn_dx(float4 g, float4 x, float4 mu, float4 is
   r.w = k.w * (g.w - m1.w - (x.w - mu.w) * is.w * m2.w);
   return r;
 }
+// |dc| = |k (g - m1 - xhat m2)| with |m1| <= max|g| and |m2| = |mean(g xhat)| <= max|g| mean|xhat| <= max|g|
+// (mean xhat^2 = 1), so |dc| <= max|k| max|g| (2 + max|xhat|): a safe, slightly loose bound (the pair format keeps
+// full precision over 18 bits of dynamic range below the scaled maximum)
+__device__ __forceinline__ float dc_scale(const float* slot) {
+  return pair_scale_from_bound(slot[2] * slot[0] * (2.f + slot[1]));
+}
 
-__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(BnBwd a) {
-  const int C4 = a.C >> 2;
-  const int64_t total = (int64_t)a.B * a.L * C4;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int cq = (int)(i % C4);
-    const int64_t m = i / C4;
-    const int b = (int)(m / a.L), l = (int)(m - (int64_t)b * a.L);
+// grid = (C / 32, row chunks); thread = (channel quad of the slab, row lane)
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(BnBwd a, int nchunks) {
+  __shared__ double s_sum[8][kSlab][3];
+  __shared__ float s_m1[kSlab], s_m2[kSlab], s_m3[kSlab];
+  const int c0 = blockIdx.x * kSlab;
+  {
+    const int c = threadIdx.x & (kSlab - 1), slice = threadIdx.x >> 5;
+    double s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    for (int t = slice; t < nchunks; t += 8) {
+      const float* p = a.part + ((int64_t)t * a.C + c0 + c) * 3;
+      s1 += (double)__ldcg(p), s2 += (double)__ldcg(p + 1), s3 += (double)__ldcg(p + 2);
+    }
+    s_sum[slice][c][0] = s1, s_sum[slice][c][1] = s2, s_sum[slice][c][2] = s3;
+    __syncthreads();
+    if (slice == 0) {
+      for (int k = 1; k < 8; ++k) s1 += s_sum[k][c][0], s2 += s_sum[k][c][1], s3 += s_sum[k][c][2];
+      const double n = (double)a.B * a.L;
+      s_m1[c] = (float)(s1 / n), s_m2[c] = (float)(s2 / n), s_m3[c] = (float)(s3 / n);
+      if (blockIdx.y == 0) {
+        a.dgamma[c0 + c] = (float)s2, a.dbeta[c0 + c] = (float)s1;
+        if (a.cs) a.dgamma_s[c0 + c] = (float)s3, a.dbeta_s[c0 + c] = (float)s1;
+      }
+    }
+    __syncthreads();
+  }
+  float sc = 1.f, scs = 1.f;
+  if (a.dc_p) sc = dc_scale(a.dc_slot);
+  if (a.dcs_p) scs = dc_scale(a.dcs_slot);
+  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
+    if (a.dc_p) a.dc_slot[3] = 1.f / sc;
+    if (a.dcs_p) a.dcs_slot[3] = 1.f / scs;
+  }
+  const int q = threadIdx.x & 7, rl = threadIdx.x >> 3;
+  const int col = c0 + q * 4;
+  const float4 m1 = *reinterpret_cast<const float4*>(s_m1 + q * 4), m2 = *reinterpret_cast<const float4*>(s_m2 + q * 4);
+  const float4 m3 = *reinterpret_cast<const float4*>(s_m3 + q * 4);
+  const float4 mu = *reinterpret_cast<const float4*>(a.coef + 2 * a.C + col);
+  const float4 is = *reinterpret_cast<const float4*>(a.coef + 3 * a.C + col);
+  const float4 ga = *reinterpret_cast<const float4*>(a.gamma + col);
+  const float4 k = make_float4(ga.x * is.x, ga.y * is.y, ga.z * is.z, ga.w * is.w);
+  float4 mus = mu, iss = is, ks = k;
+  if (a.cs) {
+    mus = *reinterpret_cast<const float4*>(a.coef_s + 2 * a.C + col);
+    iss = *reinterpret_cast<const float4*>(a.coef_s + 3 * a.C + col);
+    const float4 gs = *reinterpret_cast<const float4*>(a.gamma_s + col);
+    ks = make_float4(gs.x * iss.x, gs.y * iss.y, gs.z * iss.z, gs.w * iss.w);
+  }
+  const int M = a.B * a.L;
+  const int rows_per = (M + gridDim.y - 1) / gridDim.y;
+  const int m_end = min(M, (int)(blockIdx.y + 1) * rows_per);
+  for (int m = blockIdx.y * rows_per + rl; m < m_end; m += 32) {
+    const int b = m / a.L, l = m - b * a.L;
     const int64_t row = (int64_t)b * (a.L + 2) + 1 + l;
-    float4 g = load_g(a, b, l, cq);
-    const float4 o = *reinterpret_cast<const float4*>(a.out + row * a.C + cq * 4);
+    float4 g = load_g(a, b, l, col);
+    const float4 o = *reinterpret_cast<const float4*>(a.out + row * a.C + col);
     g.x *= o.x > 0.f ? 1.f : a.slope, g.y *= o.y > 0.f ? 1.f : a.slope;
     g.z *= o.z > 0.f ? 1.f : a.slope, g.w *= o.w > 0.f ? 1.f : a.slope;
-    if (a.gres) *reinterpret_cast<float4*>(a.gres + row * a.C + cq * 4) = g;
+    if (a.gres) *reinterpret_cast<float4*>(a.gres + row * a.C + col) = g;
     {
-      const float4 x = *reinterpret_cast<const float4*>(a.c + row * a.C + cq * 4);
-      const float4 mu = *reinterpret_cast<const float4*>(a.coef + 2 * a.C + cq * 4);
-      const float4 is = *reinterpret_cast<const float4*>(a.coef + 3 * a.C + cq * 4);
-      const float4 k = *reinterpret_cast<const float4*>(a.coef + 4 * a.C + cq * 4);
-      const float4 m1 = *reinterpret_cast<const float4*>(a.coef + 5 * a.C + cq * 4);
-      const float4 m2 = *reinterpret_cast<const float4*>(a.coef + 6 * a.C + cq * 4);
+      const float4 x = *reinterpret_cast<const float4*>(a.c + row * a.C + col);
       const int64_t drow = (int64_t)b * (a.Ld + 2) + 1 + (int64_t)a.dil * l;
-      *reinterpret_cast<float4*>(a.dc + drow * a.C + cq * 4) = bn_dx(g, x, mu, is, k, m1, m2);
+      const float4 d = bn_dx(g, x, mu, is, k, m1, m2);
+      if (a.dc) *reinterpret_cast<float4*>(a.dc + drow * a.C + col) = d;
+      if (a.dc_p) store_pair4(a.dc_p, a.dc_ps, drow * a.C + col, make_float4(d.x * sc, d.y * sc, d.z * sc, d.w * sc));
     }
     if (a.cs) {
-      const float4 x = *reinterpret_cast<const float4*>(a.cs + row * a.C + cq * 4);
-      const float4 mu = *reinterpret_cast<const float4*>(a.coef_s + 2 * a.C + cq * 4);
-      const float4 is = *reinterpret_cast<const float4*>(a.coef_s + 3 * a.C + cq * 4);
-      const float4 k = *reinterpret_cast<const float4*>(a.coef_s + 4 * a.C + cq * 4);
-      const float4 m1 = *reinterpret_cast<const float4*>(a.coef_s + 5 * a.C + cq * 4);
-      const float4 m2 = *reinterpret_cast<const float4*>(a.coef_s + 6 * a.C + cq * 4);
+      const float4 x = *reinterpret_cast<const float4*>(a.cs + row * a.C + col);
       const int64_t drow = (int64_t)b * (a.Ld_s + 2) + 1 + (int64_t)a.dil_s * l;
-      *reinterpret_cast<float4*>(a.dcs + drow * a.C + cq * 4) = bn_dx(g, x, mu, is, k, m1, m2);
+      const float4 d = bn_dx(g, x, mus, iss, ks, m1, m3);
+      if (a.dcs) *reinterpret_cast<float4*>(a.dcs + drow * a.C + col) = d;
+      if (a.dcs_p)
+        store_pair4(a.dcs_p, a.dcs_ps, drow * a.C + col, make_float4(d.x * scs, d.y * scs, d.z * scs, d.w * scs));
     }
   }
 }
@@ -422,7 +554,8 @@ __global__ void __launch_bounds__(256) linear_wgrad_rows_kernel(const float* __r
 __global__ void __launch_bounds__(256) dec_linear_fwd_kernel(const float* __restrict__ d, int F,
                                                              const float* __restrict__ W,
                                                              const float* __restrict__ bias, int C,
-                                                             float* __restrict__ t0) {
+                                                             float* __restrict__ t0, uint16_t* __restrict__ t0_p,
+                                                             int64_t t0_ps) {
   extern __shared__ float sd[];  // [F]
   const int b = blockIdx.x;
   for (int f = threadIdx.x; f < F; f += blockDim.x) sd[f] = d[(int64_t)b * F + f];
@@ -434,6 +567,15 @@ __global__ void __launch_bounds__(256) dec_linear_fwd_kernel(const float* __rest
     s += bias[c];
 #pragma unroll
     for (int l = 0; l < 4; ++l) t0[((int64_t)b * 6 + 1 + l) * C + c] = s;
+    if (t0_p) {
+      uint16_t h, lo;
+      pair_split<kPairF16>(s, h, lo);
+#pragma unroll
+      for (int l = 0; l < 4; ++l) {
+        t0_p[((int64_t)b * 6 + 1 + l) * C + c] = h;
+        t0_p[t0_ps + ((int64_t)b * 6 + 1 + l) * C + c] = lo;
+      }
+    }
   }
 }
 
@@ -733,15 +875,19 @@ int launch_stem_wgrad(const float* x, const float* dc0, float* part, int B, int 
 void launch_reduce_partials(const float* part, int nparts, int n, float* out, int accumulate, cudaStream_t s) {
   reduce_partials_kernel<<<(n + 127) / 128, 128, 0, s>>>(part, nparts, n, out, accumulate);
 }
-void launch_bn_finalize_train(const BnFinalize& f, cudaStream_t s) {
-  bn_finalize_train_kernel<<<(f.C * 32 + 255) / 256, 256, 0, s>>>(f);
-}
 void launch_bn_eval_coefs(const BnEvalEntry* table_dev, int n, const float* params, const float* run_mean,
                           const float* run_var, float* ws, cudaStream_t s) {
   bn_eval_coefs_kernel<<<n, 128, 0, s>>>(table_dev, params, run_mean, run_var, ws);
 }
-void launch_bn_apply(const BnApply& a, cudaStream_t s) {
-  int grid = ew_grid((int64_t)a.B * a.L * (a.C / 4));
+// row chunks so that slabs x chunks ~ 2 CTAs per SM, each with at least 32 rows
+static inline int slab_row_chunks(int M, int C, int sm_count) {
+  int chunks = (2 * sm_count) / (C / kSlab);
+  const int max_chunks = (M + 31) / 32;
+  if (chunks > max_chunks) chunks = max_chunks;
+  return chunks < 1 ? 1 : chunks;
+}
+void launch_bn_apply(const BnApply& a, int sm_count, cudaStream_t s) {
+  dim3 grid(a.C / kSlab, slab_row_chunks(a.B * a.L, a.C, sm_count));
   if (!a.r)
     bn_apply_kernel<0><<<grid, 256, 0, s>>>(a);
   else if (!a.rcoef)
@@ -751,13 +897,12 @@ void launch_bn_apply(const BnApply& a, cudaStream_t s) {
 }
 void launch_bn_bwd(const BnBwd& a, int sm_count, cudaStream_t s) {
   const int M = a.B * a.L;
-  (void)sm_count;
   int rows = (M + kBnBwdMaxChunks - 1) / kBnBwdMaxChunks;
   if (rows < 16) rows = 16;
   const int nchunks = (M + rows - 1) / rows;
   bn_bwd_reduce_kernel<<<nchunks, 256, 0, s>>>(a, rows);
-  bn_bwd_finalize_kernel<<<(a.C * 32 + 255) / 256, 256, 0, s>>>(a, nchunks);
-  bn_bwd_apply_kernel<<<ew_grid((int64_t)M * (a.C / 4)), 256, 0, s>>>(a);
+  dim3 grid(a.C / kSlab, slab_row_chunks(M, a.C, sm_count));
+  bn_bwd_apply_kernel<<<grid, 256, 0, s>>>(a, nchunks);
 }
 void launch_pairsum_acc(const float* src, float* dst, int B, int L, int C, cudaStream_t s) {
   pairsum_acc_kernel<<<ew_grid((int64_t)B * L * (C / 4)), 256, 0, s>>>(src, dst, B, L, C);
@@ -772,8 +917,8 @@ void launch_pool_linear_bwd(const float* dh, const float* pooled, const float* W
   linear_wgrad_rows_kernel<<<(F * (C + 1) + 63) / 64, 256, 0, s>>>(dh, F, pooled, C, B, C, F, dW, db);
 }
 void launch_dec_linear_fwd(const float* d, int B, int F, const float* W, const float* bias, int C, float* t0,
-                           float* /*t0_up*/, cudaStream_t s) {
-  dec_linear_fwd_kernel<<<B, 256, F * sizeof(float), s>>>(d, F, W, bias, C, t0);
+                           uint16_t* t0_p, int64_t t0_ps, cudaStream_t s) {
+  dec_linear_fwd_kernel<<<B, 256, F * sizeof(float), s>>>(d, F, W, bias, C, t0, t0_p, t0_ps);
 }
 void launch_dec_linear_bwd(const float* g_t0, const float* d, const float* W, int B, int F, int C, float* gx0,
                            float* dd, float* dW, float* db, cudaStream_t s) {

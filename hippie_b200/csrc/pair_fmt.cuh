@@ -1,0 +1,30 @@
+// 16-bit pair planes: x ~= hi + lo with hi = round16(x), lo = round16(x - hi).
+//   kPairF16  : fp16 pair, ~22 mantissa bits for |x| >= 2^-3 (absolute error <= 2^-25 below); saturates at 65504
+//   kPairBF16 : bf16 pair, 16 mantissa bits, fp32 exponent range (gradients)
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+
+namespace hp {
+
+enum { kPairF16 = 0, kPairBF16 = 1 };
+constexpr float kWeightPairScale = 256.f;  // weights are stored as fp16 pairs of w * 2^8 (tools/pair_precision.py)
+
+template <int FMT>
+__device__ __forceinline__ void pair_split(float x, uint16_t& h, uint16_t& l) {
+  if (FMT == kPairF16) {
+    uint16_t hh, ll;
+    float back;
+    asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(hh) : "f"(x));
+    asm("cvt.f32.f16 %0, %1;" : "=f"(back) : "h"(hh));
+    asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(ll) : "f"(x - back));
+    h = hh, l = ll;
+  } else {
+    const __nv_bfloat16 hb = __float2bfloat16_rn(x);
+    const __nv_bfloat16 lb = __float2bfloat16_rn(x - __bfloat162float(hb));
+    h = __bfloat16_as_ushort(hb), l = __bfloat16_as_ushort(lb);
+  }
+}
+
+}  // namespace hp

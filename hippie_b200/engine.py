@@ -85,7 +85,8 @@ class Engine:
         tl, tc, tp = C.c_int32(), C.c_int32(), C.c_int32()
         for i in range(self._L.hippie_num_tensors(self._h)):
             self._L.hippie_tensor_info(self._h, i, name, 256, C.byref(off), C.byref(tl), C.byref(tc), C.byref(tp))
-            self.tensors.append(TensorInfo(name.value.decode(), off.value, tl.value, tc.value, tp.value))
+            if off.value >= 0:  # tensors that only exist as fp16 pair planes (GEMM operands) have no fp32 view
+                self.tensors.append(TensorInfo(name.value.decode(), off.value, tl.value, tc.value, tp.value))
         self.device: Optional[torch.device] = None
         self.flat_params = self.flat_grads = self.exp_avg = self.exp_avg_sq = None
         self.bn_mean = self.bn_var = self.bn_count = self.workspace = None
@@ -214,7 +215,7 @@ class Engine:
         return scalars
 
     def conv_path_in_use(self) -> int:
-        """2 = tcgen05 3xTF32 implicit GEMM, 1 = FP32 CUDA-core GEMM (valid after allocate())."""
+        """2 = tcgen05 implicit GEMMs over fp16 pair planes, 1 = FP32 CUDA-core GEMMs (valid after allocate())."""
         return int(self._L.hippie_conv_path_in_use(self._h))
 
     def last_launch_count(self) -> int:

@@ -66,7 +66,7 @@ const char* hippie_last_error(hippie_handle h);
 
 /* ---- layout enumeration, in state_dict() order (hippie/model.py:360-395 construction order) ----
  * Parameters: `offset`/`numel` in floats inside the flat params / grads / exp_avg / exp_avg_sq
- * buffers (each hippie_param_floats() long; offsets are 16-byte aligned, gaps stay zero).
+ * buffers (each hippie_param_floats() long; offsets are 32-byte aligned, gaps stay zero).
  * `shape` is the torch shape (ndim <= 3).  */
 int hippie_num_params(hippie_handle h);
 int64_t hippie_param_floats(hippie_handle h);
