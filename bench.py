@@ -104,8 +104,8 @@ def cpu_reference_run(steps, warmup, budget_s=150.0):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--units", type=int, default=1_000_000, help="synthetic units staged per rank")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -226,7 +226,12 @@ def main():
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel class (implicit-GEMM convolutions), measured live with CUDA events
+    # ---- roofline of the dominant kernel, measured live: the engine brackets every implicit-GEMM launch with CUDA
+    # events on the stream it is launched on (hippie_profile).  conv_pair_kernel serves conv forward + dgrad (152 of
+    # the 463 launches, ~45 % of the summed kernel time, profiles/); it is tensor-bound: achieved = algorithmic
+    # FLOP (2*M*N*K over real rows) / event time, peak = the measured dense bf16 tensor throughput (sustained figure:
+    # the kernel runs inside a long step).  The pair scheme issues THREE kind::f16 MMAs per algorithmic product, so
+    # 1/3 is the ceiling of `frac`.
     roof = None
     try:
         from hippie_b200.profile import conv_roofline
@@ -238,16 +243,33 @@ def main():
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
+    peak_tf = peaks.get("bf16_tflops_sustained") or 1400.0
+    peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks.get("bf16_tflops_sustained") else \
+        "1.4 PFLOP/s sustained (of fallback, B200_PROFILING.md)"
     step_tflops = value / world * F_TRAIN / 1e12
-    roofline = {"bound": "fma", "achieved": step_tflops, "peak": FMA_PEAK_TFLOPS, "unit": "TFLOP/s",
-                "frac": step_tflops / FMA_PEAK_TFLOPS, "traffic": None,
-                "note": "whole step (algorithmic 689.76 MFLOP/sample) vs FP32-FMA peak 148 SM x 128 lanes x 2 x 1.965 GHz; "
-                        "the convolutions run on the FP32 CUDA-core implicit-GEMM (fp32 parity); see conv kernels below",
+    roofline = {"bound": "tensor", "achieved": None, "peak": peak_tf, "unit": "TFLOP/s", "frac": None, "traffic": None,
+                "kernel": "conv_pair_kernel<64,2> (conv forward + dgrad implicit GEMM, tcgen05 kind::f16 on fp16 pair planes)",
+                "peak_source": peak_src,
+                "note": "achieved = algorithmic FLOP / CUDA-event time of the kernel's launches in one step; the kernel issues 3 "
+                        "MMAs per algorithmic product (hi*hi + hi*lo + lo*hi), so frac <= 1/3 by construction",
                 "kernels": roof,
+                "whole_step": {"algorithmic_tflops": step_tflops, "fp32_fma_peak_tflops": FMA_PEAK_TFLOPS,
+                               "frac_of_fp32_fma_roofline": step_tflops / FMA_PEAK_TFLOPS,
+                               "note": "north_star's target (>= 50 % of the FMA roofline at bs512): algorithmic "
+                                       "689.76 MFLOP/sample vs 148 SM x 128 lanes x 2 x 1.965 GHz"},
                 "measured_peaks": {k: peaks.get(k) for k in ("hbm_gbs", "bf16_tflops", "bf16_tflops_sustained")}}
+    if isinstance(roof, dict) and "conv_fwd" in roof and "conv_dgrad" in roof:
+        ms = roof["conv_fwd"]["total_ms"] + roof["conv_dgrad"]["total_ms"]
+        fl = roof["conv_fwd"]["gflop"] + roof["conv_dgrad"]["gflop"]
+        n = roof["conv_fwd"]["launches"] + roof["conv_dgrad"]["launches"]
+        roofline["achieved"] = fl / ms  # GFLOP / ms = TFLOP/s
+        roofline["frac"] = roofline["achieved"] / peak_tf
+        roofline["avg_launch_us"] = 1e3 * ms / n
+        roofline["launches_per_step"] = n
+        roofline["algorithmic_gflop_per_launch"] = fl / n
     try:
         tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        roofline["traffic"] = tr.get("conv_gemm_bytes_per_launch")
+        roofline["traffic"] = tr.get("conv_pair_bytes_per_launch")
         roofline["traffic_source"] = tr.get("source")
     except Exception:
         pass
@@ -260,6 +282,8 @@ def main():
     line = {"metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+            "dtype_note": "fp32 tensors and fp32 accumulation; the GEMM operands are fp16 hi+lo pair planes (x = hi + lo, ~22 "
+                          "mantissa bits, three tensor-core MMAs per product), parity-tested against the fp32 reference",
             "clocks": sampler.summary(),
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms / args.steps},

@@ -12,6 +12,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -57,7 +58,7 @@ struct Conv {
   int id = -1;
 };
 struct ConvMaps {  // TMA tensor maps of the tcgen05 path, built at first use after hippie_bind
-  TcMap a_fwd, w64, w128, a_dg, w_mn, wg_dy, wg_x;
+  TcMap a_fwd, w_k, a_dg, w_mn, wg_dy, wg_x;
   bool fwd_ready = false, dg_ready = false;
   int wg_B = -1;  // the wgrad maps bound the reduction rows, so they depend on the batch size
 };
@@ -134,6 +135,39 @@ struct hippie_engine {
   int launches = 0;
   int n_convs = 0;
   bool failed = false;  // a tensor-map encode failed while launching (reported by the entry point)
+  // ---- CUDA graphs: one instantiated graph per call signature, replayed from staged inputs ----------------
+  struct CallArgs {
+    int mode;  // 0 train_fwd_bwd, 1 train_forward, 2 eval_forward, 3 embed
+    const float *x1, *x2;
+    const int64_t *src, *cls;
+    const float* eps;
+    int B;
+    float beta, w1, w2;
+    int zscore;
+    float *scalars, *enc, *mu, *lv, *d1, *d2;
+  };
+  struct GraphKey {
+    int mode, B, flags, zscore;
+    float beta, w1, w2;
+    bool operator<(const GraphKey& o) const {
+      return std::memcmp(this, &o, sizeof(GraphKey)) < 0;
+    }
+  };
+  struct GraphEntry {
+    cudaGraphExec_t exec = nullptr;
+    int launches = 0;
+    int seen = 0;  // 0 = never called (first call runs eagerly: lazy initialisation), -1 = capture failed, stay eager
+  };
+  std::map<GraphKey, GraphEntry> graphs;
+  bool use_graphs = true;
+  cudaStream_t cap = nullptr;  // capture stream (the caller's stream may be the legacy default stream)
+  int64_t st_x1 = 0, st_x2 = 0, st_src = 0, st_cls = 0, st_eps = 0, st_scal = 0, st_enc = 0, st_mu = 0, st_lv = 0,
+          st_d1 = 0, st_d2 = 0;
+  void clear_graphs() {
+    for (auto& kv : graphs)
+      if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+    graphs.clear();
+  }
   std::vector<ConvMaps> cmaps;
   bool use_tc = false;  // tcgen05 implicit GEMMs over fp16 pair planes (conv_path 0); false = FP32 CUDA-core GEMMs
   std::string tc_note;
@@ -488,6 +522,12 @@ struct hippie_engine {
     bpart_floats = (int64_t)(kBnBwdMaxChunks + 1) * 512 * 6;
     for (int i = 0; i < 2; ++i) part_off[i] = take(part_floats), bpart_off[i] = take(bpart_floats);
     adam_part = take(1024);
+    {
+      const int64_t mb = cfg.max_batch;
+      st_x1 = take(mb * cfg.len_wave), st_x2 = take(mb * std::max(cfg.len_isi, 1)), st_src = take(mb * 2);
+      st_cls = take(mb * 2), st_eps = take(mb * z), st_scal = take(8), st_enc = take(mb * z), st_mu = take(mb * z);
+      st_lv = take(mb * z), st_d1 = take(mb * cfg.len_wave), st_d2 = take(mb * std::max(cfg.len_isi, 1));
+    }
     if (pair_mode()) {
       wp_off = take(param_floats);  // 2 planes x 2 bytes per parameter
     }
@@ -525,14 +565,13 @@ struct hippie_engine {
       if (!m.fwd_ready) {
         bool ok = pair_make_act_map(&m.a_fwd, PL(in), acts[in].pstride, kPairF16, g.in_C, g.K, g.Lout, g.in_rows,
                                     g.in_stride, g.in_off, cfg.max_batch);
-        ok = ok && pair_make_w_map(&m.w64, wpl, param_floats, kPairF16, g.N, g.K, 64);
-        if (g.N % 128 == 0) ok = ok && pair_make_w_map(&m.w128, wpl, param_floats, kPairF16, g.N, g.K, 128);
+        ok = ok && pair_make_w_map(&m.w_k, wpl, param_floats, kPairF16, g.N, g.K, pair_pick_bn(B, g.N, g.Lout, sm_count));
         if (!ok) return (void)(err = "cuTensorMapEncodeTiled failed (conv forward)", failed = true);
         m.fwd_ready = true;
       }
       const int bn_tile = pair_pick_bn(B, g.N, g.Lout, sm_count);
       PairOpts o{1.f / kWeightPairScale, kPairF16, kPairF16, 0, cv.k};
-      tile = launch_conv_pair(g, m.a_fwd, bn_tile == 128 ? m.w128 : m.w64, bn_tile, B, o, br.st);
+      tile = launch_conv_pair(g, m.a_fwd, m.w_k, bn_tile, B, o, br.st);
     } else {
       tile = launch_conv_gemm_simt(g, br.st);
     }
@@ -564,7 +603,9 @@ struct hippie_engine {
       if (acts[out].poff >= 0) a.out_p = PL(out), a.out_ps = acts[out].pstride;
       if (out_up >= 0 && acts[out_up].poff >= 0) a.up_p = PL(out_up), a.up_ps = acts[out_up].pstride;
     }
+    cudaEvent_t pe = prof_begin(br);
     launch_bn_apply(a, sm_count, br.st);
+    prof_end(pe, 3, 0.0, br);
     ++launches;
   }
   // dgrad as a stride-1 convolution of the (dilated) output gradient with the transposed weights
@@ -594,16 +635,19 @@ struct hippie_engine {
     prof_end(pe, 1, 2.0 * g.M * g.N * g.K, br);
     ++launches;
   }
+  // the weight-gradient stream of the branch waits for everything issued on the branch stream so far
+  void side_wait(Branch& br) {
+    if (!br.wst || br.wst == br.st) return;
+    cudaEvent_t e = next_event();
+    cudaEventRecord(e, br.st);
+    cudaStreamWaitEvent(br.wst, e, 0);
+  }
   void wgrad(const Conv& cv, int dy, int x, int B, Branch& br) {
     WgradGemm g{};
     g.dY = A(dy), g.X = A(x), g.dW = Gp(cv.w);
     g.M = cv.cout, g.N = cv.k * cv.cin, g.R = B * (acts[dy].L + 2), g.Cin = cv.cin, g.roff = cv.k == 3 ? -1 : 0;
     cudaStream_t wst = br.wst ? br.wst : br.st;
-    if (wst != br.st) {  // dY is final once the stream reaches this point; everything the wgrad reads stays untouched
-      cudaEvent_t e = next_event();
-      cudaEventRecord(e, br.st);
-      cudaStreamWaitEvent(wst, e, 0);
-    }
+    side_wait(br);  // dY is final once the stream reaches this point; everything the wgrad reads stays untouched
     cudaEvent_t pe = prof_begin(br);
     if (use_tc) {
       ConvMaps& m = cmaps[cv.id];
@@ -615,7 +659,7 @@ struct hippie_engine {
       }
       PairOpts o{1.f, kPairF16, kPairF16, 1, cv.k};
       o.dyn_scale = slot(dy) + 3;
-      launch_wgrad_pair(g, m.wg_dy, m.wg_x, (g.N % 128 == 0) ? 128 : 64, sm_count, o, wst);
+      launch_wgrad_pair(g, m.wg_dy, m.wg_x, pair_pick_bn(B, g.N, 1, sm_count), sm_count, o, wst);
     } else {
       launch_wgrad_simt(g, sm_count, wst);
     }
@@ -636,13 +680,17 @@ struct hippie_engine {
     if (use_tc && acts[dc].poff >= 0) a.dc_p = PL(dc), a.dc_ps = acts[dc].pstride, a.dc_slot = slot(dc);
     if (use_tc && cs >= 0 && acts[dcs].poff >= 0) a.dcs_p = PL(dcs), a.dcs_ps = acts[dcs].pstride, a.dcs_slot = slot(dcs);
     a.gres = gres >= 0 ? A(gres) : nullptr;
+    cudaEvent_t pe = prof_begin(br);
     launch_bn_bwd(a, sm_count, br.st);
+    prof_end(pe, 4, 0.0, br);
     launches += kBnBwdLaunches;
   }
 
   void encoder_fwd(Encoder& E, const float* x, int B, bool train, Branch& br) {
+    cudaEvent_t pe7 = prof_begin(br);
     launch_stem_fwd(x, Pp(E.stem_w), A(E.c0), train ? ws + bns[E.bn0].part_off : nullptr, B, E.Lin, E.L0, br.st);
     ++launches;
+    prof_end(pe7, 7, 0.0, br);
     if (train) bns[E.bn0].ntiles = (B * E.L0 + 127) / 128, bns[E.bn0].tile_rows = 128, bns[E.bn0].M = B * E.L0;
     apply(E.c0, E.bn0, -1, -1, E.a0, -1, B, train, br);
     for (int i = 0; i < 8; ++i) {
@@ -658,15 +706,21 @@ struct hippie_engine {
       }
     }
     const int last = E.blk[7].out;
+    cudaEvent_t pe8 = prof_begin(br);
     launch_pool_linear_fwd(A(last), B, acts[last].L, 512, Pp(E.lin_w), Pp(E.lin_b), 2 * cfg.z_dim, ws + E.pooled,
                            ws + E.h, br.st);
+    prof_end(pe8, 8, 0.0, br);
     ++launches;
   }
   void encoder_bwd(Encoder& E, const float* x, int B, Branch& br) {
     const int last = E.blk[7].out;
-    launch_pool_linear_bwd(ws + E.dh, ws + E.pooled, Pp(E.lin_w), B, acts[last].L, 512, 2 * cfg.z_dim, A(gact.at(last)),
-                           Gp(E.lin_w), Gp(E.lin_b), br.st);
-    launches += kPoolLinearBwdLaunches;
+    cudaEvent_t pe9 = prof_begin(br);
+    side_wait(br);  // dh and pooled are final: the Linear's weight gradient runs beside the backbone backward
+    launch_linear_wgrad(ws + E.dh, 2 * cfg.z_dim, ws + E.pooled, 512, B, 512, 2 * cfg.z_dim, Gp(E.lin_w), Gp(E.lin_b),
+                        br.wst ? br.wst : br.st);
+    launch_pool_linear_bwd_x(ws + E.dh, Pp(E.lin_w), B, acts[last].L, 512, 2 * cfg.z_dim, A(gact.at(last)), br.st);
+    prof_end(pe9, 9, 0.0, br);
+    launches += 2;
     for (int i = 7; i >= 0; --i) {
       EncBlock& b = E.blk[i];
       const int gx = gact.at(b.x), gout = gact.at(b.out);
@@ -682,14 +736,18 @@ struct hippie_engine {
       wgrad(b.c1, b.dc1, b.x, B, br);
     }
     bn_bwd(gact.at(E.a0), false, E.a0, E.c0, E.bn0, -1, -1, E.dc0, 1, -1, 1, -1, B, br);
+    cudaEvent_t pe10 = prof_begin(br);
     const int np = launch_stem_wgrad(x, A(E.dc0), br.part, B, E.Lin, E.L0, br.st);
     launch_reduce_partials(br.part, np, 192, Gp(E.stem_w), 0, br.st);
+    prof_end(pe10, 10, 0.0, br);
     launches += 2;
   }
 
   void decoder_fwd(Decoder& D, int B, bool train, Branch& br) {
+    cudaEvent_t pe11 = prof_begin(br);
     launch_dec_linear_fwd(ws + D.d, B, 2 * cfg.z_dim, Pp(D.lin_w), Pp(D.lin_b), 512, A(D.t0),
                           use_tc ? PL(D.t0) : nullptr, acts[D.t0].pstride, br.st);
+    prof_end(pe11, 11, 0.0, br);
     ++launches;
     for (int i = 0; i < 8; ++i) {
       DecBlock& b = D.blk[i];
@@ -717,12 +775,14 @@ struct hippie_engine {
   }
   void decoder_tail(Decoder& D, int m, const float* target, float* dec_out, int B, bool train, float loss_w, Branch& br) {
     DecTail t = tail_args(D, target, dec_out, B, train, loss_w);
+    cudaEvent_t pe12 = prof_begin(br);
     const int ncta = launch_dec_tail(t, br.st);
     float* sse = ws + scal_off + m;
     if (train)
       launch_dec_tail_reduce(t, ncta, Gp(D.wc), Gp(D.bc), Gp(D.lo_w), Gp(D.lo_b), sse, br.st);
     else
       launch_dec_tail_reduce(t, ncta, nullptr, nullptr, nullptr, nullptr, sse, br.st);
+    prof_end(pe12, 12, 0.0, br);
     launches += 2;
   }
   void decoder_bwd(Decoder& D, int B, Branch& br) {
@@ -738,7 +798,9 @@ struct hippie_engine {
         bn_bwd(b.g_a2_up, true, b.a2, b.c2o, b.bn2, -1, -1, b.dc2, 1, -1, 1, -1, B, br);
         dgrad(b.c2, b.dc2, gx, false, B, br);
         wgrad(b.c2, b.dc2, b.x, B, br);
+        cudaEvent_t pe14 = prof_begin(br);
         launch_pairsum_acc(A(b.g_x_up), A(gx), B, acts[b.x].L, acts[b.x].C, br.st);
+        prof_end(pe14, 14, 0.0, br);
         ++launches;
       } else {
         bn_bwd(gout, false, b.out, b.c1o, b.bn1, -1, -1, b.dc1, 1, -1, 1, gx, B, br);
@@ -749,9 +811,14 @@ struct hippie_engine {
         wgrad(b.c2, b.dc2, b.x, B, br);
       }
     }
-    launch_dec_linear_bwd(A(gact.at(D.t0)), ws + D.d, Pp(D.lin_w), B, 2 * cfg.z_dim, 512, ws + D.gx0, ws + D.dd,
-                          Gp(D.lin_w), Gp(D.lin_b), br.st);
-    launches += kDecLinearBwdLaunches;
+    cudaEvent_t pe13 = prof_begin(br);
+    launch_dec_linear_bwd_x(A(gact.at(D.t0)), Pp(D.lin_w), B, 2 * cfg.z_dim, 512, ws + D.gx0, ws + D.dd, br.st);
+    side_wait(br);
+    // dW[c][f] = sum_b gx0[b][c] * d[b][f];  db[c] = sum_b gx0[b][c]
+    launch_linear_wgrad(ws + D.gx0, 512, ws + D.d, 2 * cfg.z_dim, B, 2 * cfg.z_dim, 512, Gp(D.lin_w), Gp(D.lin_b),
+                        br.wst ? br.wst : br.st);
+    prof_end(pe13, 13, 0.0, br);
+    launches += 2;
   }
 
   HeadArgs head_args(int B, const int64_t* src, const int64_t* cls, const float* eps, bool train, bool decode,
@@ -833,7 +900,9 @@ struct hippie_engine {
       join(main);
     }
     HeadArgs ha = head_args(B, src, cls, eps, train, true, out_enc, out_mu, out_logvar, beta, -1);
+    cudaEvent_t pe5 = prof_begin(b0);
     const int n_kl = launch_head_fwd(ha, main);
+    prof_end(pe5, 5, 0.0, b0);
     ++launches;
     if (two) fork(main);
     for (int m = 0; m < n_dec; ++m) {
@@ -849,7 +918,9 @@ struct hippie_engine {
       ++launches;
     }
     if (backward) {
+      cudaEvent_t pe6 = prof_begin(b0);
       launch_head_bwd(ha, main);
+      prof_end(pe6, 6, 0.0, b0);
       ++launches;
       if (two) fork(main);
       encoder_bwd(enc[0], xin[0], B, b0);
@@ -866,6 +937,100 @@ struct hippie_engine {
     }
     if (failed) return fail(-9, err);
     return check(train ? "train_fwd_bwd" : "eval_forward");
+  }
+
+  // encoders + latent head only, eval-mode BatchNorm (get_embeddings_multimodal, scripts/...:22-34)
+  int run_embed(const float* x1, const float* x2, const int64_t* src, const int64_t* cls, int B, int zscore_ddof,
+                float* out_enc, float* out_mu, float* out_logvar, cudaStream_t main) {
+    launches = 0;
+    Branch b0{main, ws + part_off[0], ws + bpart_off[0]}, b1{side, ws + part_off[1], ws + bpart_off[1]};
+    launch_bn_eval_coefs(reinterpret_cast<const BnEvalEntry*>(ws + bn_table_off), (int)bn_table.size(), P, bn_mean, bn_var,
+                         ws, main);
+    ++launches;
+    refresh_weights(false, main);
+    const bool two = n_enc == 2;
+    if (two) fork(main);
+    encoder_fwd(enc[0], x1, B, false, b0);
+    if (two) {
+      encoder_fwd(enc[1], x2, B, false, b1);
+      join(main);
+    }
+    HeadArgs ha = head_args(B, src, cls, nullptr, false, false, out_enc, out_mu, out_logvar, 0.f, zscore_ddof);
+    ha.kl_sum = nullptr;
+    launch_head_fwd(ha, main);
+    ++launches;
+    if (failed) return fail(-9, err);
+    return check("hippie_embed");
+  }
+
+  int exec(const CallArgs& a, cudaStream_t main) {
+    if (a.mode == 3) return run_embed(a.x1, a.x2, a.src, a.cls, a.B, a.zscore, a.enc, a.mu, a.lv, main);
+    return run(a.mode != 2, a.mode == 0, a.x1, a.x2, a.src, a.cls, a.eps, a.B, a.beta, a.w1, a.w2, a.scalars, a.enc, a.mu,
+               a.lv, a.d1, a.d2, main);
+  }
+
+  // Graph-aware dispatch.  Inputs are copied into fixed staging buffers (one launch), the captured launch sequence is
+  // replayed, requested outputs are copied out (one launch).  The first call of a signature runs eagerly so that every
+  // lazy initialisation (tensor maps, kernel attributes) happens outside a capture.
+  int call(const CallArgs& a, cudaStream_t main) {
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (use_graphs && !profiling) cudaStreamIsCapturing(main, &cs);
+    if (!use_graphs || profiling || cs != cudaStreamCaptureStatusNone) return exec(a, main);
+    GraphKey key;
+    std::memset(&key, 0, sizeof(key));
+    key.mode = a.mode, key.B = a.B, key.zscore = a.zscore, key.beta = a.beta, key.w1 = a.w1, key.w2 = a.w2;
+    key.flags = (a.cls ? 1 : 0) | (a.eps ? 2 : 0) | (a.scalars ? 4 : 0) | (a.enc ? 8 : 0) | (a.mu ? 16 : 0) |
+                (a.lv ? 32 : 0) | (a.d1 ? 64 : 0) | (a.d2 ? 128 : 0);
+    GraphEntry& e = graphs[key];
+    if (e.seen <= 0) {
+      if (e.seen == 0) e.seen = 1;
+      return exec(a, main);
+    }
+    const int z = cfg.z_dim;
+    IoCopy in{};
+    auto add = [](IoCopy& c, const void* src, void* dst, int64_t words) {
+      if (src && dst && words > 0) c.seg[c.n++] = IoSeg{src, dst, words};
+    };
+    add(in, a.x1, ws + st_x1, (int64_t)a.B * cfg.len_wave);
+    if (cfg.multimodal) add(in, a.x2, ws + st_x2, (int64_t)a.B * cfg.len_isi);
+    add(in, a.src, ws + st_src, (int64_t)a.B * 2);
+    add(in, a.cls, ws + st_cls, (int64_t)a.B * 2);
+    add(in, a.eps, ws + st_eps, (int64_t)a.B * z);
+    launch_io_copy(in, main);
+    if (!e.exec) {
+      CallArgs s = a;
+      s.x1 = ws + st_x1, s.x2 = cfg.multimodal ? ws + st_x2 : nullptr;
+      s.src = reinterpret_cast<const int64_t*>(ws + st_src);
+      s.cls = a.cls ? reinterpret_cast<const int64_t*>(ws + st_cls) : nullptr;
+      s.eps = a.eps ? ws + st_eps : nullptr;
+      s.scalars = a.scalars ? ws + st_scal : nullptr;
+      s.enc = a.enc ? ws + st_enc : nullptr, s.mu = a.mu ? ws + st_mu : nullptr, s.lv = a.lv ? ws + st_lv : nullptr;
+      s.d1 = a.d1 ? ws + st_d1 : nullptr, s.d2 = a.d2 ? ws + st_d2 : nullptr;
+      cudaGraph_t g = nullptr;
+      cudaError_t ce = cudaStreamBeginCapture(cap, cudaStreamCaptureModeRelaxed);
+      int rc = ce == cudaSuccess ? exec(s, cap) : (int)ce;
+      if (ce == cudaSuccess) ce = cudaStreamEndCapture(cap, &g);
+      if (rc == 0 && ce == cudaSuccess && g) ce = cudaGraphInstantiate(&e.exec, g, 0);
+      if (g) cudaGraphDestroy(g);
+      if (rc != 0 || ce != cudaSuccess || !e.exec) {  // stay eager for this signature
+        cudaGetLastError();
+        e.exec = nullptr, e.seen = -1, failed = false;
+        return exec(a, main);
+      }
+      e.launches = launches;
+    }
+    cudaGraphLaunch(e.exec, main);
+    IoCopy out{};
+    add(out, ws + st_scal, a.scalars, a.mode == 3 ? 0 : 4);
+    add(out, ws + st_enc, a.enc, (int64_t)a.B * z), add(out, ws + st_mu, a.mu, (int64_t)a.B * z);
+    add(out, ws + st_lv, a.lv, (int64_t)a.B * z);
+    if (a.mode != 3) {
+      add(out, ws + st_d1, a.d1, (int64_t)a.B * cfg.len_wave);
+      if (cfg.multimodal) add(out, ws + st_d2, a.d2, (int64_t)a.B * cfg.len_isi);
+    }
+    if (out.n) launch_io_copy(out, main);
+    launches = e.launches + 1 + (out.n ? 1 : 0);
+    return check("graph launch");
   }
 };
 
@@ -891,7 +1056,9 @@ int hippie_create(const hippie_cfg* cfg, hippie_handle* out) {
 
 void hippie_destroy(hippie_handle h) {
   if (!h) return;
+  h->clear_graphs();
   if (h->side) cudaStreamDestroy(h->side);
+  if (h->cap) cudaStreamDestroy(h->cap);
   for (auto e : h->ev_pool) cudaEventDestroy(e);
   for (int i = 0; i < 2; ++i)
     if (h->wside[i]) cudaStreamDestroy(h->wside[i]);
@@ -956,8 +1123,11 @@ int hippie_bind(hippie_handle h, float* params, float* grads, float* exp_avg, fl
   cudaStream_t st = (cudaStream_t)stream;
   h->P = params, h->G = grads, h->M1 = exp_avg, h->M2 = exp_avg_sq;
   h->bn_mean = bn_mean, h->bn_var = bn_var, h->bn_count = bn_count, h->ws = (float*)workspace;
+  h->clear_graphs();
+  if (const char* g = getenv("HIPPIE_B200_GRAPHS")) h->use_graphs = atoi(g) != 0;
   if (!h->side) {
     cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking);
+    cudaStreamCreateWithFlags(&h->cap, cudaStreamNonBlocking);
     cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
     for (int i = 0; i < 2; ++i) cudaStreamCreateWithFlags(&h->wside[i], cudaStreamNonBlocking);
     h->ev_pool.resize(512);
@@ -989,8 +1159,8 @@ int hippie_train_fwd_bwd(hippie_handle h, const float* x1, const float* x2, cons
   if (h->cfg.inference_only) return h->fail(-7, "inference-only engine");
   if (!eps) return h->fail(-4, "eps is required for training (reparameterisation noise)");
   if (B < 2) return h->fail(-3, "training-mode BatchNorm needs B >= 2");
-  return h->run(true, true, x1, x2, src, cls, eps, B, beta, w1, w2, scalars_out, out_enc, out_mu, out_logvar, out_dec1,
-                out_dec2, (cudaStream_t)stream);
+  hippie_engine::CallArgs a{0, x1, x2, src, cls, eps, B, beta, w1, w2, -1, scalars_out, out_enc, out_mu, out_logvar, out_dec1, out_dec2};
+  return h->call(a, (cudaStream_t)stream);
 }
 
 int hippie_eval_forward(hippie_handle h, const float* x1, const float* x2, const int64_t* src, const int64_t* cls,
@@ -998,8 +1168,8 @@ int hippie_eval_forward(hippie_handle h, const float* x1, const float* x2, const
                         float* out_mu, float* out_logvar, float* out_dec1, float* out_dec2, void* stream) {
   if (!h) return -1;
   if (int rc = h->validate(B, x1, x2, src)) return rc;
-  return h->run(false, false, x1, x2, src, cls, eps, B, beta, w1, w2, scalars_out, out_enc, out_mu, out_logvar,
-                out_dec1, out_dec2, (cudaStream_t)stream);
+  hippie_engine::CallArgs a{2, x1, x2, src, cls, eps, B, beta, w1, w2, -1, scalars_out, out_enc, out_mu, out_logvar, out_dec1, out_dec2};
+  return h->call(a, (cudaStream_t)stream);
 }
 
 int hippie_train_forward(hippie_handle h, const float* x1, const float* x2, const int64_t* src, const int64_t* cls,
@@ -1008,34 +1178,16 @@ int hippie_train_forward(hippie_handle h, const float* x1, const float* x2, cons
   if (!h) return -1;
   if (int rc = h->validate(B, x1, x2, src)) return rc;
   if (B < 2) return h->fail(-3, "training-mode BatchNorm needs B >= 2");
-  return h->run(true, false, x1, x2, src, cls, eps, B, beta, w1, w2, scalars_out, out_enc, out_mu, out_logvar, out_dec1,
-                out_dec2, (cudaStream_t)stream);
+  hippie_engine::CallArgs a{1, x1, x2, src, cls, eps, B, beta, w1, w2, -1, scalars_out, out_enc, out_mu, out_logvar, out_dec1, out_dec2};
+  return h->call(a, (cudaStream_t)stream);
 }
 
 int hippie_embed(hippie_handle h, const float* x1, const float* x2, const int64_t* src, const int64_t* cls, int32_t B,
                  int32_t zscore_ddof, float* out_enc, float* out_mu, float* out_logvar, void* stream) {
   if (!h) return -1;
   if (int rc = h->validate(B, x1, x2, src)) return rc;
-  cudaStream_t main = (cudaStream_t)stream;
-  h->launches = 0;
-  Branch b0{main, h->ws + h->part_off[0], h->ws + h->bpart_off[0]}, b1{h->side, h->ws + h->part_off[1], h->ws + h->bpart_off[1]};
-  launch_bn_eval_coefs(reinterpret_cast<const BnEvalEntry*>(h->ws + h->bn_table_off), (int)h->bn_table.size(), h->P,
-                       h->bn_mean, h->bn_var, h->ws, main);
-  ++h->launches;
-  h->refresh_weights(false, main);
-  const bool two = h->n_enc == 2;
-  if (two) h->fork(main);
-  h->encoder_fwd(h->enc[0], x1, B, false, b0);
-  if (two) {
-    h->encoder_fwd(h->enc[1], x2, B, false, b1);
-    h->join(main);
-  }
-  HeadArgs ha = h->head_args(B, src, cls, nullptr, false, false, out_enc, out_mu, out_logvar, 0.f, zscore_ddof);
-  ha.kl_sum = nullptr;
-  launch_head_fwd(ha, main);
-  ++h->launches;
-  if (h->failed) return h->fail(-9, h->err);
-  return h->check("hippie_embed");
+  hippie_engine::CallArgs a{3, x1, x2, src, cls, nullptr, B, 0.f, 0.f, 0.f, zscore_ddof, nullptr, out_enc, out_mu, out_logvar, nullptr, nullptr};
+  return h->call(a, (cudaStream_t)stream);
 }
 
 int hippie_clip_adamw(hippie_handle h, float lr, float beta1, float beta2, float eps, float weight_decay, float max_norm,

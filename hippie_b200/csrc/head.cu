@@ -133,19 +133,25 @@ __device__ void ph_dgrad(const Tc& tc, const float* dy, int ldy, const float* __
   }
 }
 
-// dW[j][i] = sum_b dy[b][j] * x[b][i];  db[j] = sum_b dy[b][j]
+// dW[j][i] = sum_b dy[b][j] * x[b][i];  db[j] = sum_b dy[b][j]     one warp per output, lanes over the batch
 __device__ void ph_wgrad(const Tc& tc, const float* dy, int ldy, const float* x, int ldx, int nin, int nout, float* dW,
                          float* db, int B) {
   const int total = nout * (nin + 1);
-  for (int idx = tc.t0; idx < total; idx += tc.ts) {
+  const int warp = tc.t0 >> 5, lane = threadIdx.x & 31, nw = tc.ts >> 5;
+  for (int idx = warp; idx < total; idx += nw) {
     const int j = idx / (nin + 1), i = idx % (nin + 1);
     float s = 0.f;
     if (i < nin) {
-      for (int b = 0; b < B; ++b) s = fmaf(dy[(int64_t)b * ldy + j], x[(int64_t)b * ldx + i], s);
-      dW[(int64_t)j * nin + i] = s;
+      for (int b = lane; b < B; b += 32) s = fmaf(dy[(int64_t)b * ldy + j], x[(int64_t)b * ldx + i], s);
     } else {
-      for (int b = 0; b < B; ++b) s += dy[(int64_t)b * ldy + j];
-      db[j] = s;
+      for (int b = lane; b < B; b += 32) s += dy[(int64_t)b * ldy + j];
+    }
+    s = warp_sum(s);
+    if (lane == 0) {
+      if (i < nin)
+        dW[(int64_t)j * nin + i] = s;
+      else
+        db[j] = s;
     }
   }
 }

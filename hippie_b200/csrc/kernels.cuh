@@ -23,8 +23,6 @@ constexpr float kBnMomentum = 0.1f;
 struct ConvGemm {
   const float* A;     // input tensor base (row 0)
   const float* W;     // [N][K] K-contiguous
-  const float* W_lo;  // tcgen05 3xTF32 path: W - trunc_tf32(W); unused by the FP32 SIMT kernel
-  const float* A_lo;  // tcgen05 3xTF32 path: A - trunc_tf32(A)
   const float* bias;  // [N] or null
   float* C;           // output tensor base (row 0)
   float* part;        // BatchNorm statistics partials [mtile][N][2] = (sum, centred M2), or null
@@ -42,24 +40,10 @@ struct ConvGemm {
 // returns the number of logical rows per statistics tile (BM) it used
 int launch_conv_gemm_simt(const ConvGemm& g, cudaStream_t s);
 
-// ---- tcgen05 path (conv_tc.cu): TMA tensor maps are built on the host at first use ----------------------
+// ---- TMA tensor maps of the tcgen05 path (conv_pair.cu) are built on the host at first use ---------------
 struct alignas(64) TcMap {
   unsigned char opaque[128];  // CUtensorMap
 };
-bool tc_init(std::string* err);  // resolves cuTensorMapEncodeTiled through the runtime; sets kernel attributes
-bool tc_make_act_map(TcMap* out, const float* base, int in_C, int K, int Lout, int in_rows, int in_stride, int in_off,
-                     int max_batch);
-bool tc_make_weight_map(TcMap* out, const float* w, int N, int K, int bn);
-int tc_pick_bn(int B, int N, int Lout, int sm_count);
-struct WgradGemm;
-bool tc_make_rows_map(TcMap* out, const float* base, int row_floats, int channels, int rows, int box_groups);
-void tc_debug_conv(int dbg);  // tools/tc_test only
-void tc_debug_wgrad_knobs(uint32_t lbo, uint32_t sbo, uint32_t ltype, int tma_swizzle);  // tools/tc_test only
-void launch_wgrad_tc(const WgradGemm& g, const TcMap& mapDY, const TcMap& mapX, int bn, int sm_count, int passes,
-                     cudaStream_t s);
-// passes = 3: fp32-accurate 3xTF32; passes = 1: one tf32 pass with round-to-nearest operands
-int launch_conv_gemm_tc(const ConvGemm& g, const TcMap& mapA, const TcMap& mapW, int bn, int B, int passes,
-                        cudaStream_t s);
 
 // ---- weight gradient:  dW[m, n] += sum_r dY[r, m] * X[(r + roff) * Cin + n]  (split-K, atomics) -------
 struct WgradGemm {
@@ -194,17 +178,18 @@ void launch_pairsum_acc(const float* src, float* dst, int B, int L, int C, cudaS
 // ---- encoder tail: adaptive_avg_pool1d + Linear(512 -> F)   reference hippie/backbones.py:100-102 -------
 void launch_pool_linear_fwd(const float* x4, int B, int L, int C, const float* W, const float* bias, int F,
                             float* pooled, float* h, cudaStream_t s);
-// dpool -> g_x4 (overwrite), dW/db written into grads
-void launch_pool_linear_bwd(const float* dh, const float* pooled, const float* W, int B, int L, int C, int F,
-                            float* g_x4, float* dW, float* db, cudaStream_t s);
-constexpr int kPoolLinearBwdLaunches = 2;
+// dpool -> g_x4 (overwrite)
+void launch_pool_linear_bwd_x(const float* dh, const float* W, int B, int L, int C, int F, float* g_x4, cudaStream_t s);
+// dW[j][i] = sum_b dy[b][j] * x[b][i], db[j] = sum_b dy[b][j]: the weight gradients of the Linear layers next to the
+// backbones; off the critical path (the engine launches them on the weight-gradient streams)
+void launch_linear_wgrad(const float* dy, int ldy, const float* x, int ldx, int B, int nin, int nout, float* dW, float* db,
+                         cudaStream_t s);
 
 // ---- decoder head: Linear(F -> 512) + unsqueeze + nearest x4   reference hippie/backbones.py:129-131 ---
 void launch_dec_linear_fwd(const float* d, int B, int F, const float* W, const float* bias, int C, float* t0,
                            uint16_t* t0_p /*fp16 pair planes or null*/, int64_t t0_ps, cudaStream_t s);
-void launch_dec_linear_bwd(const float* g_t0, const float* d, const float* W, int B, int F, int C, float* gx0,
-                           float* dd, float* dW, float* db, cudaStream_t s);
-constexpr int kDecLinearBwdLaunches = 2;
+void launch_dec_linear_bwd_x(const float* g_t0, const float* W, int B, int F, int C, float* gx0, float* dd,
+                             cudaStream_t s);
 
 // ---- decoder tail: nearest x2 -> conv(64->1,k3,bias) -> view -> Linear(64 -> Lo) + MSE  -----------------
 //      reference hippie/backbones.py:117-118,136-139 and hippie/model.py:465-466
@@ -292,6 +277,18 @@ struct AdamArgs {
 };
 void launch_clip_adamw(const AdamArgs& a, cudaStream_t s);
 constexpr int kClipAdamLaunches = 3;
+
+// up to 8 segment copies of 4-byte words in one launch (input staging / output delivery around a graph replay)
+struct IoSeg {
+  const void* src;
+  void* dst;
+  int64_t words;
+};
+struct IoCopy {
+  IoSeg seg[8];
+  int n;
+};
+void launch_io_copy(const IoCopy& c, cudaStream_t s);
 
 // transposed + tap-flipped copies of the conv weights for dgrad:  wt[ci][k-1-t][co] = w[co][t][ci]
 struct WtEntry {

@@ -3,6 +3,7 @@
 // channels-last padded rows (kernels.cuh).  Reference anchors are given per kernel.
 #include "kernels.cuh"
 #include "pair_fmt.cuh"
+#include "pdl.cuh"
 
 namespace hp {
 
@@ -198,6 +199,8 @@ template <int RES>  // 0 none, 1 identity, 2 BatchNorm'd shortcut
 __global__ void __launch_bounds__(256) bn_apply_kernel(BnApply a) {
   __shared__ float s_sc[kSlab], s_sh[kSlab], s_mu[kSlab], r_sc[kSlab], r_sh[kSlab], r_mu[kSlab];
   __shared__ ChanAcc s_acc[8][kSlab];
+  pdl_trigger();
+  pdl_wait();
   const int c0 = blockIdx.x * kSlab;
   if (a.train) {
     bn_finalize_slab(a.fin, c0, blockIdx.y == 0, s_sc, s_sh, s_mu, s_acc);
@@ -291,6 +294,8 @@ __device__ __forceinline__ float block_max(float v, float* red) {  // 256 thread
 __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(BnBwd a, int rows_per_cta) {
   __shared__ float4 red[3][256];
   __shared__ float mred[8];
+  pdl_trigger();
+  pdl_wait();
   const int C4 = a.C >> 2;
   const int RL = 256 / C4;  // row lanes
   const int cq = threadIdx.x % C4, rl = threadIdx.x / C4;
@@ -387,6 +392,8 @@ __device__ __forceinline__ float dc_scale(const float* slot) {
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(BnBwd a, int nchunks) {
   __shared__ double s_sum[8][kSlab][3];
   __shared__ float s_m1[kSlab], s_m2[kSlab], s_m3[kSlab];
+  pdl_trigger();
+  pdl_wait();
   const int c0 = blockIdx.x * kSlab;
   {
     const int c = threadIdx.x & (kSlab - 1), slice = threadIdx.x >> 5;
@@ -461,6 +468,8 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(BnBwd a, int nchunks)
 
 __global__ void __launch_bounds__(256) pairsum_acc_kernel(const float* __restrict__ src, float* __restrict__ dst, int B,
                                                           int L, int C) {
+  pdl_trigger();
+  pdl_wait();
   const int C4 = C >> 2;
   const int64_t total = (int64_t)B * L * C4;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -833,6 +842,14 @@ __global__ void __launch_bounds__(256) adamw_kernel(AdamArgs a, float decay, flo
 }
 
 // wt[ci][k-1-t][co] = w[co][t][ci]
+__global__ void __launch_bounds__(256) io_copy_kernel(IoCopy c) {
+  const IoSeg sg = c.seg[blockIdx.y];
+  const uint32_t* src = static_cast<const uint32_t*>(sg.src);
+  uint32_t* dst = static_cast<uint32_t*>(sg.dst);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < sg.words; i += (int64_t)gridDim.x * blockDim.x)
+    dst[i] = src[i];
+}
+
 __global__ void __launch_bounds__(256) refresh_wt_kernel(const WtEntry* __restrict__ tab,
                                                          const float* __restrict__ params, float* __restrict__ ws) {
   __shared__ float tile[32][33];
@@ -889,42 +906,42 @@ static inline int slab_row_chunks(int M, int C, int sm_count) {
 void launch_bn_apply(const BnApply& a, int sm_count, cudaStream_t s) {
   dim3 grid(a.C / kSlab, slab_row_chunks(a.B * a.L, a.C, sm_count));
   if (!a.r)
-    bn_apply_kernel<0><<<grid, 256, 0, s>>>(a);
+    launch_pdl(bn_apply_kernel<0>, grid, dim3(256), 0, s, a);
   else if (!a.rcoef)
-    bn_apply_kernel<1><<<grid, 256, 0, s>>>(a);
+    launch_pdl(bn_apply_kernel<1>, grid, dim3(256), 0, s, a);
   else
-    bn_apply_kernel<2><<<grid, 256, 0, s>>>(a);
+    launch_pdl(bn_apply_kernel<2>, grid, dim3(256), 0, s, a);
 }
 void launch_bn_bwd(const BnBwd& a, int sm_count, cudaStream_t s) {
   const int M = a.B * a.L;
   int rows = (M + kBnBwdMaxChunks - 1) / kBnBwdMaxChunks;
   if (rows < 16) rows = 16;
   const int nchunks = (M + rows - 1) / rows;
-  bn_bwd_reduce_kernel<<<nchunks, 256, 0, s>>>(a, rows);
+  launch_pdl(bn_bwd_reduce_kernel, dim3(nchunks), dim3(256), 0, s, a, rows);
   dim3 grid(a.C / kSlab, slab_row_chunks(M, a.C, sm_count));
-  bn_bwd_apply_kernel<<<grid, 256, 0, s>>>(a, nchunks);
+  launch_pdl(bn_bwd_apply_kernel, grid, dim3(256), 0, s, a, nchunks);
 }
 void launch_pairsum_acc(const float* src, float* dst, int B, int L, int C, cudaStream_t s) {
-  pairsum_acc_kernel<<<ew_grid((int64_t)B * L * (C / 4)), 256, 0, s>>>(src, dst, B, L, C);
+  launch_pdl(pairsum_acc_kernel, dim3(ew_grid((int64_t)B * L * (C / 4))), dim3(256), 0, s, src, dst, B, L, C);
 }
 void launch_pool_linear_fwd(const float* x4, int B, int L, int C, const float* W, const float* bias, int F,
                             float* pooled, float* h, cudaStream_t s) {
   pool_linear_fwd_kernel<<<B, 128, C * sizeof(float), s>>>(x4, L, C, W, bias, F, pooled, h);
 }
-void launch_pool_linear_bwd(const float* dh, const float* pooled, const float* W, int B, int L, int C, int F,
-                            float* g_x4, float* dW, float* db, cudaStream_t s) {
+void launch_pool_linear_bwd_x(const float* dh, const float* W, int B, int L, int C, int F, float* g_x4, cudaStream_t s) {
   pool_linear_bwd_x_kernel<<<B, 128, F * sizeof(float), s>>>(dh, W, L, C, F, g_x4);
-  linear_wgrad_rows_kernel<<<(F * (C + 1) + 63) / 64, 256, 0, s>>>(dh, F, pooled, C, B, C, F, dW, db);
+}
+void launch_linear_wgrad(const float* dy, int ldy, const float* x, int ldx, int B, int nin, int nout, float* dW, float* db,
+                         cudaStream_t s) {
+  linear_wgrad_rows_kernel<<<(nout * (nin + 1) + 63) / 64, 256, 0, s>>>(dy, ldy, x, ldx, B, nin, nout, dW, db);
 }
 void launch_dec_linear_fwd(const float* d, int B, int F, const float* W, const float* bias, int C, float* t0,
                            uint16_t* t0_p, int64_t t0_ps, cudaStream_t s) {
   dec_linear_fwd_kernel<<<B, 256, F * sizeof(float), s>>>(d, F, W, bias, C, t0, t0_p, t0_ps);
 }
-void launch_dec_linear_bwd(const float* g_t0, const float* d, const float* W, int B, int F, int C, float* gx0,
-                           float* dd, float* dW, float* db, cudaStream_t s) {
+void launch_dec_linear_bwd_x(const float* g_t0, const float* W, int B, int F, int C, float* gx0, float* dd,
+                             cudaStream_t s) {
   dec_linear_bwd_x_kernel<<<B, 256, C * sizeof(float), s>>>(g_t0, W, F, C, gx0, dd);
-  // dW[c][f] = sum_b gx0[b][c] * d[b][f];  db[c] = sum_b gx0[b][c]
-  linear_wgrad_rows_kernel<<<(C * (F + 1) + 63) / 64, 256, 0, s>>>(gx0, C, d, F, B, F, C, dW, db);
 }
 static size_t dec_tail_smem(int Lo) { return (size_t)(34 * 65 + Lo * 65 + 64 + ((Lo + 3) & ~3) + 68 + 192) * sizeof(float); }
 int launch_dec_tail(const DecTail& t, cudaStream_t s) {
@@ -957,6 +974,10 @@ void launch_clip_adamw(const AdamArgs& a, cudaStream_t s) {
   const float decay = (float)(1.0 - (double)a.lr * (double)a.wd);
   adamw_kernel<<<ew_grid(a.n), 256, 0, s>>>(a, decay, (float)((double)a.lr / bc1), (float)sqrt(bc2),
                                             (float)((double)a.lr / bc1c), (float)sqrt(bc2c));
+}
+void launch_io_copy(const IoCopy& c, cudaStream_t s) {
+  if (c.n <= 0) return;
+  io_copy_kernel<<<dim3(32, c.n), 256, 0, s>>>(c);
 }
 void launch_refresh_wt(const WtEntry* table_dev, int n, const float* params, float* ws, cudaStream_t s) {
   dim3 grid(64, 1, n);

@@ -1,4 +1,4 @@
-// PTX helpers shared by the tcgen05 kernels (conv_tc.cu: in-kernel 3xTF32 split; conv_pair.cu: 16-bit pair planes).
+// PTX helpers of the tcgen05 kernels (conv_pair.cu): mbarriers, TMA loads, UMMA descriptors, TMEM loads.
 #pragma once
 #include <cuda.h>
 #include <stdint.h>
@@ -7,7 +7,6 @@ namespace hp {
 namespace tc {
 
 constexpr int TC_BM = 128;
-constexpr int TC_BK = 32;  // floats per k-block = one 128-byte swizzle row
 constexpr int TC_THREADS = 192;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -63,30 +62,6 @@ __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
 
-// shared-memory matrix descriptor: K-major, 128-byte swizzle, 8-row groups 1024 B apart (cute::UMMA::SmemDescriptor)
-__device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t saddr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);  // start address, 16-byte units
-  d |= (uint64_t)1 << 16;                   // leading byte offset (unused for swizzled K-major)
-  d |= (uint64_t)(1024 >> 4) << 32;         // stride byte offset between 8-row groups
-  d |= (uint64_t)1 << 46;                   // descriptor version (Blackwell)
-  d |= (uint64_t)2 << 61;                   // SWIZZLE_128B
-  return d;
-}
-// instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=tf32, K-major both, M=128, N=BN
-__host__ __device__ constexpr uint32_t umma_idesc_tf32(int n) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
-}
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
-      "}" ::"r"(tmem_d),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
-      : "memory");
-}
 // kind::f16 (fp16 / bf16 operands, K = 16 per instruction).  fmt: 0 = F16, 1 = BF16; *_mn: 1 = MN-major operand.
 __host__ __device__ constexpr uint32_t umma_idesc_16(int n, int a_fmt, int b_fmt, int a_mn, int b_mn) {
   return (1u << 4) | ((uint32_t)a_fmt << 7) | ((uint32_t)b_fmt << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |

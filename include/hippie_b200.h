@@ -11,9 +11,12 @@
  * Conventions
  *   - plain C: pointers, sizes and PODs only; no torch types.  All tensor pointers are DEVICE
  *     pointers owned by the caller (PyTorch); the engine never allocates, frees or resizes them.
- *   - every launch goes to the caller-supplied `stream` (a cudaStream_t passed as void*); two
- *     internal side streams are forked from / joined to it with events, so the whole call is
- *     CUDA-graph capturable.  No hidden host syncs, no host reads of device data.
+ *   - every launch goes to the caller-supplied `stream` (a cudaStream_t passed as void*); internal
+ *     side streams are forked from / joined to it with events.  No hidden host syncs, no host reads
+ *     of device data.  From the second call of a signature (entry point, B, which optional pointers
+ *     are given, beta / w1 / w2) on, the launch sequence is replayed as a CUDA graph from staged
+ *     inputs (HIPPIE_B200_GRAPHS=0 disables that); calls made while the caller is capturing its own
+ *     graph are recorded into the caller's graph instead.
  *   - return value: 0 = ok, <0 = argument/config error, >0 = cudaError_t.  hippie_last_error()
  *     returns a message for the most recent non-zero return of that handle.
  *   - one handle per (process, device); not thread-safe.
@@ -46,10 +49,8 @@ typedef struct hippie_cfg {
   int32_t multimodal; /* 1 = MultiModalCVAE, 0 = hippieUnimodalCVAE                             */
   int32_t max_batch;  /* largest B any call will pass; sizes the workspace                      */
   int32_t inference_only; /* 1 = no gradient tensors in the workspace (embedding engines)      */
-  int32_t conv_path;  /* 0 = auto (tcgen05 3xTF32, FP32 CUDA-core GEMM if TMA maps are unavailable),
-                         1 = force the FP32 CUDA-core GEMM, 2 = require tcgen05 (bind fails otherwise),
-                         3 = tcgen05 with fast backward: forward stays 3xTF32 (loss / embedding parity),
-                             dgrad and wgrad run ONE tf32 pass with round-to-nearest operands          */
+  int32_t conv_path;  /* 0 = tcgen05 implicit GEMMs over fp16 pair planes (bind fails when TMA tensor maps are
+                         unavailable), 1 = FP32 CUDA-core implicit GEMMs (the parity yardstick of the former)     */
 } hippie_cfg;
 
 /* Layout kinds of a parameter inside the flat buffer. */
@@ -141,7 +142,7 @@ int hippie_embed(hippie_handle h, const float* x1, const float* x2, const int64_
 /* Number of kernel launches issued by the most recent call of each kind (bench.py gpu_launches). */
 int hippie_last_launch_count(hippie_handle h);
 
-/* 2 = the tcgen05 3xTF32 implicit GEMM serves conv forward / dgrad, 1 = the FP32 CUDA-core GEMM does. */
+/* 2 = the tcgen05 pair-plane implicit GEMMs serve conv forward / dgrad / wgrad, 1 = the FP32 CUDA-core GEMMs do. */
 int hippie_conv_path_in_use(hippie_handle h);
 
 /* Measurement aid for bench.py (not part of the reference interface): when enabled, every implicit-GEMM launch
