@@ -42,15 +42,44 @@ def synth(n, seed=1234):
 
 
 class ClockSampler(threading.Thread):
+    """Samples SM clocks and throttle reasons DURING the timed region (NVML, 20 ms period; nvidia-smi as a fallback)."""
+
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.rows, self.stop_flag = index, [], False
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_sm = pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nvml = None
+
+    def _sample_nvml(self):
+        n = self.nvml
+        sm = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
+        try:
+            r = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+        except Exception:
+            r = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+        flag = lambda name: bool(r & getattr(n, name, 0))
+        self.rows.append([str(sm), str(self.max_sm),
+                          "Active" if flag("nvmlClocksThrottleReasonHwSlowdown") else "Not Active",
+                          "Active" if flag("nvmlClocksThrottleReasonHwThermalSlowdown") else "Not Active",
+                          "Active" if flag("nvmlClocksThrottleReasonSwThermalSlowdown") else "Not Active",
+                          "Active" if flag("nvmlClocksThrottleReasonSwPowerCap") else "Not Active"])
 
     def run(self):
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         while not self.stop_flag:
             try:
+                if self.nvml is not None:
+                    self._sample_nvml()
+                    time.sleep(0.02)
+                    continue
                 out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits"],
                                      capture_output=True, text=True, timeout=5).stdout.strip()
                 if out:
@@ -65,7 +94,7 @@ class ClockSampler(threading.Thread):
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": reasons,
-                "samples": len(sm)}
+                "samples": len(sm), "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 def cpu_reference_run(steps, warmup, budget_s=150.0):

@@ -43,6 +43,11 @@ constexpr int PK = 64;  // K elements per k-block = one 128-byte swizzle row of 
 // prologue / epilogue of one CTA (or of the next kernel, see pdl.cuh) overlaps the main loop of the other.  Measured on
 // the bs512 step: 4.77 ms (128x128 + 128x64 tiles, 1 CTA/SM) -> 4.36 ms; the step is bound by the chain of short
 // dependent kernels, not by tile efficiency.
+// Phase stamps of one CTA (tools/pair_test, PT_STAMPS=1): prologue 0.26 us, first fill 0.67 us, main loop 0.53 us per
+// k-block (ANY layer, any grid), epilogue 3.3 us.  The k-block period is set by the TMA unit's ROW rate, not by bytes:
+// a k-block is 384 box rows of 128 B; halving the rows to 64 B (32-wide k-blocks, 64-byte swizzle, 4 stages: tried)
+// costs 0.38 us per half block, i.e. the same ~1.4 ns per row.  More MACs per fetched row (wider tiles, 2-CTA pairs)
+// is the way to a faster main loop; deeper rings are not.
 constexpr int kBN = 64, kStages = 2;
 
 struct PairConv {
@@ -58,7 +63,15 @@ struct PairConv {
   int kb_per_tap;  // b_mn: k-blocks per tap (= Cout / 64)
   int taps;        // b_mn: kernel size (3 or 1); tap of k-block kb = taps - 1 - kb / kb_per_tap
   const float* dyn_scale;  // optional device scalar multiplied into out_scale
+  unsigned long long* stamps;  // tools/pair_test only: %globaltimer at the phase boundaries of CTA (0, 0)
 };
+__device__ __forceinline__ void stamp(const PairConv& p, int i) {
+  if (p.stamps && blockIdx.x == 0 && blockIdx.y == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    p.stamps[i] = t;
+  }
+}
 
 template <int BN, int STAGES>
 struct PairSmem {
@@ -88,6 +101,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
 
   pdl_trigger();
+  if (threadIdx.x == 0) stamp(p, 0);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b0 = blockIdx.x * p.nb, n0 = blockIdx.y * BN;
   const int nkb = p.K / PK;
@@ -114,6 +128,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2)
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();  // everything above touched only shared / tensor memory
+  if (threadIdx.x == 0) stamp(p, 1);
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -148,6 +163,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2)
         const int s = kb % STAGES;
         const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
         mbar_wait(&full[s], ph);
+        if (kb == 0) stamp(p, 2);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t st = smem_u32(ring + s * S::STAGE_BYTES);
         const uint64_t a_hi = umma_desc(st, 16, 1024, 2), a_lo = umma_desc(st + S::A_LO, 16, 1024, 2);
@@ -175,6 +191,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2)
     // ===================== epilogue =====================
     const int t = threadIdx.x - 64;  // 0..127
     mbar_wait(accum, 0);
+    if (t == 0) stamp(p, 3);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     float* stage = reinterpret_cast<float*>(ring);  // [128][BN + 4]; the ring is idle once `accum` has fired
     const int q = warp & 3;                         // TMEM lane quarter this warp may read
@@ -196,6 +213,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2)
             make_uint4(r[i * 4], r[i * 4 + 1], r[i * 4 + 2], r[i * 4 + 3]);
     }
     asm volatile("bar.sync 1, 128;" ::: "memory");  // the four epilogue warps only
+    if (t == 0) stamp(p, 4);
 
     const int nvalid = min(rows_tile, (p.B - b0) * p.Lout);  // rows of this tile that are real outputs
     {  // coalesced stores: thread -> (row group, fixed column quad)
@@ -216,6 +234,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2)
         *dst = v;
       }
     }
+    if (t == 0) stamp(p, 5);
     if (p.part) {  // BatchNorm statistics of this tile: (sum, centred sum of squares) per column
       // BN == 64: two threads per column (rows split in halves, combined with Chan's formula through shared memory)
       constexpr int TPC = 128 / BN;  // threads per column
@@ -269,6 +288,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2)
 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if (threadIdx.x == 0) stamp(p, 6);
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(S::TMEM_COLS) : "memory");
   }
@@ -516,7 +536,7 @@ int launch_conv_pair(const ConvGemm& g, const TcMap& mapA, const TcMap& mapB, in
   p.out_scale = o.out_scale;
   p.idesc = umma_idesc_16(bn, o.a_fmt, o.b_fmt, 0, o.b_mn ? 1 : 0);
   p.b_mn = o.b_mn, p.taps = o.taps, p.kb_per_tap = o.taps > 0 ? (g.K / o.taps) / PK : 1;
-  p.dyn_scale = o.dyn_scale;
+  p.dyn_scale = o.dyn_scale, p.stamps = o.stamps;
   dim3 grid((B + p.nb - 1) / p.nb, g.N / bn);
 
   const CUtensorMap& a = *reinterpret_cast<const CUtensorMap*>(mapA.opaque);
@@ -533,7 +553,7 @@ void launch_wgrad_pair(const WgradGemm& g, const TcMap& mapDY, const TcMap& mapX
   bn = kBN;
   p.idesc = umma_idesc_16(bn, o.a_fmt, o.b_fmt, 1, 1);
   const int tiles = ((g.M + TC_BM - 1) / TC_BM) * (g.N / bn);
-  int splits = sm_count / tiles;
+  int splits = (2 * sm_count) / tiles;  // two CTAs per SM
   const int kblocks = (g.R + PK - 1) / PK;
   if (splits > (kblocks + 3) / 4) splits = (kblocks + 3) / 4;  // at least 4 k-blocks (256 rows) per CTA
   if (splits < 1) splits = 1;

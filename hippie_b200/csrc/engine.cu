@@ -1126,10 +1126,13 @@ int hippie_bind(hippie_handle h, float* params, float* grads, float* exp_avg, fl
   h->clear_graphs();
   if (const char* g = getenv("HIPPIE_B200_GRAPHS")) h->use_graphs = atoi(g) != 0;
   if (!h->side) {
-    cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking);
-    cudaStreamCreateWithFlags(&h->cap, cudaStreamNonBlocking);
+    // the branch chains are the critical path: they get the highest priority, the weight-gradient streams the lowest
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    cudaStreamCreateWithPriority(&h->side, cudaStreamNonBlocking, prio_hi);
+    cudaStreamCreateWithPriority(&h->cap, cudaStreamNonBlocking, prio_hi);
     cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
-    for (int i = 0; i < 2; ++i) cudaStreamCreateWithFlags(&h->wside[i], cudaStreamNonBlocking);
+    for (int i = 0; i < 2; ++i) cudaStreamCreateWithPriority(&h->wside[i], cudaStreamNonBlocking, prio_lo);
     h->ev_pool.resize(512);
     for (auto& e : h->ev_pool) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming);

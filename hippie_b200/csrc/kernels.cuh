@@ -63,6 +63,7 @@ struct PairOpts {
   int b_mn;          // conv: 1 = B tiles read MN-major from the forward weight planes [co][t][ci] (dgrad)
   int taps;          // conv, b_mn = 1: kernel size of the layer
   const float* dyn_scale = nullptr;  // device float multiplied into out_scale (1 / scale of a gradient pair tensor)
+  unsigned long long* stamps = nullptr;  // tools/pair_test: 8 device slots for %globaltimer phase stamps of CTA (0, 0)
 };
 bool pair_init(std::string* err);
 bool pair_make_act_map(TcMap* out, const void* planes, int64_t plane_stride, int fmt, int in_C, int K, int Lout,

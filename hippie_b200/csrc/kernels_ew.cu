@@ -135,33 +135,38 @@ __global__ void reduce_partials_kernel(const float* __restrict__ part, int npart
 constexpr int kSlab = 32;  // channels per CTA: 128-byte row segments
 
 struct ChanAcc {
-  double n, mean, m2;
+  double s, q;
 };
-__device__ __forceinline__ void chan_merge(ChanAcc& a, double nb, double mean_b, double m2_b) {
-  if (nb <= 0.0) return;
-  const double n = a.n + nb, delta = mean_b - a.mean;
-  a.mean += delta * (nb / n);
-  a.m2 += m2_b + delta * delta * (a.n * nb / n);
-  a.n = n;
-}
 
 // 256 threads.  Results for the slab's channels land in shared arrays sc / sh / mu (scale, shift = beta, mean).
+// Per tile t with n_t rows the conv left (s_t, m2_t) = (sum, centred sum of squares); with S = sum s_t,
+// Q = sum (m2_t + s_t^2 / n_t):  mean = S / M,  M2 = Q - S^2 / M  (Chan's combination written as sums; double keeps
+// the cancellation harmless: relative error 1e-16 * (1 + mean^2 / var)).  No division inside the loop.
 __device__ __forceinline__ void bn_finalize_slab(const BnFinalize& f, int c0, bool publish, float* sc, float* sh,
                                                  float* mu, ChanAcc (*acc)[kSlab]) {
   const int c = threadIdx.x & (kSlab - 1), slice = threadIdx.x >> 5;  // 8 slices of tiles
-  ChanAcc a{0.0, 0.0, 0.0};
+  const double inv_full = 1.0 / (double)f.tile_rows;
+  const int last = f.ntiles - 1;
+  const double inv_last = 1.0 / (double)(f.M - last * f.tile_rows);
+  double S = 0.0, Q = 0.0;
+  const float* base = f.part + ((int64_t)c0 + c) * 2;
+#pragma unroll 4
   for (int t = slice; t < f.ntiles; t += 8) {
-    const float2 p = __ldcg(reinterpret_cast<const float2*>(f.part + ((int64_t)t * f.C + c0 + c) * 2));
-    const int nt = min(f.tile_rows, f.M - t * f.tile_rows);
-    chan_merge(a, (double)nt, (double)p.x / (double)nt, (double)p.y);
+    const float2 p = __ldcg(reinterpret_cast<const float2*>(base + (int64_t)t * f.C * 2));
+    const double st = (double)p.x;
+    S += st;
+    Q += (double)p.y + st * st * (t == last ? inv_last : inv_full);
   }
-  acc[slice][c] = a;
+  acc[slice][c] = ChanAcc{S, Q};
   __syncthreads();
   if (slice == 0) {
-    for (int k = 1; k < 8; ++k) chan_merge(a, acc[k][c].n, acc[k][c].mean, acc[k][c].m2);
-    const double var_b = a.m2 / (double)f.M;
+    for (int k = 1; k < 8; ++k) S += acc[k][c].s, Q += acc[k][c].q;
+    const double mean = S / (double)f.M;
+    double m2 = Q - S * mean;
+    m2 = m2 > 0.0 ? m2 : 0.0;
+    const double var_b = m2 / (double)f.M;
     const float invstd = (float)(1.0 / sqrt(var_b + (double)kBnEps));
-    const float meanf = (float)a.mean;
+    const float meanf = (float)mean;
     const int cc = c0 + c;
     const float scale = f.gamma[cc] * invstd, beta = f.beta[cc];
     sc[c] = scale, sh[c] = beta, mu[c] = meanf;
@@ -170,7 +175,7 @@ __device__ __forceinline__ void bn_finalize_slab(const BnFinalize& f, int c0, bo
       f.coef[1 * f.C + cc] = beta;
       f.coef[2 * f.C + cc] = meanf;
       f.coef[3 * f.C + cc] = invstd;
-      const float var_u = (float)(a.m2 / (double)max(f.M - 1, 1));
+      const float var_u = (float)(m2 / (double)max(f.M - 1, 1));
       f.run_mean[cc] = (1.f - kBnMomentum) * f.run_mean[cc] + kBnMomentum * meanf;
       f.run_var[cc] = (1.f - kBnMomentum) * f.run_var[cc] + kBnMomentum * var_u;
       if (cc == 0) *f.run_count += 1;
@@ -229,32 +234,43 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(BnApply a) {
   const int rows_per = (M + gridDim.y - 1) / gridDim.y;
   const int m_end = min(M, (int)(blockIdx.y + 1) * rows_per);
   const int col = c0 + q * 4;
-  for (int m = blockIdx.y * rows_per + rl; m < m_end; m += 32) {
-    const int b = m / a.L, l = m - b * a.L;
-    const int64_t row = (int64_t)b * (a.L + 2) + 1 + l;
-    const float4 x = *reinterpret_cast<const float4*>(a.c + row * a.C + col);
-    float4 y;
-    y.x = fmaf(x.x - mu.x, sc.x, be.x), y.y = fmaf(x.y - mu.y, sc.y, be.y);
-    y.z = fmaf(x.z - mu.z, sc.z, be.z), y.w = fmaf(x.w - mu.w, sc.w, be.w);
-    if (RES == 1) {
-      const float4 r = *reinterpret_cast<const float4*>(a.r + row * a.C + col);
-      y.x += r.x, y.y += r.y, y.z += r.z, y.w += r.w;
-    } else if (RES == 2) {
-      const float4 r = *reinterpret_cast<const float4*>(a.r + row * a.C + col);
-      y.x += fmaf(r.x - rm.x, rs.x, rb.x), y.y += fmaf(r.y - rm.y, rs.y, rb.y);
-      y.z += fmaf(r.z - rm.z, rs.z, rb.z), y.w += fmaf(r.w - rm.w, rs.w, rb.w);
+  constexpr int U = 4;  // independent rows per thread and iteration: the kernel is latency-bound, keep loads in flight
+  for (int m0 = blockIdx.y * rows_per + rl; m0 < m_end; m0 += 32 * U) {
+    float4 x[U], r[U];
+    int64_t row[U], ru[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int m = m0 + 32 * u;
+      if (m < m_end) {
+        const int b = m / a.L, l = m - b * a.L;
+        row[u] = (int64_t)b * (a.L + 2) + 1 + l, ru[u] = (int64_t)b * (2 * a.L + 2) + 1 + 2 * l;
+        x[u] = *reinterpret_cast<const float4*>(a.c + row[u] * a.C + col);
+        if (RES != 0) r[u] = *reinterpret_cast<const float4*>(a.r + row[u] * a.C + col);
+      }
     }
-    y.x = lrelu(y.x, a.slope), y.y = lrelu(y.y, a.slope), y.z = lrelu(y.z, a.slope), y.w = lrelu(y.w, a.slope);
-    *reinterpret_cast<float4*>(a.out + row * a.C + col) = y;
-    if (a.out_p) store_pair4(a.out_p, a.out_ps, row * a.C + col, y);
-    const int64_t ru = (int64_t)b * (2 * a.L + 2) + 1 + 2 * l;
-    if (a.out_up) {
-      *reinterpret_cast<float4*>(a.out_up + ru * a.C + col) = y;
-      *reinterpret_cast<float4*>(a.out_up + (ru + 1) * a.C + col) = y;
-    }
-    if (a.up_p) {
-      store_pair4(a.up_p, a.up_ps, ru * a.C + col, y);
-      store_pair4(a.up_p, a.up_ps, (ru + 1) * a.C + col, y);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (m0 + 32 * u >= m_end) break;
+      float4 y;
+      y.x = fmaf(x[u].x - mu.x, sc.x, be.x), y.y = fmaf(x[u].y - mu.y, sc.y, be.y);
+      y.z = fmaf(x[u].z - mu.z, sc.z, be.z), y.w = fmaf(x[u].w - mu.w, sc.w, be.w);
+      if (RES == 1) {
+        y.x += r[u].x, y.y += r[u].y, y.z += r[u].z, y.w += r[u].w;
+      } else if (RES == 2) {
+        y.x += fmaf(r[u].x - rm.x, rs.x, rb.x), y.y += fmaf(r[u].y - rm.y, rs.y, rb.y);
+        y.z += fmaf(r[u].z - rm.z, rs.z, rb.z), y.w += fmaf(r[u].w - rm.w, rs.w, rb.w);
+      }
+      y.x = lrelu(y.x, a.slope), y.y = lrelu(y.y, a.slope), y.z = lrelu(y.z, a.slope), y.w = lrelu(y.w, a.slope);
+      *reinterpret_cast<float4*>(a.out + row[u] * a.C + col) = y;
+      if (a.out_p) store_pair4(a.out_p, a.out_ps, row[u] * a.C + col, y);
+      if (a.out_up) {
+        *reinterpret_cast<float4*>(a.out_up + ru[u] * a.C + col) = y;
+        *reinterpret_cast<float4*>(a.out_up + (ru[u] + 1) * a.C + col) = y;
+      }
+      if (a.up_p) {
+        store_pair4(a.up_p, a.up_ps, ru[u] * a.C + col, y);
+        store_pair4(a.up_p, a.up_ps, (ru[u] + 1) * a.C + col, y);
+      }
     }
   }
 }
@@ -320,26 +336,41 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(BnBwd a, int rows_pe
                             make_float4(ga.x * iss.x, ga.y * iss.y, ga.z * iss.z, ga.w * iss.w)));
       }
     }
-    for (int m = m_begin + rl; m < m_end; m += RL) {
-      const int b = m / a.L, l = m - b * a.L;
-      const int64_t row = (int64_t)b * (a.L + 2) + 1 + l;
-      float4 g = load_g(a, b, l, cq * 4);
-      const float4 o = *reinterpret_cast<const float4*>(a.out + row * a.C + cq * 4);
-      g.x *= o.x > 0.f ? 1.f : a.slope, g.y *= o.y > 0.f ? 1.f : a.slope;
-      g.z *= o.z > 0.f ? 1.f : a.slope, g.w *= o.w > 0.f ? 1.f : a.slope;
-      const float4 x = *reinterpret_cast<const float4*>(a.c + row * a.C + cq * 4);
-      s1.x += g.x, s1.y += g.y, s1.z += g.z, s1.w += g.w;
-      const float4 xh = make_float4((x.x - mu.x) * is.x, (x.y - mu.y) * is.y, (x.z - mu.z) * is.z, (x.w - mu.w) * is.w);
-      s2.x = fmaf(g.x, xh.x, s2.x), s2.y = fmaf(g.y, xh.y, s2.y);
-      s2.z = fmaf(g.z, xh.z, s2.z), s2.w = fmaf(g.w, xh.w, s2.w);
-      gm = fmax4abs(gm, g), xm = fmax4abs(xm, xh);
-      if (a.cs) {
-        const float4 xs = *reinterpret_cast<const float4*>(a.cs + row * a.C + cq * 4);
-        const float4 xsh = make_float4((xs.x - mus.x) * iss.x, (xs.y - mus.y) * iss.y, (xs.z - mus.z) * iss.z,
-                                       (xs.w - mus.w) * iss.w);
-        s3.x = fmaf(g.x, xsh.x, s3.x), s3.y = fmaf(g.y, xsh.y, s3.y);
-        s3.z = fmaf(g.z, xsh.z, s3.z), s3.w = fmaf(g.w, xsh.w, s3.w);
-        xsm = fmax4abs(xsm, xsh);
+    constexpr int U = 2;
+    for (int m0 = m_begin + rl; m0 < m_end; m0 += RL * U) {
+      float4 gv[U], ov[U], xv[U], xsv[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int m = m0 + RL * u;
+        if (m < m_end) {
+          const int b = m / a.L, l = m - b * a.L;
+          const int64_t row = (int64_t)b * (a.L + 2) + 1 + l;
+          gv[u] = load_g(a, b, l, cq * 4);
+          ov[u] = *reinterpret_cast<const float4*>(a.out + row * a.C + cq * 4);
+          xv[u] = *reinterpret_cast<const float4*>(a.c + row * a.C + cq * 4);
+          if (a.cs) xsv[u] = *reinterpret_cast<const float4*>(a.cs + row * a.C + cq * 4);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (m0 + RL * u >= m_end) break;
+        float4 g = gv[u];
+        const float4 o = ov[u], x = xv[u];
+        g.x *= o.x > 0.f ? 1.f : a.slope, g.y *= o.y > 0.f ? 1.f : a.slope;
+        g.z *= o.z > 0.f ? 1.f : a.slope, g.w *= o.w > 0.f ? 1.f : a.slope;
+        s1.x += g.x, s1.y += g.y, s1.z += g.z, s1.w += g.w;
+        const float4 xh = make_float4((x.x - mu.x) * is.x, (x.y - mu.y) * is.y, (x.z - mu.z) * is.z, (x.w - mu.w) * is.w);
+        s2.x = fmaf(g.x, xh.x, s2.x), s2.y = fmaf(g.y, xh.y, s2.y);
+        s2.z = fmaf(g.z, xh.z, s2.z), s2.w = fmaf(g.w, xh.w, s2.w);
+        gm = fmax4abs(gm, g), xm = fmax4abs(xm, xh);
+        if (a.cs) {
+          const float4 xs = xsv[u];
+          const float4 xsh = make_float4((xs.x - mus.x) * iss.x, (xs.y - mus.y) * iss.y, (xs.z - mus.z) * iss.z,
+                                         (xs.w - mus.w) * iss.w);
+          s3.x = fmaf(g.x, xsh.x, s3.x), s3.y = fmaf(g.y, xsh.y, s3.y);
+          s3.z = fmaf(g.z, xsh.z, s3.z), s3.w = fmaf(g.w, xsh.w, s3.w);
+          xsm = fmax4abs(xsm, xsh);
+        }
       }
     }
   }
@@ -440,28 +471,46 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(BnBwd a, int nchunks)
   const int M = a.B * a.L;
   const int rows_per = (M + gridDim.y - 1) / gridDim.y;
   const int m_end = min(M, (int)(blockIdx.y + 1) * rows_per);
-  for (int m = blockIdx.y * rows_per + rl; m < m_end; m += 32) {
-    const int b = m / a.L, l = m - b * a.L;
-    const int64_t row = (int64_t)b * (a.L + 2) + 1 + l;
-    float4 g = load_g(a, b, l, col);
-    const float4 o = *reinterpret_cast<const float4*>(a.out + row * a.C + col);
-    g.x *= o.x > 0.f ? 1.f : a.slope, g.y *= o.y > 0.f ? 1.f : a.slope;
-    g.z *= o.z > 0.f ? 1.f : a.slope, g.w *= o.w > 0.f ? 1.f : a.slope;
-    if (a.gres) *reinterpret_cast<float4*>(a.gres + row * a.C + col) = g;
-    {
-      const float4 x = *reinterpret_cast<const float4*>(a.c + row * a.C + col);
-      const int64_t drow = (int64_t)b * (a.Ld + 2) + 1 + (int64_t)a.dil * l;
-      const float4 d = bn_dx(g, x, mu, is, k, m1, m2);
-      if (a.dc) *reinterpret_cast<float4*>(a.dc + drow * a.C + col) = d;
-      if (a.dc_p) store_pair4(a.dc_p, a.dc_ps, drow * a.C + col, make_float4(d.x * sc, d.y * sc, d.z * sc, d.w * sc));
+  constexpr int U = 2;
+  for (int m0 = blockIdx.y * rows_per + rl; m0 < m_end; m0 += 32 * U) {
+    float4 gv[U], ov[U], xv[U], xsv[U];
+    int bb[U], ll[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int m = m0 + 32 * u;
+      if (m < m_end) {
+        const int b = m / a.L, l = m - b * a.L;
+        const int64_t row = (int64_t)b * (a.L + 2) + 1 + l;
+        bb[u] = b, ll[u] = l;
+        gv[u] = load_g(a, b, l, col);
+        ov[u] = *reinterpret_cast<const float4*>(a.out + row * a.C + col);
+        xv[u] = *reinterpret_cast<const float4*>(a.c + row * a.C + col);
+        if (a.cs) xsv[u] = *reinterpret_cast<const float4*>(a.cs + row * a.C + col);
+      }
     }
-    if (a.cs) {
-      const float4 x = *reinterpret_cast<const float4*>(a.cs + row * a.C + col);
-      const int64_t drow = (int64_t)b * (a.Ld_s + 2) + 1 + (int64_t)a.dil_s * l;
-      const float4 d = bn_dx(g, x, mus, iss, ks, m1, m3);
-      if (a.dcs) *reinterpret_cast<float4*>(a.dcs + drow * a.C + col) = d;
-      if (a.dcs_p)
-        store_pair4(a.dcs_p, a.dcs_ps, drow * a.C + col, make_float4(d.x * scs, d.y * scs, d.z * scs, d.w * scs));
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (m0 + 32 * u >= m_end) break;
+      const int b = bb[u], l = ll[u];
+      const int64_t row = (int64_t)b * (a.L + 2) + 1 + l;
+      float4 g = gv[u];
+      const float4 o = ov[u];
+      g.x *= o.x > 0.f ? 1.f : a.slope, g.y *= o.y > 0.f ? 1.f : a.slope;
+      g.z *= o.z > 0.f ? 1.f : a.slope, g.w *= o.w > 0.f ? 1.f : a.slope;
+      if (a.gres) *reinterpret_cast<float4*>(a.gres + row * a.C + col) = g;
+      {
+        const int64_t drow = (int64_t)b * (a.Ld + 2) + 1 + (int64_t)a.dil * l;
+        const float4 d = bn_dx(g, xv[u], mu, is, k, m1, m2);
+        if (a.dc) *reinterpret_cast<float4*>(a.dc + drow * a.C + col) = d;
+        if (a.dc_p) store_pair4(a.dc_p, a.dc_ps, drow * a.C + col, make_float4(d.x * sc, d.y * sc, d.z * sc, d.w * sc));
+      }
+      if (a.cs) {
+        const int64_t drow = (int64_t)b * (a.Ld_s + 2) + 1 + (int64_t)a.dil_s * l;
+        const float4 d = bn_dx(g, xsv[u], mus, iss, ks, m1, m3);
+        if (a.dcs) *reinterpret_cast<float4*>(a.dcs + drow * a.C + col) = d;
+        if (a.dcs_p)
+          store_pair4(a.dcs_p, a.dcs_ps, drow * a.C + col, make_float4(d.x * scs, d.y * scs, d.z * scs, d.w * scs));
+      }
     }
   }
 }

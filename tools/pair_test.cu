@@ -130,6 +130,21 @@ static void test_conv(int B, int L, int Cin, int Cout, int k, int stride, bool b
   }
   const float t1 = time_ms([&] { launch_conv_gemm_simt(g1, 0); }, 20);
   const float t2 = time_ms([&] { launch_conv_pair(g2, ma, mw, bn, B, o, 0); }, 20);
+  if (getenv("PT_STAMPS")) {  // phase stamps of CTA (0, 0) of one isolated launch
+    unsigned long long* ds;
+    CK(cudaMalloc(&ds, 64));
+    CK(cudaMemset(ds, 0, 64));
+    PairOpts o2 = o;
+    o2.stamps = ds;
+    CK(cudaDeviceSynchronize());
+    launch_conv_pair(g2, ma, mw, bn, B, o2, 0);
+    CK(cudaDeviceSynchronize());
+    unsigned long long hs[8];
+    CK(cudaMemcpy(hs, ds, 64, cudaMemcpyDeviceToHost));
+    printf("   stamps ns: prologue %llu | first tile landed %llu | main loop %llu | tmem->smem %llu | stores %llu | stats %llu\n",
+           hs[1] - hs[0], hs[2] - hs[1], hs[3] - hs[2], hs[4] - hs[3], hs[5] - hs[4], hs[6] - hs[5]);
+    cudaFree(ds);
+  }
   const double fl = 2.0 * g.M * g.N * g.K;
   printf("conv  B=%4d L=%3d %3d->%3d k%d s%d bias%d a%d b%d bn%3d | rel err %.2e stats %.1e | simt %7.1f us %6.1f TF | pair %7.1f us %6.1f TF\n",
          B, L, Cin, Cout, k, stride, bias, a_fmt, b_fmt, bn, md / mr, stat_err, t1 * 1e3, fl / t1 / 1e9, t2 * 1e3, fl / t2 / 1e9);
