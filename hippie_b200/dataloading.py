@@ -107,6 +107,17 @@ class EphysTensorDataset(Dataset):
         self.isi = F.interpolate(t.unsqueeze(1), size=(ISI_LEN,), mode="linear")
         self.labels = None if labels is None else torch.as_tensor(np.asarray(labels)).long()
 
+    @classmethod
+    def concat(cls, parts):
+        """torch.utils.data.ConcatDataset over already-transformed tables (their raw widths may differ)."""
+        out = cls.__new__(cls)
+        out.wave = torch.cat([p.wave for p in parts])
+        out.isi = torch.cat([p.isi for p in parts])
+        labelled = [p.labels is not None for p in parts]
+        assert all(labelled) or not any(labelled), "either every table carries labels or none does"
+        out.labels = torch.cat([p.labels for p in parts]) if all(labelled) and parts else None
+        return out
+
     def __len__(self):
         return self.wave.shape[0]
 
@@ -154,3 +165,62 @@ class BalancedBatchSampler(Sampler):
 
     def __len__(self):
         return self.balanced_max * len(self.keys)
+
+
+class EphysBatchLoader:
+    """Whole-batch loader over an `EphysTensorDataset`: the index stream, the batch boundaries and the consumption of
+    torch's default generator are those of `torch.utils.data.DataLoader(dataset, batch_size, shuffle=..., sampler=...)`
+    (one int64 for the iterator's base seed, one more to seed RandomSampler's private generator when shuffling), but a
+    batch is ONE gather from the pre-transformed tensors instead of B `__getitem__` calls + collation -- the reference's
+    per-item path tops out near 20 K items/s, a B200 consumes > 130 K samples/s.
+
+    `indices` restricts the loader to a subset (what `torch.utils.data.Subset(dataset, indices)` does); `rank` / `world`
+    give every data-parallel rank the r-th contiguous slice of each global batch of `world * batch_size` indices
+    (hippie_b200/parallel.py:shard_batch_indices).  With `pin_memory=True` batches are staged in pinned host memory so
+    that the module's `.to(device, non_blocking=True)` copies overlap the previous step."""
+
+    def __init__(self, dataset: "EphysTensorDataset", batch_size: int, shuffle: bool = False, sampler=None,
+                 indices=None, drop_last: bool = False, pin_memory: bool = False, rank: int = 0, world: int = 1):
+        assert not (shuffle and sampler is not None), "sampler option is mutually exclusive with shuffle"
+        self.dataset, self.batch_size, self.shuffle, self.sampler = dataset, int(batch_size), shuffle, sampler
+        self.indices = None if indices is None else [int(i) for i in indices]
+        self.drop_last, self.pin_memory, self.rank, self.world = drop_last, pin_memory, rank, world
+
+    def _n(self) -> int:
+        if self.sampler is not None:
+            return len(self.sampler)
+        return len(self.dataset) if self.indices is None else len(self.indices)
+
+    def __len__(self) -> int:
+        per_step = self.batch_size * self.world
+        n = self._n()
+        return n // per_step if self.drop_last else (n + per_step - 1) // per_step
+
+    def _order(self):
+        torch.empty((), dtype=torch.int64).random_()  # DataLoader: _base_seed of the iterator
+        n = self._n()
+        if self.sampler is not None:
+            order = [int(i) for i in self.sampler]
+        elif self.shuffle:  # RandomSampler without replacement, private generator seeded from the default one
+            seed = int(torch.empty((), dtype=torch.int64).random_().item())
+            g = torch.Generator()
+            g.manual_seed(seed)
+            order = torch.randperm(n, generator=g).tolist()
+        else:
+            order = list(range(n))
+        return order if self.indices is None else [self.indices[i] for i in order]
+
+    def __iter__(self):
+        order = self._order()
+        per_step = self.batch_size * self.world
+        for lo in range(0, len(order), per_step):
+            chunk = order[lo:lo + per_step]
+            if self.drop_last and len(chunk) < per_step:
+                break
+            mine = chunk[self.rank * self.batch_size:(self.rank + 1) * self.batch_size]
+            if not mine:
+                continue
+            batch = self.dataset.batch(mine)
+            if self.pin_memory and torch.cuda.is_available():
+                batch = tuple(t.pin_memory() for t in batch)
+            yield batch

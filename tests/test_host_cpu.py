@@ -191,3 +191,93 @@ def test_data_parallel_exchange_gloo_world2(tmp_path):
                          capture_output=True, text=True, timeout=240)
     assert out.returncode == 0, out.stdout + out.stderr
     assert out.stdout.count("ok") == 2
+
+
+def test_batch_loader_matches_torch_dataloader_bit_exact():
+    """EphysBatchLoader reproduces DataLoader's index stream, batch boundaries and default-generator consumption
+    (shuffle, Subset, sampler), and shards global batches for data-parallel ranks."""
+    from hippie_b200.dataloading import BalancedBatchSampler, EphysBatchLoader, EphysDatasetLabeled, EphysTensorDataset
+    rng = np.random.default_rng(0)
+    wf, isi, lab = rng.normal(size=(37, 47)), np.abs(rng.normal(size=(37, 100))), np.arange(37) % 4
+    ds = EphysDatasetLabeled(wf, isi, lab, mode="both", normalize=False)
+    dt = EphysTensorDataset(wf, isi, lab)
+
+    def same(a, b):
+        return len(a) == len(b) and all(torch.equal(x, y) for p, q in zip(a, b) for x, y in zip(p, q))
+
+    for shuffle in (False, True):
+        torch.manual_seed(3)
+        a = list(torch.utils.data.DataLoader(ds, batch_size=8, shuffle=shuffle))
+        sa = torch.get_rng_state()
+        torch.manual_seed(3)
+        loader = EphysBatchLoader(dt, 8, shuffle=shuffle)
+        b = list(loader)
+        assert same(a, b) and torch.equal(sa, torch.get_rng_state()) and len(loader) == 5
+    idx = [5, 1, 9, 30, 2, 7, 8]
+    torch.manual_seed(4)
+    a = list(torch.utils.data.DataLoader(torch.utils.data.Subset(ds, idx), batch_size=3, shuffle=True))
+    sa = torch.get_rng_state()
+    torch.manual_seed(4)
+    assert same(a, list(EphysBatchLoader(dt, 3, shuffle=True, indices=idx))) and torch.equal(sa, torch.get_rng_state())
+    s1, s2 = BalancedBatchSampler(ds, torch.as_tensor(lab), seed=1), BalancedBatchSampler(dt, torch.as_tensor(lab), seed=1)
+    assert same(list(torch.utils.data.DataLoader(ds, batch_size=6, sampler=s1)), list(EphysBatchLoader(dt, 6, sampler=s2)))
+    # data parallel: the two ranks' batches interleave to the single-process batches of twice the size
+    whole = list(EphysBatchLoader(dt, 8, shuffle=False))
+    r0, r1 = list(EphysBatchLoader(dt, 4, rank=0, world=2)), list(EphysBatchLoader(dt, 4, rank=1, world=2))
+    assert len(r0) == len(whole) and torch.equal(torch.cat([r0[0][0], r1[0][0]]), whole[0][0])
+    assert sum(b[0].shape[0] for b in r0 + r1) == 37
+    cat = EphysTensorDataset.concat([dt, EphysTensorDataset(wf[:5, :40], isi[:5, :51], lab[:5])])
+    assert len(cat) == 42 and cat.wave.shape == (42, 1, 50) and cat.isi.shape == (42, 1, 100)
+
+
+def test_trainer_callbacks_and_limits(tmp_path):
+    from hippie_b200.trainer import EarlyStopping, ModelCheckpoint, _limit
+
+    class FakeTrainer:
+        current_epoch, global_step, should_stop, is_global_zero = 0, 0, False, True
+        log_dir = str(tmp_path)
+        saved = []
+
+        def save_checkpoint(self, path):
+            self.saved.append(path)
+            open(path, "w").write("x")
+
+    tr, ck, es = FakeTrainer(), ModelCheckpoint("val_loss"), EarlyStopping("val_loss", patience=2)
+    for epoch, v in enumerate([3.0, 2.0, 2.5, 2.2, 2.1]):
+        tr.current_epoch, tr.global_step = epoch, 10 * (epoch + 1)
+        for cb in (ck, es):
+            cb.on_validation_end(tr, None, {"val_loss": v})
+        if tr.should_stop:
+            break
+    assert ck.best_model_score == 2.0 and ck.best_model_path.endswith("epoch=1-step=20.ckpt")
+    assert os.path.exists(ck.best_model_path) and not os.path.exists(tr.saved[0])  # top-1: the older file is removed
+    assert tr.should_stop and es.stopped_epoch == 3 and es.wait_count == 2
+    assert _limit(10, None) == 10 and _limit(10, 0.25) == 2 and _limit(10, 3) == 3 and _limit(None, 0.5) is None
+    with pytest.raises(RuntimeError, match="CPU"):
+        from hippie_b200.trainer import Trainer
+        Trainer(accelerator="cpu")
+
+
+def test_cli_flags_match_the_reference():
+    """Every flag of the reference's two CLIs exists with the same default (scripts/train_model_with_multimodal.py:38-69,
+    scripts/inference_from_trained_model.py:15-46)."""
+    import importlib.util
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+    def load(name):
+        spec = importlib.util.spec_from_file_location("cli_" + name, os.path.join(root, "scripts", name + ".py"))
+        mod = importlib.util.module_from_spec(spec)
+        sys.path.insert(0, os.path.join(root, "scripts"))
+        spec.loader.exec_module(mod)
+        return mod
+
+    a = load("train_model_with_multimodal").parse_args([])
+    want = dict(z_dim=5, weight_decay=0.01, learning_rate=0.001, beta=1, dataset="cellexplorer-celltype", upload_model=False,
+                wandb_tag="no_curr_sup_pretrain_data", project="HIPPIE", finetune_without_labels=True, pretrain_max_epochs=1,
+                finetune_max_epochs=1, supervised_max_epochs=1, batch_size=512, supervised_batch_size=64,
+                early_stopping_patience=30, gradient_clip_val=1.0, train_val_split=0.8, finetune_split=0.1,
+                limit_train_batches=None, limit_val_batches=None, model_type="unimodal", mod1_weight=1.0, mod2_weight=1.0)
+    for k, v in want.items():
+        assert getattr(a, k) == v, k
+    b = load("inference_from_trained_model").parse_args(["--wave-checkpoint", "w.ckpt", "--time-checkpoint", "t.ckpt"])
+    assert (b.z_dim, b.dataset, b.output_dir) == (64, "cellexplorer-celltype", "./embeddings")
