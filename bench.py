@@ -250,6 +250,63 @@ def main():
     h2d = BS * (50 + 100) * 4 + BS * 8
     d2h = 4
 
+    # ---- the other two workloads of BASELINE.json (reported beside the headline, same run): the embedding pass
+    # (configs[3]: encoder means of both modalities, sample-sharded, no communication) and the small-batch supervised
+    # step (configs[4]: bs64 with class labels, latency-bound)
+    extra = {}
+    try:
+        from hippie_b200.engine import Engine
+        EB = 4096
+        emb = Engine(Z, 50, 100, 5, 5, 5, True, EB, True).allocate(dev)
+        emb.flat_params.copy_(eng.flat_params), emb.bn_mean.copy_(eng.bn_mean), emb.bn_var.copy_(eng.bn_var)
+        n_eb = n_units // EB
+        out_d = {k: torch.empty(EB, Z, device=dev) for k in ("enc", "mu", "logvar")}
+        out_h = torch.empty(EB, Z).pin_memory()
+
+        def embed_dev(i):
+            j = i % n_eb
+            sl = slice(j * EB, (j + 1) * EB)
+            emb.embed(x1d[sl], x2d[sl], srcd[sl], None, zscore_ddof=0, out=out_d)
+
+        def embed_e2e(i):
+            j = i % n_eb
+            sl = slice(j * EB, (j + 1) * EB)
+            emb.embed(x1p[sl].to(dev, non_blocking=True), x2p[sl].to(dev, non_blocking=True),
+                      srcp[sl].to(dev, non_blocking=True), None, zscore_ddof=0, out=out_d)
+            out_h.copy_(out_d["mu"], non_blocking=True)
+
+        n_e = max(20, args.steps // 4)
+        for i in range(3):
+            embed_dev(i), embed_e2e(i)
+        ms_d, ms_e = timed(embed_dev, n_e), timed(embed_e2e, n_e)
+        extra["embed"] = {"metric": "embed samples/s (encoders + fusion head, eval BatchNorm, z-scored `encoded` + mu)",
+                          "batch": EB, "value": EB * world * n_e / (ms_d * 1e-3), "e2e": EB * world * n_e / (ms_e * 1e-3),
+                          "unit": "samples/s", "h2d_bytes_per_batch": EB * (150 * 4 + 8), "d2h_bytes_per_batch": EB * Z * 4,
+                          "algorithmic_tflops": EB * n_e / (ms_d * 1e-3) * F_EMBED / 1e12}
+        del emb
+        SB = 64
+        cls64 = torch.randint(0, 4, (SB,), device=dev)
+
+        def sup_step(i):
+            sl = slice((i % n_batches) * BS, (i % n_batches) * BS + SB)
+            eng.train_fwd_bwd(x1d[sl], x2d[sl], srcd[sl], cls64, eps_all[i % 64][:SB].contiguous(), 0.5, 1.0, 1.0, scalars=scal)
+            if world > 1:
+                dist.all_reduce(eng.flat_grads)
+            step_no[0] += 1
+            eng.clip_adamw(1e-4, 0.01, step_no[0], max_norm=1.0, grad_scale=inv_world, step_cls=step_no[0], has_cls_grad=True,
+                           scalars=scal)
+
+        state = [t.clone() for t in (eng.flat_params, eng.exp_avg, eng.exp_avg_sq, eng.bn_mean, eng.bn_var)]
+        for i in range(3):
+            sup_step(i)
+        ms_s = timed(sup_step, n_e)
+        for t, v in zip((eng.flat_params, eng.exp_avg, eng.exp_avg_sq, eng.bn_mean, eng.bn_var), state):
+            t.copy_(v)
+        extra["supervised_bs64"] = {"metric": "supervised finetune step (class labels, bs64/GPU)", "ms_per_step": ms_s / n_e,
+                                    "value": SB * world * n_e / (ms_s * 1e-3), "unit": "samples/s"}
+    except Exception as e:  # pragma: no cover
+        extra["error"] = repr(e)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -317,7 +374,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": launches_per_step * args.steps, "gpu_launches_per_step": launches_per_step,
-            "roofline": roofline, "cpu_baseline": cpu, "loss_last": float(scal[0])}
+            "roofline": roofline, "cpu_baseline": cpu, "loss_last": float(scal[0]), "other_workloads": extra}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
