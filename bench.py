@@ -173,11 +173,13 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     from hippie_b200.model import MultiModalCVAE, MultiModalCVAETrainModule
+    from hippie_b200.parallel import train_step_overlapped
 
     torch.manual_seed(42)
     model = MultiModalCVAE(Z, 50, 100, class_hidden_dim=5, num_sources=5, num_classes=5, max_batch=BS)
     module = MultiModalCVAETrainModule(model, learning_rate=1e-3, weight_decay=0.01, beta=0.5)
     module.to(dev)
+    module.world_size = world
     eng = model.engine
     if args.conv_path:
         raise SystemExit("--conv-path is set at engine creation; use HIPPIE_CONV_PATH")
@@ -195,9 +197,10 @@ def main():
     def dev_step(i):
         j = i % n_batches
         sl = slice(j * BS, (j + 1) * BS)
-        eng.train_fwd_bwd(x1d[sl], x2d[sl], srcd[sl], None, eps_all[i % 64], 0.5, 1.0, 1.0, scalars=scal)
-        if world > 1:
-            dist.all_reduce(eng.flat_grads)
+        if world > 1:  # all-reduce of the decoder + head gradients overlaps the encoders' backward pass
+            train_step_overlapped(eng, x1d[sl], x2d[sl], srcd[sl], None, eps_all[i % 64], 0.5, 1.0, 1.0, scalars=scal)
+        else:
+            eng.train_fwd_bwd(x1d[sl], x2d[sl], srcd[sl], None, eps_all[i % 64], 0.5, 1.0, 1.0, scalars=scal)
         step_no[0] += 1
         eng.clip_adamw(1e-3, 0.01, step_no[0], max_norm=1.0, grad_scale=inv_world, scalars=scal)
 
@@ -237,10 +240,8 @@ def main():
         j = i % n_batches
         sl = slice(j * BS, (j + 1) * BS)
         batch = (x1p[sl].to(dev, non_blocking=True), x2p[sl].to(dev, non_blocking=True), srcp[sl].to(dev, non_blocking=True))
-        loss = module.training_step(batch, i)
-        if world > 1:
-            dist.all_reduce(eng.flat_grads)
-        module.optimizer.step(max_norm=1.0, grad_scale=inv_world)
+        loss = module.training_step(batch, i)  # data parallel: the module all-reduces the gradients (overlapped)
+        module.optimizer.step(max_norm=1.0, grad_scale=module.grad_scale)
         return float(loss)  # D2H read of the step's loss (what the reference's .item() does, hippie/model.py:480)
 
     for i in range(3):

@@ -57,6 +57,9 @@ SIGNATURES = {
     "hippie_bind": (C.c_int, [_H, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, _i64p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "hippie_train_fwd_bwd": (C.c_int, [_H, _f32p, _f32p, _i64p, _i64p, _f32p, C.c_int32, C.c_float, C.c_float,
                                        C.c_float, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, C.c_void_p]),
+    "hippie_train_fwd_bwd_part": (C.c_int, [_H, _f32p, _f32p, _i64p, _i64p, _f32p, C.c_int32, C.c_float, C.c_float,
+                                            C.c_float, _f32p, C.c_int32, C.c_void_p]),
+    "hippie_grad_split": (C.c_int64, [_H]),
     "hippie_eval_forward": (C.c_int, [_H, _f32p, _f32p, _i64p, _i64p, _f32p, C.c_int32, C.c_float, C.c_float,
                                       C.c_float, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, C.c_void_p]),
     "hippie_train_forward": (C.c_int, [_H, _f32p, _f32p, _i64p, _i64p, _f32p, C.c_int32, C.c_float, C.c_float,

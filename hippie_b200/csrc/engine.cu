@@ -111,6 +111,7 @@ struct hippie_engine {
   std::vector<Act> acts;
   std::map<int, int> gact;  // activation index -> gradient tensor index
   int64_t param_floats = 0, bn_floats = 0, ws_floats = 0;
+  int64_t grad_split = 0;  // first parameter offset that does not belong to an encoder backbone
   int n_enc = 0, n_dec = 0;
   Encoder enc[2];
   Decoder dec[2];
@@ -137,7 +138,7 @@ struct hippie_engine {
   bool failed = false;  // a tensor-map encode failed while launching (reported by the entry point)
   // ---- CUDA graphs: one instantiated graph per call signature, replayed from staged inputs ----------------
   struct CallArgs {
-    int mode;  // 0 train_fwd_bwd, 1 train_forward, 2 eval_forward, 3 embed
+    int mode;  // 0 train_fwd_bwd, 1 train_forward, 2 eval_forward, 3 embed, 4 / 5 = parts 0 / 1 of a split train_fwd_bwd
     const float *x1, *x2;
     const int64_t *src, *cls;
     const float* eps;
@@ -495,6 +496,7 @@ struct hippie_engine {
     memset(&H, 0xff, sizeof(H));  // all -1
     const std::string f = cfg.multimodal ? "fusion_encoder" : "encoder_fc";
     H.f0_w = off_of(f + ".0.weight"), H.f0_b = off_of(f + ".0.bias");
+    grad_split = H.f0_w;
     H.fbn_g = off_of(f + ".1.weight"), H.fbn_b = off_of(f + ".1.bias");
     H.f3_w = off_of(f + ".3.weight"), H.f3_b = off_of(f + ".3.bias");
     H.fbn_run = bns[bidx.at(f + ".1")].run_off, H.fbn_cnt = bidx.at(f + ".1");
@@ -874,11 +876,16 @@ struct hippie_engine {
   // full forward (+ loss, + backward when train)
   int run(bool train, bool backward, const float* x1, const float* x2, const int64_t* src, const int64_t* cls,
           const float* eps, int B, float beta, float w1, float w2, float* scalars_out, float* out_enc, float* out_mu,
-          float* out_logvar, float* out_dec1, float* out_dec2, cudaStream_t main) {
+          float* out_logvar, float* out_dec1, float* out_dec2, cudaStream_t main, int part = -1) {
     launches = 0;
     Branch b0{main, ws + part_off[0], ws + bpart_off[0]}, b1{profiling ? main : side, ws + part_off[1], ws + bpart_off[1]};
     if (backward && !profiling) b0.wst = wside[0], b1.wst = wside[1];
     const float* xin[2] = {x1, x2};
+    if (part == 1) {  // second part of a split step: the encoders' backward pass only
+      encoders_bwd(xin, B, b0, b1, main);
+      if (failed) return fail(-9, err);
+      return check("train_fwd_bwd (part 1)");
+    }
     float* dec_out[2] = {out_dec1, out_dec2};
     const float lw[2] = {cfg.multimodal ? w1 : 1.f, w2};
     cudaMemsetAsync(ws + scal_off, 0, 64 * sizeof(float), main);
@@ -922,21 +929,31 @@ struct hippie_engine {
       launch_head_bwd(ha, main);
       prof_end(pe6, 6, 0.0, b0);
       ++launches;
-      if (two) fork(main);
-      encoder_bwd(enc[0], xin[0], B, b0);
-      if (two) {
-        encoder_bwd(enc[1], xin[1], B, b1);
-        join(main);
-      }
-      for (int i = 0; i < 2; ++i)
-        if (!profiling) {  // the weight-gradient streams rejoin the caller's stream
-          cudaEvent_t e = next_event();
-          cudaEventRecord(e, wside[i]);
-          cudaStreamWaitEvent(main, e, 0);
-        }
+      if (part == 0)
+        join_wgrad(main);  // decoder + head gradients are final when part 0 completes
+      else
+        encoders_bwd(xin, B, b0, b1, main);
     }
     if (failed) return fail(-9, err);
     return check(train ? "train_fwd_bwd" : "eval_forward");
+  }
+  void join_wgrad(cudaStream_t main) {  // the weight-gradient streams rejoin the caller's stream
+    if (profiling) return;
+    for (int i = 0; i < 2; ++i) {
+      cudaEvent_t e = next_event();
+      cudaEventRecord(e, wside[i]);
+      cudaStreamWaitEvent(main, e, 0);
+    }
+  }
+  void encoders_bwd(const float* const* xin, int B, Branch& b0, Branch& b1, cudaStream_t main) {
+    const bool two = n_enc == 2;
+    if (two) fork(main);
+    encoder_bwd(enc[0], xin[0], B, b0);
+    if (two) {
+      encoder_bwd(enc[1], xin[1], B, b1);
+      join(main);
+    }
+    join_wgrad(main);
   }
 
   // encoders + latent head only, eval-mode BatchNorm (get_embeddings_multimodal, scripts/...:22-34)
@@ -965,8 +982,9 @@ struct hippie_engine {
 
   int exec(const CallArgs& a, cudaStream_t main) {
     if (a.mode == 3) return run_embed(a.x1, a.x2, a.src, a.cls, a.B, a.zscore, a.enc, a.mu, a.lv, main);
-    return run(a.mode != 2, a.mode == 0, a.x1, a.x2, a.src, a.cls, a.eps, a.B, a.beta, a.w1, a.w2, a.scalars, a.enc, a.mu,
-               a.lv, a.d1, a.d2, main);
+    const bool backward = a.mode == 0 || a.mode >= 4;
+    return run(a.mode != 2, backward, a.x1, a.x2, a.src, a.cls, a.eps, a.B, a.beta, a.w1, a.w2, a.scalars, a.enc, a.mu, a.lv,
+               a.d1, a.d2, main, a.mode >= 4 ? a.mode - 4 : -1);
   }
 
   // Graph-aware dispatch.  Inputs are copied into fixed staging buffers (one launch), the captured launch sequence is
@@ -1165,6 +1183,22 @@ int hippie_train_fwd_bwd(hippie_handle h, const float* x1, const float* x2, cons
   hippie_engine::CallArgs a{0, x1, x2, src, cls, eps, B, beta, w1, w2, -1, scalars_out, out_enc, out_mu, out_logvar, out_dec1, out_dec2};
   return h->call(a, (cudaStream_t)stream);
 }
+
+int hippie_train_fwd_bwd_part(hippie_handle h, const float* x1, const float* x2, const int64_t* src, const int64_t* cls,
+                              const float* eps, int32_t B, float beta, float w1, float w2, float* scalars_out,
+                              int32_t part, void* stream) {
+  if (!h) return -1;
+  if (int rc = h->validate(B, x1, x2, src)) return rc;
+  if (h->cfg.inference_only) return h->fail(-7, "inference-only engine");
+  if (part != 0 && part != 1) return h->fail(-3, "part must be 0 or 1");
+  if (!eps) return h->fail(-4, "eps is required for training (reparameterisation noise)");
+  if (B < 2) return h->fail(-3, "training-mode BatchNorm needs B >= 2");
+  hippie_engine::CallArgs a{4 + part, x1, x2, src, cls, eps, B, beta, w1, w2, -1, part == 0 ? scalars_out : nullptr,
+                            nullptr, nullptr, nullptr, nullptr, nullptr};
+  return h->call(a, (cudaStream_t)stream);
+}
+
+int64_t hippie_grad_split(hippie_handle h) { return h ? h->grad_split : -1; }
 
 int hippie_eval_forward(hippie_handle h, const float* x1, const float* x2, const int64_t* src, const int64_t* cls,
                         const float* eps, int32_t B, float beta, float w1, float w2, float* scalars_out, float* out_enc,

@@ -180,6 +180,22 @@ class Engine:
             _ptr(outs.get("dec2")), self._stream()))
         return scalars, (outs if outputs else None)
 
+    def train_fwd_bwd_part(self, part: int, x1, x2, src, cls, eps, beta: float, w1: float = 1.0, w2: float = 1.0,
+                           scalars=None):
+        """Part 0 (forward, loss, decoder + head backward) or part 1 (encoder backward) of the train step; after part 0
+        `flat_grads[grad_split:]` is final, after part 1 `flat_grads[:grad_split]` (hippie_train_fwd_bwd_part)."""
+        B = x1.shape[0]
+        self._io(x1, x2, src, cls, eps, B)
+        if scalars is None and part == 0:
+            scalars = torch.zeros(8, dtype=torch.float32, device=self.device)
+        self._check(self._L.hippie_train_fwd_bwd_part(self._h, _ptr(x1), _ptr(x2), _ptr(src), _ptr(cls), _ptr(eps), B, beta,
+                                                      w1, w2, _ptr(scalars), part, self._stream()))
+        return scalars
+
+    @property
+    def grad_split(self) -> int:
+        return int(self._L.hippie_grad_split(self._h))
+
     def train_forward(self, x1, x2, src, cls, eps, beta: float = 1.0, w1: float = 1.0, w2: float = 1.0, scalars=None):
         return self.eval_forward(x1, x2, src, cls, eps, beta, w1, w2, scalars, _fn="hippie_train_forward")
 

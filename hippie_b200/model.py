@@ -17,6 +17,7 @@ import torch
 import torch.nn as nn
 
 from .engine import Engine, LAYOUT_CONV_OKI
+from .parallel import train_step_overlapped
 
 
 class _Node(nn.Module):
@@ -325,6 +326,7 @@ class _TrainModuleBase(nn.Module):
         self._ring = None
         self._ring_pos = 0
         self.world_size = 1  # set by the data-parallel trainer
+        self.grad_scale = 1.0  # factor the optimizer applies to the (summed) gradients: 1 / world after an all-reduce
 
     def log(self, name, value, *a, **k):
         self.logged[name] = value
@@ -392,8 +394,9 @@ class MultiModalCVAETrainModule(_TrainModuleBase):
         if eps is None:
             eps = m._draw_eps(x1.shape[0])
         s = self._scalars()
-        m.engine.train_fwd_bwd(x1, x2, src, cls, eps, float(self.beta), float(self.mod1_weight),
-                               float(self.mod2_weight), scalars=s)
+        # data parallel: the gradient all-reduce is issued from here so that it overlaps the encoders' backward pass
+        self.grad_scale = train_step_overlapped(m.engine, x1, x2, src, cls, eps, float(self.beta), float(self.mod1_weight),
+                                                float(self.mod2_weight), scalars=s)
         self.optimizer.has_cls_grad = cls is not None
         self.log("train_loss", s[0]), self.log("train_mse_loss1", s[1])
         self.log("train_mse_loss2", s[2]), self.log("train_kl_loss", s[3])
@@ -443,7 +446,7 @@ class hippieUnimodalEmbeddingModelCVAE(_TrainModuleBase):
             eps = m._draw_eps(x.shape[0])
         s = self._scalars()
         if train:
-            m.engine.train_fwd_bwd(x, None, src, cls, eps, float(self.beta), 1.0, 1.0, scalars=s)
+            self.grad_scale = train_step_overlapped(m.engine, x, None, src, cls, eps, float(self.beta), 1.0, 1.0, scalars=s)
             self.optimizer.has_cls_grad = cls is not None
         else:
             m.engine.eval_forward(x, None, src, cls, eps, float(self.beta), 1.0, 1.0, scalars=s)

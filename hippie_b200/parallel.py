@@ -44,3 +44,20 @@ def broadcast_state(tensors: Sequence[torch.Tensor], src: int = 0, group=None):
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         for t in tensors:
             dist.broadcast(t, src=src, group=group)
+
+
+def train_step_overlapped(engine, x1, x2, src, cls, eps, beta, w1=1.0, w2=1.0, scalars=None, group=None) -> float:
+    """One data-parallel forward + backward with the gradient exchange overlapped with the backward pass: the all-reduce
+    of the latent-head + decoder gradients (52 % of the buffer, final after part 0) runs on NCCL's stream while the
+    encoders' backward pass (part 1) executes; the encoder gradients follow.  Returns the factor for the optimizer
+    (1/world).  Without an initialised process group this is a plain train_fwd_bwd."""
+    if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
+        engine.train_fwd_bwd(x1, x2, src, cls, eps, beta, w1, w2, scalars=scalars)
+        return 1.0
+    split = engine.grad_split
+    engine.train_fwd_bwd_part(0, x1, x2, src, cls, eps, beta, w1, w2, scalars=scalars)
+    tail = dist.all_reduce(engine.flat_grads[split:], op=dist.ReduceOp.SUM, group=group, async_op=True)
+    engine.train_fwd_bwd_part(1, x1, x2, src, cls, eps, beta, w1, w2)
+    head = dist.all_reduce(engine.flat_grads[:split], op=dist.ReduceOp.SUM, group=group, async_op=True)
+    tail.wait(), head.wait()
+    return 1.0 / dist.get_world_size(group)

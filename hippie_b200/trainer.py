@@ -12,7 +12,8 @@ per batch | on_validation_epoch_end -> epoch-mean `val_loss` -> ModelCheckpoint 
 training loop synchronises with the host: losses stay on the device until the epoch mean is taken.
 
 Data parallel: when `torch.distributed` is initialised every rank runs this loop on its own shard of the batches; the
-flat gradient buffer is all-reduced between `training_step` and the optimizer (hippie_b200/parallel.py), the epoch-mean
+flat gradient buffer is all-reduced inside `training_step`, overlapped with the encoders' backward pass
+(hippie_b200/parallel.py:train_step_overlapped), the epoch-mean
 validation loss is averaged over the ranks and rank 0 writes the checkpoints.
 """
 from __future__ import annotations
@@ -22,8 +23,6 @@ from typing import Iterable, Optional, Sequence
 
 import torch
 import torch.distributed as dist
-
-from .parallel import all_reduce_gradients
 
 CKPT_VERSION = "2.0.0+hippie_b200"  # value of the "pytorch-lightning_version" key (layout of Lightning >= 1.6)
 
@@ -195,9 +194,8 @@ class Trainer:
             for i, batch in enumerate(train_dataloaders):
                 if max_train is not None and i >= max_train:
                     break
-                module.training_step(batch, i)
-                scale = all_reduce_gradients(module.model.engine.flat_grads) if self.world_size > 1 else 1.0
-                module.optimizer.step(max_norm=clip, grad_scale=scale)
+                module.training_step(batch, i)  # data parallel: all-reduces the gradients itself (overlapped)
+                module.optimizer.step(max_norm=clip, grad_scale=module.grad_scale)
                 self.global_step += 1
                 if self.logger is not None and self.global_step % self.log_every_n_steps == 0 and self.is_global_zero:
                     self.logger.log_metrics({k: float(v) for k, v in module.logged.items()}, step=self.global_step)

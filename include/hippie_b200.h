@@ -106,6 +106,17 @@ int hippie_train_fwd_bwd(hippie_handle h, const float* x1, const float* x2, cons
                          float* out_enc, float* out_mu, float* out_logvar, float* out_dec1, float* out_dec2,
                          void* stream);
 
+/* The same step in two stream-ordered parts, for data-parallel callers that overlap the gradient exchange with the
+ * backward pass (reference: Lightning's implicit DDP does the same with its gradient buckets):
+ *   part 0 = forward + loss + decoder backward + latent-head backward; when it completes, grads[hippie_grad_split(h) ..
+ *            hippie_param_floats(h)) are final (latent head + both decoders, 52 % of the parameters);
+ *   part 1 = encoder backward; afterwards grads[0 .. hippie_grad_split(h)) are final.
+ * Calling part 0 then part 1 with the same arguments is equivalent to hippie_train_fwd_bwd. */
+int hippie_train_fwd_bwd_part(hippie_handle h, const float* x1, const float* x2, const int64_t* src, const int64_t* cls,
+                              const float* eps, int32_t B, float beta, float w1, float w2, float* scalars_out,
+                              int32_t part, void* stream);
+int64_t hippie_grad_split(hippie_handle h);
+
 /* Replaces Lightning's gradient_clip_val (scripts/train_model_with_multimodal.py:55,701 ->
  * torch.nn.utils.clip_grad_norm_) followed by torch.optim.AdamW.step (hippie/model.py:447).
  *   grad_scale multiplies every gradient first (1/world after a summing all-reduce);

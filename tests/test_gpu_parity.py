@@ -199,3 +199,31 @@ def test_properties_at_benchmark_size_bs512():
         assert torch.equal(whole[k], torch.cat([h[k] for h in halves])), k
     z = eng.embed(x1, x2, src, zscore_ddof=0)["enc"]
     assert z.mean(dim=1).abs().max().item() <= 1e-5 and (z.var(dim=1, unbiased=False) - 1).abs().max().item() <= 1e-4
+
+
+def test_split_step_equals_whole_step():
+    """hippie_train_fwd_bwd_part(0) + (1) == hippie_train_fwd_bwd: same loss scalars bit for bit, same gradients up to the
+    order of the weight-gradient atomics, and the documented halves of the gradient buffer are final after each part."""
+    cfg = O.CVAEConfig(z_dim=10)
+    B = 96
+    eng = U.make_engine(cfg, B)
+    st = O.init_state(cfg, seed=42)
+    dev = eng.device
+    x1, x2, labels, eps = U.case_inputs(cfg, B, False, seed=5)
+    x1, x2, src, eps = x1.to(dev), x2.to(dev), labels.to(dev), eps.to(dev)
+    for _ in range(3):  # eager call, graph capture, graph replay
+        eng.load_named(st)
+        s_whole, _ = eng.train_fwd_bwd(x1, x2, src, None, eps, 0.5, 1.0, 1.0)
+        g_whole = eng.flat_grads.clone()
+        eng.load_named(st)
+        s0 = eng.train_fwd_bwd_part(0, x1, x2, src, None, eps, 0.5, 1.0, 1.0)
+        split = eng.grad_split
+        tail = eng.flat_grads[split:].clone()
+        assert eng.flat_grads[:split].abs().max().item() == 0.0  # encoder gradients untouched so far
+        eng.train_fwd_bwd_part(1, x1, x2, src, None, eps, 0.5, 1.0, 1.0)
+        assert torch.equal(s_whole[:4], s0[:4])
+        assert torch.equal(eng.flat_grads[split:], tail)  # part 1 does not touch the decoder / head gradients
+        rel = ((eng.flat_grads - g_whole).norm() / g_whole.norm()).item()
+        assert rel <= 1e-5, rel
+    assert 0 < split < eng.param_floats
+    assert eng.params[[p.offset for p in eng.params].index(split)].name == "fusion_encoder.0.weight"
