@@ -24,14 +24,6 @@ class _Node(nn.Module):
     """Anonymous container used to reproduce the reference's module tree (and hence its state_dict keys)."""
 
 
-def _init_like_reference(p, flat_cpu: torch.Tensor):
-    """torch's default initialisers in the reference's construction order (== engine param order), drawn on the
-    CPU generator exactly like nn.Conv1d / nn.Linear / nn.Embedding / nn.BatchNorm1d do, so that after
-    `torch.manual_seed(s)` the values equal the reference model's bit for bit (scripts/
-    train_model_with_multimodal.py:78,663).  Returns nothing; writes into the flat buffer."""
-    raise NotImplementedError
-
-
 class _EngineModule(nn.Module):
     """Base of MultiModalCVAE / hippieUnimodalCVAE: owns the Engine and the flat buffers."""
 

@@ -227,3 +227,50 @@ def test_split_step_equals_whole_step():
         assert rel <= 1e-5, rel
     assert 0 < split < eng.param_floats
     assert eng.params[[p.offset for p in eng.params].index(split)].name == "fusion_encoder.0.weight"
+
+
+def test_fp32_cuda_core_path_is_the_yardstick():
+    """conv_path = 1 (FP32 CUDA-core implicit GEMMs, no pair planes) passes the same parity gate, and the tensor-core
+    path agrees with it on the forward to fp32 rounding level."""
+    cfg, B, lab = CASES["mm_z10_b48"]
+    res1, eng1 = U.run_train_case(cfg, B, lab, conv_path=1)
+    assert eng1.conv_path_in_use() == 1
+    _check_train(res1)
+    res0, eng0 = U.run_train_case(cfg, B, lab, conv_path=0)
+    assert eng0.conv_path_in_use() == 2
+    for a, b in zip(res0["loss_rel"], res1["loss_rel"]):
+        assert abs(a - b) <= 2e-6
+
+
+def test_free_running_steps_stay_inside_the_reference_envelope():
+    """Six consecutive optimisation steps WITHOUT teacher forcing.  The reference itself is chaotic after step 0: its own
+    fp32 and fp64 runs drift apart by 1e-4 .. 1e-2 relative within a few steps (Adam's first updates
+    are ~lr * sign(g), so rounding-level gradient differences flip updates).  The engine's loss curve therefore has to
+    stay within a small multiple of the reference's OWN fp32-vs-fp64 spread, measured in the same test."""
+    cfg = O.CVAEConfig(z_dim=10)
+    B, steps = 256, 6
+    eng = U.make_engine(cfg, B)
+    st32 = O.init_state(cfg, seed=42)
+    st64 = U.to_dtype(st32, torch.float64)
+    eng.load_named(st32)
+    dev = eng.device
+    x1, x2, labels, g = O.synthetic_batch(B * steps, seed=321)
+    eps = torch.randn(steps, B, cfg.z_dim, generator=g)
+    opt32, opt64 = O.new_opt_state(st32, cfg), O.new_opt_state(st64, cfg)
+    ref32, ref64, got = [], [], []
+    kw = dict(lr=1e-3, weight_decay=0.01, beta=0.5, max_norm=1.0)
+    for i in range(steps):
+        sl = slice(i * B, (i + 1) * B)
+        st32, opt32, info = O.train_step(st32, opt32, cfg, x1[sl], x2[sl], labels[sl], eps[i], **kw)
+        ref32.append(float(info["loss"]))
+        st64, opt64, info = O.train_step(st64, opt64, cfg, x1[sl].double(), x2[sl].double(), labels[sl], eps[i].double(), **kw)
+        ref64.append(float(info["loss"]))
+        s, _ = eng.train_fwd_bwd(x1[sl].to(dev), x2[sl].to(dev), labels[sl].to(dev), None, eps[i].to(dev), 0.5)
+        eng.clip_adamw(1e-3, 0.01, i + 1, max_norm=1.0)
+        got.append(float(s[0]))
+    assert abs(got[0] - ref64[0]) <= 1e-5 * abs(ref64[0])  # step 0 starts from identical state
+    spread = 0.0
+    for a, r32, r64 in zip(got, ref32, ref64):
+        spread = max(spread, abs(r32 - r64) / abs(r64))
+        assert abs(a - r64) / abs(r64) <= 4.0 * spread + 1e-3, (got, ref32, ref64)
+    assert got[-1] < got[0]

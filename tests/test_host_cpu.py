@@ -165,7 +165,7 @@ def test_shard_helpers():
 _GLOO_WORKER = r'''
 import os, sys, torch, torch.distributed as dist
 sys.path.insert(0, sys.argv[1])
-from hippie_b200.parallel import all_reduce_gradients, broadcast_state, shard_batch_indices
+from hippie_b200.parallel import all_reduce_gradients, broadcast_state, shard_batch_indices, train_step_overlapped
 dist.init_process_group("gloo")
 r, w = dist.get_rank(), dist.get_world_size()
 g = torch.arange(12, dtype=torch.float32) * (r + 1)
@@ -178,6 +178,25 @@ mine = shard_batch_indices(list(range(10)), 0, r, w, 3)
 allv = [None, None]
 dist.all_gather_object(allv, mine)
 assert allv == [[0, 1, 2], [3, 4, 5]]
+
+class StubEngine:  # the host logic of the overlapped exchange, without a GPU: part 0 fills the tail, part 1 the head
+    grad_split = 5
+    def __init__(self, rank):
+        self.flat_grads = torch.zeros(12)
+        self.rank, self.calls = rank, []
+    def train_fwd_bwd_part(self, part, *a, **k):
+        self.calls.append(part)
+        if part == 0:
+            self.flat_grads.zero_()
+            self.flat_grads[self.grad_split:] = torch.arange(7, dtype=torch.float32) + 10 * self.rank
+        else:
+            self.flat_grads[:self.grad_split] += torch.arange(5, dtype=torch.float32) * (self.rank + 1)
+        return None
+eng = StubEngine(r)
+scale = train_step_overlapped(eng, None, None, None, None, None, 0.5)
+assert scale == 0.5 and eng.calls == [0, 1]
+assert torch.equal(eng.flat_grads[5:], 2 * torch.arange(7, dtype=torch.float32) + 10), eng.flat_grads
+assert torch.equal(eng.flat_grads[:5], 3 * torch.arange(5, dtype=torch.float32)), eng.flat_grads
 dist.destroy_process_group()
 print("ok", r)
 '''

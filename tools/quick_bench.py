@@ -34,7 +34,7 @@ e1.record()
 torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / steps
 print(f"train B={B}: {ms:.3f} ms/step  {B / ms * 1e3:.0f} samples/s  (host wall {1e3 * (time.time() - t0) / steps:.3f} ms/step)  loss {scal[0].item():.5f} gnorm {scal[4].item():.4f}")
-print("launches fwd+bwd", 602, "TFLOP/s (algorithmic 689.76 MFLOP/sample): %.2f" % (B * 689.76456e6 / (ms * 1e-3) / 1e12))
+print("launches per step", eng.last_launch_count() + 3, " TFLOP/s (algorithmic 689.76 MFLOP/sample): %.2f" % (B * 689.76456e6 / (ms * 1e-3) / 1e12))
 for i in range(3):
     eng.embed(x1, x2, src, None)
 torch.cuda.synchronize()
