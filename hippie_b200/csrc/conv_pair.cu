@@ -468,22 +468,23 @@ bool encode(TcMap* out, int fmt, int rank, const void* base, const cuuint64_t* d
 }  // namespace
 
 bool pair_init(std::string* err) {
-  if (g_enc) return true;
-  void* fn = nullptr;
-  cudaDriverEntryPointQueryResult qres;
-  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
-  if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) {
-    if (err) *err = "cuTensorMapEncodeTiled is not available from the driver";
-    return false;
+  if (!g_enc) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) {
+      if (err) *err = "cuTensorMapEncodeTiled is not available from the driver";
+      return false;
+    }
+    g_enc = reinterpret_cast<EncodeTiledFn>(fn);
   }
-  g_enc = reinterpret_cast<EncodeTiledFn>(fn);
+  // function attributes belong to the current device's context: set them on every bind
   cudaFuncSetAttribute(conv_pair_kernel<kBN, kStages>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                        PairSmem<kBN, kStages>::TOTAL);
   cudaFuncSetAttribute(wgrad_pair_kernel<kBN, kStages>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                        PairSmem<kBN, kStages>::TOTAL);
   if (cudaGetLastError() != cudaSuccess) {
     if (err) *err = "cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed";
-    g_enc = nullptr;
     return false;
   }
   return true;

@@ -161,6 +161,7 @@ struct hippie_engine {
   };
   std::map<GraphKey, GraphEntry> graphs;
   bool use_graphs = true;
+  static constexpr size_t kMaxGraphs = 32;  // distinct call signatures kept as instantiated graphs
   cudaStream_t cap = nullptr;  // capture stream (the caller's stream may be the legacy default stream)
   int64_t st_x1 = 0, st_x2 = 0, st_src = 0, st_cls = 0, st_eps = 0, st_scal = 0, st_enc = 0, st_mu = 0, st_lv = 0,
           st_d1 = 0, st_d2 = 0;
@@ -999,6 +1000,7 @@ struct hippie_engine {
     key.mode = a.mode, key.B = a.B, key.zscore = a.zscore, key.beta = a.beta, key.w1 = a.w1, key.w2 = a.w2;
     key.flags = (a.cls ? 1 : 0) | (a.eps ? 2 : 0) | (a.scalars ? 4 : 0) | (a.enc ? 8 : 0) | (a.mu ? 16 : 0) |
                 (a.lv ? 32 : 0) | (a.d1 ? 64 : 0) | (a.d2 ? 128 : 0);
+    if (graphs.size() >= kMaxGraphs && !graphs.count(key)) return exec(a, main);  // e.g. a beta schedule: stay eager
     GraphEntry& e = graphs[key];
     if (e.seen <= 0) {
       if (e.seen == 0) e.seen = 1;
