@@ -67,6 +67,8 @@ SIGNATURES = {
     "hippie_embed": (C.c_int, [_H, _f32p, _f32p, _i64p, _i64p, C.c_int32, C.c_int32, _f32p, _f32p, _f32p, C.c_void_p]),
     "hippie_clip_adamw": (C.c_int, [_H, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
                                     C.c_int32, C.c_int32, C.c_int32, _f32p, C.c_void_p]),
+    "hippie_preprocess_batch": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, _i64p, C.c_int32, _f32p, C.c_int32,
+                                          _f32p, C.c_int32, C.c_void_p]),
     "hippie_last_launch_count": (C.c_int, [_H]),
     "hippie_conv_path_in_use": (C.c_int, [_H]),
     "hippie_profile": (C.c_int, [_H, C.c_int]),

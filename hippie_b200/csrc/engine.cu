@@ -1248,6 +1248,18 @@ int hippie_clip_adamw(hippie_handle h, float lr, float beta1, float beta2, float
   return h->check("hippie_clip_adamw");
 }
 
+int hippie_preprocess_batch(const double* wave_raw, int32_t wave_width, const double* isi_raw, int32_t isi_width,
+                            const int64_t* index, int32_t B, float* x1, int32_t len_wave, float* x2, int32_t len_isi,
+                            void* stream) {
+  if (B == 0) return 0;
+  if (B < 0 || (wave_raw && (!x1 || wave_width < 1 || len_wave < 1)) || (isi_raw && (!x2 || isi_width < 1 || len_isi < 1)))
+    return -1;
+  if (wave_raw) launch_preprocess(wave_raw, wave_width, index, B, len_wave, 0, x1, (cudaStream_t)stream);
+  if (isi_raw) launch_preprocess(isi_raw, isi_width, index, B, len_isi, 1, x2, (cudaStream_t)stream);
+  cudaError_t ce = cudaGetLastError();
+  return ce == cudaSuccess ? 0 : (int)ce;
+}
+
 int hippie_last_launch_count(hippie_handle h) { return h ? h->launches : -1; }
 
 int hippie_conv_path_in_use(hippie_handle h) { return h ? (h->use_tc ? 2 : 1) : -1; }

@@ -279,6 +279,10 @@ struct AdamArgs {
 void launch_clip_adamw(const AdamArgs& a, cudaStream_t s);
 constexpr int kClipAdamLaunches = 3;
 
+// rows index[b] (null: b) of a raw float64 table -> [B][size] float32: cast, optional log(x + 1), linear interpolation
+void launch_preprocess(const double* raw, int width, const int64_t* index, int B, int size, int take_log, float* out,
+                       cudaStream_t s);
+
 // up to 8 segment copies of 4-byte words in one launch (input staging / output delivery around a graph replay)
 struct IoSeg {
   const void* src;

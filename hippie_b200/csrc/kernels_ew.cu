@@ -891,6 +891,30 @@ __global__ void __launch_bounds__(256) adamw_kernel(AdamArgs a, float decay, flo
 }
 
 // wt[ci][k-1-t][co] = w[co][t][ci]
+// ------------------------------------------------------------------------------------------------
+// Batch preprocessing (EphysDataset.__getitem__, reference hippie/dataloading.py:27-56): rows index[b] of a raw float64
+// table -> float32, optional log(x + 1), linear interpolation with align_corners=False exactly as ATen's CPU kernel
+// evaluates it (oracle/cvae_oracle.py:interp_linear):  scale = fp32(n) / size;  src = max(fma(scale, i + 0.5, -0.5), 0);
+// i0 = min(floor(src), n - 1);  i1 = min(i0 + 1, n - 1);  w1 = src - i0;  w0 = 1 - w1;  out = fma(x[i0], w0, x[i1] * w1).
+// The waveform path is bit-exact; log() is the correctly rounded float of the double logarithm, which differs from
+// ATen's vectorised logf by one ulp for ~0.3 % of the values.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) preprocess_kernel(const double* __restrict__ raw, int width,
+                                                         const int64_t* __restrict__ index, int B, int size, int take_log,
+                                                         float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * size) return;
+  const int b = i / size, j = i - b * size;
+  const double* row = raw + (index ? index[b] : (int64_t)b) * width;
+  const float scale = __fdiv_rn((float)width, (float)size);
+  const float src = fmaxf(__fmaf_rn(scale, (float)j + 0.5f, -0.5f), 0.f);
+  const int i0 = min((int)floorf(src), width - 1), i1 = min(i0 + 1, width - 1);
+  const float w1 = fminf(fmaxf(__fsub_rn(src, (float)i0), 0.f), 1.f), w0 = __fsub_rn(1.f, w1);
+  float x0 = (float)row[i0], x1 = (float)row[i1];
+  if (take_log) x0 = (float)log((double)__fadd_rn(x0, 1.f)), x1 = (float)log((double)__fadd_rn(x1, 1.f));
+  out[i] = __fmaf_rn(x0, w0, __fmul_rn(x1, w1));
+}
+
 __global__ void __launch_bounds__(256) io_copy_kernel(IoCopy c) {
   const IoSeg sg = c.seg[blockIdx.y];
   const uint32_t* src = static_cast<const uint32_t*>(sg.src);
@@ -1023,6 +1047,10 @@ void launch_clip_adamw(const AdamArgs& a, cudaStream_t s) {
   const float decay = (float)(1.0 - (double)a.lr * (double)a.wd);
   adamw_kernel<<<ew_grid(a.n), 256, 0, s>>>(a, decay, (float)((double)a.lr / bc1), (float)sqrt(bc2),
                                             (float)((double)a.lr / bc1c), (float)sqrt(bc2c));
+}
+void launch_preprocess(const double* raw, int width, const int64_t* index, int B, int size, int take_log, float* out,
+                       cudaStream_t s) {
+  preprocess_kernel<<<(B * size + 255) / 256, 256, 0, s>>>(raw, width, index, B, size, take_log, out);
 }
 void launch_io_copy(const IoCopy& c, cudaStream_t s) {
   if (c.n <= 0) return;

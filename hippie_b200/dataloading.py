@@ -224,3 +224,39 @@ class EphysBatchLoader:
             if self.pin_memory and torch.cuda.is_available():
                 batch = tuple(t.pin_memory() for t in batch)
             yield batch
+
+
+class DeviceTable:
+    """A raw source table (waveforms + ISI histograms as pandas reads them, float64) resident on the GPU; `batch(indices)`
+    produces the model inputs of those rows with ONE kernel launch per modality (hippie_preprocess_batch): float32 cast,
+    log(isi + 1), linear interpolation to 50 / 100 samples -- what `EphysDataset.__getitem__` does per item on the host
+    (reference hippie/dataloading.py:27-56).  Waveforms are bit-exact with the host path, ISI values within one ulp before
+    interpolation.  Indices come from the unchanged host samplers (`EphysBatchLoader._order`, `BalancedBatchSampler`)."""
+
+    def __init__(self, waveforms, isi_dists, labels=None, device="cuda"):
+        from . import _lib
+        self._L = _lib.lib()
+        self.device = torch.device(device)
+        self.wave = torch.as_tensor(np.asarray(waveforms, dtype=np.float64)).contiguous().to(self.device)
+        self.isi = torch.as_tensor(np.asarray(isi_dists, dtype=np.float64)).contiguous().to(self.device)
+        assert self.wave.shape[0] == self.isi.shape[0]
+        self.labels = None if labels is None else torch.as_tensor(np.asarray(labels)).long().to(self.device)
+
+    def __len__(self):
+        return self.wave.shape[0]
+
+    def batch(self, indices):
+        import ctypes as C
+        idx = torch.as_tensor(indices, dtype=torch.int64).to(self.device, non_blocking=True).contiguous()
+        B = idx.numel()
+        x1 = torch.empty(B, 1, WAVE_LEN, dtype=torch.float32, device=self.device)
+        x2 = torch.empty(B, 1, ISI_LEN, dtype=torch.float32, device=self.device)
+        ptr = lambda t: C.c_void_p(t.data_ptr())
+        rc = self._L.hippie_preprocess_batch(ptr(self.wave), self.wave.shape[1], ptr(self.isi), self.isi.shape[1], ptr(idx), B,
+                                             ptr(x1), WAVE_LEN, ptr(x2), ISI_LEN,
+                                             C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        if rc != 0:
+            raise RuntimeError(f"hippie_preprocess_batch failed ({rc})")
+        if self.labels is None:
+            return x1, x2
+        return x1, x2, self.labels[idx]

@@ -150,6 +150,16 @@ int hippie_train_forward(hippie_handle h, const float* x1, const float* x2, cons
 int hippie_embed(hippie_handle h, const float* x1, const float* x2, const int64_t* src, const int64_t* cls,
                  int32_t B, int32_t zscore_ddof, float* out_enc, float* out_mu, float* out_logvar, void* stream);
 
+/* Replaces EphysDataset / EphysDatasetLabeled.__getitem__ + DataLoader collation for one batch (hippie/dataloading.py:
+ * 27-56, 74-101; normalize=False as every reference script passes): rows index[0..B) (NULL = rows 0..B-1) of raw,
+ * device-resident float64 tables as pandas reads them -> float32 cast, log(isi + 1), linear interpolation
+ * (align_corners=False) to len_wave / len_isi samples, written as x1 [B,1,len_wave] / x2 [B,1,len_isi].  Either table may
+ * be NULL.  Stateless (no handle).  The waveform path is bit-exact with the reference's CPU result; the ISI path is
+ * within one ulp of it before interpolation (ATen's vectorised logf is not correctly rounded). */
+int hippie_preprocess_batch(const double* wave_raw, int32_t wave_width, const double* isi_raw, int32_t isi_width,
+                            const int64_t* index, int32_t B, float* x1, int32_t len_wave, float* x2, int32_t len_isi,
+                            void* stream);
+
 /* Number of kernel launches issued by the most recent call of each kind (bench.py gpu_launches). */
 int hippie_last_launch_count(hippie_handle h);
 

@@ -274,3 +274,30 @@ def test_free_running_steps_stay_inside_the_reference_envelope():
         spread = max(spread, abs(r32 - r64) / abs(r64))
         assert abs(a - r64) / abs(r64) <= 4.0 * spread + 1e-3, (got, ref32, ref64)
     assert got[-1] < got[0]
+
+
+def test_device_preprocessing_matches_the_host_dataset(golden_dir):
+    """hippie_preprocess_batch (GPU) vs EphysDataset.__getitem__ semantics (oracle.dataset_item, pinned against the
+    reference's fixture): waveforms bit for bit; ISI within 2 ulp (ATen's CPU logf is not correctly rounded)."""
+    from hippie_b200.dataloading import DeviceTable
+    fx = np.load(os.path.join(golden_dir, "cellexplorer_raw48.npz"))
+    tab = DeviceTable(fx["wf"], fx["isi"], labels=np.arange(48) % 4)
+    idx = [5, 0, 47, 13, 13, 2]
+    x1, x2, lab = tab.batch(idx)
+    assert x1.shape == (6, 1, 50) and x2.shape == (6, 1, 100) and lab.tolist() == [i % 4 for i in idx]
+    assert np.array_equal(x1.cpu().numpy(), fx["x1"][idx])  # the reference's own output, bit for bit
+    ref2 = torch.tensor(fx["x2"][idx])
+    ulp = (x2.cpu().view(torch.int32) - ref2.view(torch.int32)).abs().max().item()
+    assert ulp <= 2, ulp
+    assert (x2.cpu() != ref2).float().mean().item() < 0.02
+    # ragged widths (other source tables are 40 / 351 samples wide) and the identity index
+    rng = np.random.default_rng(1)
+    for ww, wi in ((40, 51), (351, 100), (50, 100)):
+        wf, isi = rng.normal(size=(9, ww)), np.abs(rng.normal(size=(9, wi)))
+        a, b = DeviceTable(wf, isi).batch(range(9))
+        for r in range(9):
+            oa, ob = O.dataset_item(wf[r], isi[r])
+            assert torch.equal(a[r].cpu(), oa), (ww, r)
+            assert (b[r].cpu().view(torch.int32) - ob.view(torch.int32)).abs().max().item() <= 2
+    e1, e2 = DeviceTable(np.zeros((3, 47)), np.zeros((3, 100))).batch([])
+    assert e1.shape == (0, 1, 50) and e2.shape == (0, 1, 100)
