@@ -64,6 +64,7 @@ struct PairConv {
   int taps;        // b_mn: kernel size (3 or 1); tap of k-block kb = taps - 1 - kb / kb_per_tap
   const float* dyn_scale;  // optional device scalar multiplied into out_scale
   unsigned long long* stamps;  // tools/pair_test only: %globaltimer at the phase boundaries of CTA (0, 0)
+  EvalFold fold;               // eval-mode BatchNorm (+ residual, LeakyReLU, pair planes) applied in the epilogue
 };
 __device__ __forceinline__ void stamp(const PairConv& p, int i) {
   if (p.stamps && blockIdx.x == 0 && blockIdx.y == 0) {
@@ -221,17 +222,43 @@ __global__ void __launch_bounds__(TC_THREADS, 2)
       const int quad = t % QUADS;
       float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
       if (p.bias) bv = *reinterpret_cast<const float4*>(p.bias + n0 + quad * 4);
+      const EvalFold& fo = p.fold;
+      float4 fsc = bv, fbe = bv, fmu = bv;
+      if (fo.coef) {
+        fsc = *reinterpret_cast<const float4*>(fo.coef + 0 * p.N + n0 + quad * 4);
+        fbe = *reinterpret_cast<const float4*>(fo.coef + 1 * p.N + n0 + quad * 4);
+        fmu = *reinterpret_cast<const float4*>(fo.coef + 2 * p.N + n0 + quad * 4);
+      }
       for (int r = t / QUADS; r < nvalid; r += 128 / QUADS) {
         const int bs = r / p.Lout, l = r - bs * p.Lout;
         float4 v = *reinterpret_cast<const float4*>(&stage[r * S::EPI_STRIDE + quad * 4]);
         v.x += bv.x, v.y += bv.y, v.z += bv.z, v.w += bv.w;
-        float4* dst = reinterpret_cast<float4*>(
-            p.C + ((int64_t)(b0 + bs) * p.out_rows + p.out_off + (int64_t)l * p.out_lstride) * p.N + n0 + quad * 4);
+        const int64_t off = ((int64_t)(b0 + bs) * p.out_rows + p.out_off + (int64_t)l * p.out_lstride) * p.N + n0 + quad * 4;
+        float4* dst = reinterpret_cast<float4*>(p.C + off);
         if (p.accumulate) {
           const float4 o = *dst;
           v.x += o.x, v.y += o.y, v.z += o.z, v.w += o.w;
         }
-        *dst = v;
+        if (fo.coef) {  // same expressions as bn_apply_kernel: the folded result is bit-identical to conv + apply
+          float4 y;
+          y.x = fmaf(v.x - fmu.x, fsc.x, fbe.x), y.y = fmaf(v.y - fmu.y, fsc.y, fbe.y);
+          y.z = fmaf(v.z - fmu.z, fsc.z, fbe.z), y.w = fmaf(v.w - fmu.w, fsc.w, fbe.w);
+          if (fo.res) {
+            const float4 rr = *reinterpret_cast<const float4*>(fo.res + off);
+            y.x += rr.x, y.y += rr.y, y.z += rr.z, y.w += rr.w;
+          }
+          y.x = y.x > 0.f ? y.x : y.x * fo.slope, y.y = y.y > 0.f ? y.y : y.y * fo.slope;
+          y.z = y.z > 0.f ? y.z : y.z * fo.slope, y.w = y.w > 0.f ? y.w : y.w * fo.slope;
+          if (fo.write_f32) *dst = y;
+          if (fo.out_p) store_pair4(fo.out_p, fo.out_ps, off, y);
+          if (fo.up_p) {
+            const int64_t ou = ((int64_t)(b0 + bs) * (2 * p.Lout + 2) + 1 + 2 * l) * p.N + n0 + quad * 4;
+            store_pair4(fo.up_p, fo.up_ps, ou, y);
+            store_pair4(fo.up_p, fo.up_ps, ou + p.N, y);
+          }
+        } else {
+          *dst = v;
+        }
       }
     }
     if (t == 0) stamp(p, 5);
@@ -538,6 +565,7 @@ int launch_conv_pair(const ConvGemm& g, const TcMap& mapA, const TcMap& mapB, in
   p.idesc = umma_idesc_16(bn, o.a_fmt, o.b_fmt, 0, o.b_mn ? 1 : 0);
   p.b_mn = o.b_mn, p.taps = o.taps, p.kb_per_tap = o.taps > 0 ? (g.K / o.taps) / PK : 1;
   p.dyn_scale = o.dyn_scale, p.stamps = o.stamps;
+  if (o.fold) p.fold = *o.fold;
   dim3 grid((B + p.nb - 1) / p.nb, g.N / bn);
 
   const CUtensorMap& a = *reinterpret_cast<const CUtensorMap*>(mapA.opaque);

@@ -553,7 +553,19 @@ struct hippie_engine {
   float* Pp(int p) { return P + params[p].off; }
   float* Gp(int p) { return G + params[p].off; }
 
-  void conv_fwd(const Conv& cv, int in, int out, int bn, int B, bool train, Branch& br) {
+  // eval mode on the tcgen05 path: the BatchNorm that follows a conv (running statistics), the residual, the LeakyReLU
+  // and the pair-plane conversion run in the conv's epilogue -- no bn_apply launches, no fp32 round trip of the conv output
+  bool fold_eval(bool train) const { return !train && use_tc && !profiling; }
+  // out = lrelu_slope(bn(conv(in)) + res): `out` is the ACTIVATION tensor (fp32 written only when the caller needs it)
+  void conv_fwd_folded(const Conv& cv, int in, int bn, int res, int out, int out_up, float slope, bool write_f32, int B,
+                       Branch& br) {
+    EvalFold f{};
+    f.coef = coef(bn), f.res = res >= 0 ? A(res) : nullptr, f.slope = slope, f.write_f32 = write_f32 ? 1 : 0;
+    if (acts[out].poff >= 0) f.out_p = PL(out), f.out_ps = acts[out].pstride;
+    if (out_up >= 0 && acts[out_up].poff >= 0) f.up_p = PL(out_up), f.up_ps = acts[out_up].pstride;
+    conv_fwd(cv, in, out, -1, B, false, br, &f);
+  }
+  void conv_fwd(const Conv& cv, int in, int out, int bn, int B, bool train, Branch& br, const EvalFold* fold = nullptr) {
     ConvGemm g{};
     g.A = A(in), g.W = Pp(cv.w), g.bias = cv.b >= 0 ? Pp(cv.b) : nullptr, g.C = A(out);
     g.part = (train && bn >= 0) ? ws + bns[bn].part_off : nullptr;
@@ -574,6 +586,7 @@ struct hippie_engine {
       }
       const int bn_tile = pair_pick_bn(B, g.N, g.Lout, sm_count);
       PairOpts o{1.f / kWeightPairScale, kPairF16, kPairF16, 0, cv.k};
+      o.fold = fold;
       tile = launch_conv_pair(g, m.a_fwd, m.w_k, bn_tile, B, o, br.st);
     } else {
       tile = launch_conv_gemm_simt(g, br.st);
@@ -698,6 +711,12 @@ struct hippie_engine {
     apply(E.c0, E.bn0, -1, -1, E.a0, -1, B, train, br);
     for (int i = 0; i < 8; ++i) {
       EncBlock& b = E.blk[i];
+      if (fold_eval(train)) {
+        conv_fwd_folded(b.c1, b.x, b.bn1, -1, b.a1, -1, kSlopeBackbone, false, B, br);  // a1: planes only
+        if (b.down) conv_fwd_folded(b.cs, b.x, b.bns, -1, b.cso, -1, 1.f, true, B, br);  // shortcut: BatchNorm, no LeakyReLU
+        conv_fwd_folded(b.c2, b.a1, b.bn2, b.down ? b.cso : b.x, b.out, -1, kSlopeBackbone, true, B, br);
+        continue;
+      }
       conv_fwd(b.c1, b.x, b.c1o, b.bn1, B, train, br);
       apply(b.c1o, b.bn1, -1, -1, b.a1, -1, B, train, br);
       conv_fwd(b.c2, b.a1, b.c2o, b.bn2, B, train, br);
@@ -754,6 +773,16 @@ struct hippie_engine {
     ++launches;
     for (int i = 0; i < 8; ++i) {
       DecBlock& b = D.blk[i];
+      if (fold_eval(train)) {
+        conv_fwd_folded(b.c2, b.x, b.bn2, -1, b.a2, b.a2_up, kSlopeBackbone, false, B, br);  // a2 / a2_up: planes only
+        if (b.up) {
+          conv_fwd_folded(b.cs, b.x_up, b.bns, -1, b.cso, -1, 1.f, true, B, br);
+          conv_fwd_folded(b.c1, b.a2_up, b.bn1, b.cso, b.out, b.out_up, kSlopeBackbone, true, B, br);
+        } else {
+          conv_fwd_folded(b.c1, b.a2, b.bn1, b.x, b.out, b.out_up, kSlopeBackbone, true, B, br);
+        }
+        continue;
+      }
       conv_fwd(b.c2, b.x, b.c2o, b.bn2, B, train, br);
       apply(b.c2o, b.bn2, -1, -1, b.a2, b.a2_up, B, train, br);
       if (b.up) {

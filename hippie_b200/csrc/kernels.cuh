@@ -57,6 +57,19 @@ struct WgradGemm {
 void launch_wgrad_simt(const WgradGemm& g, int sm_count, cudaStream_t s);
 
 // ---- 16-bit pair planes (conv_pair.cu): operands are (hi, lo) planes written by the producing kernels ----
+// Eval-mode BatchNorm folded into the conv epilogue (running statistics are known before the conv runs):
+//   y = lrelu((acc - mean) * scale + beta + res)  written as fp32 (optional), as fp16 pair planes (optional) and as the
+//   nearest x2 up-sampled pair planes (optional) -- the same arithmetic, in the same order, as bn_apply_kernel.
+struct EvalFold {
+  const float* coef = nullptr;  // [0] = scale, [1] = beta, [2] = mean (C floats each); null = no folding
+  const float* res = nullptr;   // residual tensor (same layout as the output) or null
+  float slope = 1.f;            // LeakyReLU slope; 1 = no activation (shortcut branch)
+  int write_f32 = 1;
+  uint16_t* out_p = nullptr;
+  int64_t out_ps = 0;
+  uint16_t* up_p = nullptr;  // planes of the up-sampled copy: rows 2l, 2l+1 of a [B][2L+2][C] tensor
+  int64_t up_ps = 0;
+};
 struct PairOpts {
   float out_scale;   // applied to the accumulator sum in the epilogue (2^-8 when B holds scaled weights)
   int a_fmt, b_fmt;  // kPairF16 / kPairBF16 (pair_fmt.cuh)
@@ -64,6 +77,7 @@ struct PairOpts {
   int taps;          // conv, b_mn = 1: kernel size of the layer
   const float* dyn_scale = nullptr;  // device float multiplied into out_scale (1 / scale of a gradient pair tensor)
   unsigned long long* stamps = nullptr;  // tools/pair_test: 8 device slots for %globaltimer phase stamps of CTA (0, 0)
+  const EvalFold* fold = nullptr;        // conv forward in eval mode
 };
 bool pair_init(std::string* err);
 bool pair_make_act_map(TcMap* out, const void* planes, int64_t plane_stride, int fmt, int in_C, int K, int Lout,

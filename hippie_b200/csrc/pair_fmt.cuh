@@ -27,4 +27,13 @@ __device__ __forceinline__ void pair_split(float x, uint16_t& h, uint16_t& l) {
   }
 }
 
+// 4 consecutive channels -> fp16 pair planes (hi at p, lo at p + ps), 8 bytes per plane
+__device__ __forceinline__ void store_pair4(uint16_t* p, int64_t ps, int64_t idx, float4 v) {
+  uint16_t h0, h1, h2, h3, l0, l1, l2, l3;
+  pair_split<kPairF16>(v.x, h0, l0), pair_split<kPairF16>(v.y, h1, l1);
+  pair_split<kPairF16>(v.z, h2, l2), pair_split<kPairF16>(v.w, h3, l3);
+  *reinterpret_cast<uint2*>(p + idx) = make_uint2((uint32_t)h0 | ((uint32_t)h1 << 16), (uint32_t)h2 | ((uint32_t)h3 << 16));
+  *reinterpret_cast<uint2*>(p + ps + idx) = make_uint2((uint32_t)l0 | ((uint32_t)l1 << 16), (uint32_t)l2 | ((uint32_t)l3 << 16));
+}
+
 }  // namespace hp

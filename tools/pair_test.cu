@@ -247,6 +247,62 @@ static void test_wgrad(int B, int L, int Cin, int Cout, int k, int a_fmt, int b_
   cudaFree(ddy), cudaFree(dx), cudaFree(dw1), cudaFree(dw2), cudaFree(pdy), cudaFree(px);
 }
 
+// Two independent conv problems, alone and concurrently on two streams: do they share a chip-wide bottleneck?
+struct ConvProb {
+  ConvGemm g;
+  TcMap ma, mw;
+  int bn, B;
+  PairOpts o;
+};
+static ConvProb make_prob(int B, int L, int Cin, int Cout, unsigned seed) {
+  const int k = 3, Lout = L;
+  const int64_t in_floats = ((int64_t)B * (L + 2) + 2) * Cin, out_floats = ((int64_t)B * (Lout + 2) + 2) * Cout;
+  std::vector<float> hx(in_floats), hw((size_t)Cout * k * Cin);
+  fill(hx, seed, 1.0f), fill(hw, seed + 1, 0.05f);
+  float *dx = upload(hx), *dw = upload(hw), *dc;
+  CK(cudaMalloc(&dc, out_floats * 4));
+  void* px = planes_of(dx, in_floats, 1.f, F16);
+  void* pw = planes_of(dw, (int64_t)hw.size(), 256.f, F16);
+  ConvProb pr{};
+  pr.g.A = dx + Cin, pr.g.W = dw, pr.g.C = dc + Cout, pr.g.M = B * Lout, pr.g.N = Cout, pr.g.K = k * Cin, pr.g.Lout = Lout;
+  pr.g.in_rows = L + 2, pr.g.in_stride = 1, pr.g.in_off = 0, pr.g.in_C = Cin;
+  pr.g.out_rows = Lout + 2, pr.g.out_off = 1, pr.g.out_lstride = 1;
+  pr.bn = pair_pick_bn(B, Cout, Lout, 148), pr.B = B;
+  pair_make_act_map(&pr.ma, (const uint16_t*)px + Cin, in_floats, F16, Cin, pr.g.K, Lout, L + 2, 1, 0, B);
+  pair_make_w_map(&pr.mw, pw, (int64_t)hw.size(), F16, Cout, pr.g.K, pr.bn);
+  pr.o = PairOpts{1.f / 256.f, F16, F16, 0, k};
+  return pr;
+}
+static void test_concurrency(int B, int L, int C) {
+  ConvProb a = make_prob(B, L, C, C, 21), b = make_prob(B, L, C, C, 31);
+  cudaStream_t s1, s2;
+  cudaStreamCreateWithFlags(&s1, cudaStreamNonBlocking), cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking);
+  const int iters = 50;
+  auto run = [&](bool ua, bool ub) {
+    cudaEvent_t e0, e1, j;
+    cudaEventCreate(&e0), cudaEventCreate(&e1), cudaEventCreate(&j);
+    cudaDeviceSynchronize();
+    cudaEventRecord(e0, s1);
+    cudaStreamWaitEvent(s2, e0, 0);
+    for (int i = 0; i < iters; ++i) {
+      if (ua) launch_conv_pair(a.g, a.ma, a.mw, a.bn, a.B, a.o, s1);
+      if (ub) launch_conv_pair(b.g, b.ma, b.mw, b.bn, b.B, b.o, s2);
+    }
+    cudaEventRecord(j, s2);
+    cudaStreamWaitEvent(s1, j, 0);
+    cudaEventRecord(e1, s1);
+    cudaEventSynchronize(e1);
+    float ms;
+    cudaEventElapsedTime(&ms, e0, e1);
+    return ms * 1e3f / iters;
+  };
+  run(true, true);
+  const float ta = run(true, false), tb = run(false, true), tab = run(true, true);
+  const int nb = 128 / L, ctas = ((B + nb - 1) / nb) * (C / 64);
+  printf("concurrency B=%4d L=%2d C=%3d (%3d CTAs each): A alone %6.1f us, B alone %6.1f us, A||B %6.1f us per pair  (sum %6.1f)\n", B, L,
+         C, ctas, ta, tb, tab, ta + tb);
+}
+
 int main(int argc, char** argv) {
   std::string err;
   if (!pair_init(&err)) {
@@ -255,6 +311,14 @@ int main(int argc, char** argv) {
   }
   const int B = argc > 1 ? atoi(argv[1]) : 512;
   const int sel = argc > 2 ? atoi(argv[2]) : 0;
+  if (sel == 4) {
+    test_concurrency(128, 4, 512);   // 32 CTAs each
+    test_concurrency(256, 4, 512);   // 64 CTAs each: together 128 <= 148 SMs
+    test_concurrency(512, 4, 512);   // 128 CTAs each
+    test_concurrency(1024, 4, 512);  // 256 CTAs each
+    test_concurrency(512, 32, 64);   // K = 192
+    return 0;
+  }
   if (sel == 0 || sel == 1) {
     test_conv(8, 4, 64, 64, 3, 1, false, F16, F16);
     test_conv(B, 25, 64, 64, 3, 1, false, F16, F16);
