@@ -598,8 +598,8 @@ struct hippie_engine {
   // the apply kernel turns the partials the conv left into coefficients (and running statistics) itself
   BnFinalize finalize_args(int bn) {
     BnFinalize f{};
-    f.part = ws + bns[bn].part_off, f.ntiles = bns[bn].ntiles, f.tile_rows = bns[bn].tile_rows, f.M = bns[bn].M;
-    f.C = bns[bn].C;
+    f.part = ws + bns[bn].part_off, f.C = bns[bn].C;
+    f.set_shape(bns[bn].ntiles, bns[bn].tile_rows, bns[bn].M);
     f.gamma = Pp(bns[bn].gamma), f.beta = Pp(bns[bn].beta);
     f.run_mean = bn_mean + bns[bn].run_off, f.run_var = bn_var + bns[bn].run_off, f.run_count = bn_count + bn;
     f.coef = coef(bn);
@@ -689,6 +689,7 @@ struct hippie_engine {
     a.g = A(g), a.g_up = g_up ? 1 : 0, a.out = A(out), a.c = A(c), a.coef = coef(bn);
     a.cs = cs >= 0 ? A(cs) : nullptr, a.coef_s = cs >= 0 ? coef(bnsi) : nullptr;
     a.part = br.bpart, a.B = B, a.L = acts[out].L, a.C = acts[out].C, a.slope = kSlopeBackbone;
+    a.inv_n = 1.0 / ((double)B * acts[out].L);
     a.gamma = Pp(bns[bn].gamma), a.dgamma = Gp(bns[bn].gamma), a.dbeta = Gp(bns[bn].beta);
     if (cs >= 0) a.gamma_s = Pp(bns[bnsi].gamma), a.dgamma_s = Gp(bns[bnsi].gamma), a.dbeta_s = Gp(bns[bnsi].beta);
     a.dc = A(dc), a.dil = dil, a.Ld = acts[dc].L;

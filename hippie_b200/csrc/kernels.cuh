@@ -109,6 +109,14 @@ void launch_reduce_partials(const float* part, int nparts, int n, float* out, in
 struct BnFinalize {
   const float* part;  // [ntiles][C][2]
   int ntiles, tile_rows, M, C;
+  // host-computed reciprocals (double division / sqrt are ~0.2 us software sequences on the device, and the finalize
+  // phase sits on the critical path of every BatchNorm): 1/M, 1/max(M-1,1), 1/tile_rows, 1/(rows of the last tile)
+  double inv_M, inv_Mm1, inv_tile, inv_last;
+  void set_shape(int ntiles_, int tile_rows_, int M_) {
+    ntiles = ntiles_, tile_rows = tile_rows_, M = M_;
+    inv_M = 1.0 / M_, inv_Mm1 = 1.0 / (M_ > 1 ? M_ - 1 : 1), inv_tile = 1.0 / tile_rows_;
+    inv_last = 1.0 / (M_ - (ntiles_ - 1) * tile_rows_);
+  }
   const float* gamma;
   const float* beta;
   float* run_mean;
@@ -144,6 +152,7 @@ struct BnApply {
   int64_t out_ps = 0;
   uint16_t* up_p = nullptr;
   int64_t up_ps = 0;
+  unsigned long long* stamps = nullptr;  // tools/bn_test: %globaltimer phase stamps of CTA (0, 0)
 };
 void launch_bn_apply(const BnApply& a, int sm_count, cudaStream_t s);
 
@@ -173,6 +182,7 @@ struct BnBwd {
   float* dcs;
   int dil_s, Ld_s;
   float* gres;  // if non-null: g_pre is written here (identity shortcut), same layout as out
+  double inv_n = 0.0;  // 1 / (B * L), computed on the host
   // pair path: dc / dcs may be null; the gradients go to fp16 pair planes scaled by a power of two chosen from an upper
   // bound of max|dc|.  slot = (max|g_pre|, max|xhat|, max|gamma*invstd|, 1 / scale): [0..2] are atomicMax targets that
   // the engine zeroes once per step, [3] is read by the dgrad / wgrad epilogues

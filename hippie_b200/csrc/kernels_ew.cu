@@ -137,39 +137,59 @@ struct ChanAcc {
 __device__ __forceinline__ void bn_finalize_slab(const BnFinalize& f, int c0, bool publish, float* sc, float* sh,
                                                  float* mu, ChanAcc (*acc)[kSlab]) {
   const int c = threadIdx.x & (kSlab - 1), slice = threadIdx.x >> 5;  // 8 slices of tiles
-  const double inv_full = 1.0 / (double)f.tile_rows;
+  const double inv_full = f.inv_tile, inv_last = f.inv_last;
   const int last = f.ntiles - 1;
-  const double inv_last = 1.0 / (double)(f.M - last * f.tile_rows);
   double S = 0.0, Q = 0.0;
   const float* base = f.part + ((int64_t)c0 + c) * 2;
-#pragma unroll 4
-  for (int t = slice; t < f.ntiles; t += 8) {
-    const float2 p = __ldcg(reinterpret_cast<const float2*>(base + (int64_t)t * f.C * 2));
-    const double st = (double)p.x;
-    S += st;
-    Q += (double)p.y + st * st * (t == last ? inv_last : inv_full);
+  // everything the last step needs is requested up front: the phase is a chain of L2 round trips otherwise
+  float gam = 0.f, bet = 0.f, rmean = 0.f, rvar = 0.f;
+  if (slice == 0) {
+    gam = f.gamma[c0 + c], bet = f.beta[c0 + c];
+    if (publish) rmean = f.run_mean[c0 + c], rvar = f.run_var[c0 + c];
+  }
+  // 8 tiles in flight per thread: the loop is a chain of L2 round trips otherwise (up to 32 tiles per thread)
+  constexpr int FL = 8;
+  for (int t0 = slice; t0 < f.ntiles; t0 += 8 * FL) {
+    float2 pv[FL];
+#pragma unroll
+    for (int u = 0; u < FL; ++u) {
+      const int t = t0 + 8 * u;
+      pv[u] = t < f.ntiles ? __ldcg(reinterpret_cast<const float2*>(base + (int64_t)t * f.C * 2)) : make_float2(0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < FL; ++u) {
+      const int t = t0 + 8 * u;
+      const double st = (double)pv[u].x;
+      S += st;
+      Q += (double)pv[u].y + st * st * (t == last ? inv_last : inv_full);
+    }
   }
   acc[slice][c] = ChanAcc{S, Q};
   __syncthreads();
   if (slice == 0) {
     for (int k = 1; k < 8; ++k) S += acc[k][c].s, Q += acc[k][c].q;
-    const double mean = S / (double)f.M;
+    const double mean = S * f.inv_M;
     double m2 = Q - S * mean;
     m2 = m2 > 0.0 ? m2 : 0.0;
-    const double var_b = m2 / (double)f.M;
-    const float invstd = (float)(1.0 / sqrt(var_b + (double)kBnEps));
+    const double var_b = m2 * f.inv_M;
+    // 1 / sqrt(v) in double without the software sqrt / division: float estimate + two Newton steps (multiplies only)
+    const double vv = var_b + (double)kBnEps;
+    double y = (double)rsqrtf((float)vv);
+    y = y * (1.5 - 0.5 * vv * y * y);
+    y = y * (1.5 - 0.5 * vv * y * y);
+    const float invstd = (float)y;
     const float meanf = (float)mean;
     const int cc = c0 + c;
-    const float scale = f.gamma[cc] * invstd, beta = f.beta[cc];
+    const float scale = gam * invstd, beta = bet;
     sc[c] = scale, sh[c] = beta, mu[c] = meanf;
     if (publish) {
       f.coef[0 * f.C + cc] = scale;
       f.coef[1 * f.C + cc] = beta;
       f.coef[2 * f.C + cc] = meanf;
       f.coef[3 * f.C + cc] = invstd;
-      const float var_u = (float)(m2 / (double)max(f.M - 1, 1));
-      f.run_mean[cc] = (1.f - kBnMomentum) * f.run_mean[cc] + kBnMomentum * meanf;
-      f.run_var[cc] = (1.f - kBnMomentum) * f.run_var[cc] + kBnMomentum * var_u;
+      const float var_u = (float)(m2 * f.inv_Mm1);
+      f.run_mean[cc] = (1.f - kBnMomentum) * rmean + kBnMomentum * meanf;
+      f.run_var[cc] = (1.f - kBnMomentum) * rvar + kBnMomentum * var_u;
       if (cc == 0) *f.run_count += 1;
     }
   }
@@ -197,7 +217,17 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(BnApply a) {
   __shared__ float s_sc[kSlab], s_sh[kSlab], s_mu[kSlab], r_sc[kSlab], r_sh[kSlab], r_mu[kSlab];
   __shared__ ChanAcc s_acc[8][kSlab];
   pdl_trigger();
+  const bool stamping = a.stamps && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0;
+  auto stamp = [&](int i) {
+    if (stamping) {
+      unsigned long long tt;
+      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tt));
+      a.stamps[i] = tt;
+    }
+  };
+  stamp(0);
   pdl_wait();
+  stamp(1);
   const int c0 = blockIdx.x * kSlab;
   if (a.train) {
     bn_finalize_slab(a.fin, c0, blockIdx.y == 0, s_sc, s_sh, s_mu, s_acc);
@@ -214,6 +244,7 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(BnApply a) {
     }
     __syncthreads();
   }
+  stamp(2);
   const int q = threadIdx.x & 7, rl = threadIdx.x >> 3;
   const float4 sc = *reinterpret_cast<const float4*>(s_sc + q * 4), be = *reinterpret_cast<const float4*>(s_sh + q * 4);
   const float4 mu = *reinterpret_cast<const float4*>(s_mu + q * 4);
@@ -265,6 +296,7 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(BnApply a) {
       }
     }
   }
+  stamp(3);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -421,16 +453,24 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(BnBwd a, int nchunks)
   {
     const int c = threadIdx.x & (kSlab - 1), slice = threadIdx.x >> 5;
     double s1 = 0.0, s2 = 0.0, s3 = 0.0;
-    for (int t = slice; t < nchunks; t += 8) {
-      const float* p = a.part + ((int64_t)t * a.C + c0 + c) * 3;
-      s1 += (double)__ldcg(p), s2 += (double)__ldcg(p + 1), s3 += (double)__ldcg(p + 2);
+    for (int t0 = slice; t0 < nchunks; t0 += 64) {  // 8 chunks (24 loads) in flight per thread
+      float v[8][3];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int t = t0 + 8 * u;
+        const float* p = a.part + ((int64_t)min(t, nchunks - 1) * a.C + c0 + c) * 3;
+        const bool ok = t < nchunks;
+        v[u][0] = ok ? __ldcg(p) : 0.f, v[u][1] = ok ? __ldcg(p + 1) : 0.f, v[u][2] = ok ? __ldcg(p + 2) : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) s1 += (double)v[u][0], s2 += (double)v[u][1], s3 += (double)v[u][2];
     }
     s_sum[slice][c][0] = s1, s_sum[slice][c][1] = s2, s_sum[slice][c][2] = s3;
     __syncthreads();
     if (slice == 0) {
       for (int k = 1; k < 8; ++k) s1 += s_sum[k][c][0], s2 += s_sum[k][c][1], s3 += s_sum[k][c][2];
-      const double n = (double)a.B * a.L;
-      s_m1[c] = (float)(s1 / n), s_m2[c] = (float)(s2 / n), s_m3[c] = (float)(s3 / n);
+      const double inv_n = a.inv_n;
+      s_m1[c] = (float)(s1 * inv_n), s_m2[c] = (float)(s2 * inv_n), s_m3[c] = (float)(s3 * inv_n);
       if (blockIdx.y == 0) {
         a.dgamma[c0 + c] = (float)s2, a.dbeta[c0 + c] = (float)s1;
         if (a.cs) a.dgamma_s[c0 + c] = (float)s3, a.dbeta_s[c0 + c] = (float)s1;
