@@ -54,6 +54,40 @@ static void run(int B, int L, int C, int res) {
          B, L, C, res, ntiles, ms * 1e3 / 50, hs[1] - hs[0], hs[2] - hs[1], hs[3] - hs[2], (double)M * C * (4 + 4 + 4 + (res ? 4 : 0)) / 1e6);
   cudaFree(c), cudaFree(r), cudaFree(out), cudaFree(planes), cudaFree(part), cudaFree(coef);
 }
+static void run_bwd(int B, int L, int C, int shortcut) {
+  const int64_t rows = (int64_t)B * (L + 2) + 2, n = rows * C;
+  float *g, *out, *c, *cs, *coef, *coef_s, *gamma, *dg, *db, *part, *gres, *slot;
+  uint16_t* planes;
+  CK(cudaMalloc(&g, n * 4)), CK(cudaMalloc(&out, n * 4)), CK(cudaMalloc(&c, n * 4)), CK(cudaMalloc(&cs, n * 4));
+  CK(cudaMalloc(&gres, n * 4)), CK(cudaMalloc(&planes, n * 8)), CK(cudaMalloc(&coef, C * 32)), CK(cudaMalloc(&coef_s, C * 32));
+  CK(cudaMalloc(&gamma, C * 4)), CK(cudaMalloc(&dg, C * 4)), CK(cudaMalloc(&db, C * 4)), CK(cudaMalloc(&slot, 64));
+  CK(cudaMalloc(&part, (size_t)(kBnBwdMaxChunks + 1) * C * 3 * 4));
+  CK(cudaMemset(g, 0, n * 4)), CK(cudaMemset(out, 0, n * 4)), CK(cudaMemset(c, 0, n * 4)), CK(cudaMemset(cs, 0, n * 4));
+  CK(cudaMemset(coef, 0, C * 32)), CK(cudaMemset(coef_s, 0, C * 32)), CK(cudaMemset(gamma, 0, C * 4)), CK(cudaMemset(slot, 0, 64));
+  BnBwd a{};
+  a.g = g + C, a.out = out + C, a.c = c + C, a.coef = coef, a.part = part, a.B = B, a.L = L, a.C = C, a.slope = 0.01f;
+  a.gamma = gamma, a.dgamma = dg, a.dbeta = db, a.dil = 1, a.Ld = L, a.inv_n = 1.0 / ((double)B * L);
+  a.dc_p = planes + C, a.dc_ps = n, a.dc_slot = slot;
+  if (shortcut) {
+    a.cs = cs + C, a.coef_s = coef_s, a.gamma_s = gamma, a.dgamma_s = dg, a.dbeta_s = db;
+    a.dcs_p = planes + 2 * n + C, a.dcs_ps = n, a.dcs_slot = slot + 8, a.dil_s = 1, a.Ld_s = L;
+  } else {
+    a.gres = gres + C;
+  }
+  for (int i = 0; i < 3; ++i) launch_bn_bwd(a, 148, 0);
+  CK(cudaDeviceSynchronize());
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0), cudaEventCreate(&e1);
+  cudaEventRecord(e0);
+  for (int i = 0; i < 50; ++i) launch_bn_bwd(a, 148, 0);
+  cudaEventRecord(e1);
+  CK(cudaEventSynchronize(e1));
+  float ms;
+  cudaEventElapsedTime(&ms, e0, e1);
+  printf("bn_bwd (reduce + apply) B=%d L=%2d C=%3d shortcut%d: %6.2f us per pair back-to-back | %.1f MB moved\n", B, L, C, shortcut,
+         ms * 1e3 / 50, (double)B * L * C * 4 * (2 * (3 + shortcut) + 1 + shortcut + (shortcut ? 0 : 1)) / 1e6);
+}
+
 int main() {
   run(512, 50, 64, 0);
   run(512, 50, 64, 1);
@@ -63,5 +97,12 @@ int main() {
   run(512, 4, 512, 1);
   run(512, 32, 64, 1);
   run(64, 50, 64, 0);
+  run_bwd(512, 50, 64, 0);
+  run_bwd(512, 25, 128, 0);
+  run_bwd(512, 13, 256, 1);
+  run_bwd(512, 7, 512, 0);
+  run_bwd(512, 4, 512, 1);
+  run_bwd(512, 32, 64, 0);
+  run_bwd(64, 50, 64, 0);
   return 0;
 }
