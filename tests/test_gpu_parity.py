@@ -301,3 +301,20 @@ def test_device_preprocessing_matches_the_host_dataset(golden_dir):
             assert (b[r].cpu().view(torch.int32) - ob.view(torch.int32)).abs().max().item() <= 2
     e1, e2 = DeviceTable(np.zeros((3, 47)), np.zeros((3, 100))).batch([])
     assert e1.shape == (0, 1, 50) and e2.shape == (0, 1, 100)
+
+
+def test_large_batch_embedding_equals_small_batches():
+    """4096 units in one call (multi-wave grids, the throughput configuration of bench.py's embedding workload) must
+    equal, bit for bit, the concatenation of bs512 calls: units are independent in eval mode."""
+    cfg = O.CVAEConfig(z_dim=10)
+    N = 4096
+    eng = U.make_engine(cfg, N, inference_only=True)
+    eng.load_named(U.perturbed_state(cfg))
+    x1, x2, labels, _ = O.synthetic_batch(N, seed=9)
+    dev = eng.device
+    x1, x2, src = x1.to(dev), x2.to(dev), labels.to(dev)
+    whole = eng.embed(x1, x2, src)
+    parts = [eng.embed(x1[i:i + 512].contiguous(), x2[i:i + 512].contiguous(), src[i:i + 512].contiguous())
+             for i in range(0, N, 512)]
+    for k in ("enc", "mu", "logvar"):
+        assert torch.equal(whole[k], torch.cat([p[k] for p in parts])), k
