@@ -1,9 +1,10 @@
 // tcgen05 implicit-GEMM conv1d (forward, dgrad) and weight gradient over 16-bit PAIR PLANES.
 //
 // Every GEMM operand lives in HBM as two 16-bit planes (hi, lo) with  x ~= hi + lo :
-//   forward   activations fp16 pair (scale 1), weights fp16 pair (scale 2^8)          -> ~22 mantissa bits
-//   backward  output gradients bf16 pair (no range issue), weights / activations as in the forward
-// and one product is three tensor-core MMAs  hi*hi + hi*lo + lo*hi  (kind::f16, K = 16, fp32 accumulation in TMEM).
+//   activations fp16 pair (scale 1), weights fp16 pair (scale 2^8), output gradients fp16 pair scaled by a power of
+//   two chosen on the device from a bound of max|g| (bn_bwd_apply_kernel)                      -> ~22 mantissa bits
+// (mixed fp16 x bf16 operands are an illegal instruction on sm_100a; a bf16 pair is supported by the kernels and used by
+// tools/pair_test only) and one product is three tensor-core MMAs  hi*hi + hi*lo + lo*hi  (kind::f16, K = 16, fp32 accumulation in TMEM).
 // tools/pair_precision.py shows the fp16 pair matches fp32 operands on the loss / embedding bounds (like 3xTF32),
 // at HALF the tensor time and ~1/3 of the shared-memory traffic of an in-kernel 3xTF32 split: the kernels below are
 // pure TMA -> MMA pipelines, the producers of the tensors write the planes (kernels_ew.cu).

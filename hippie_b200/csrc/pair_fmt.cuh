@@ -1,6 +1,6 @@
 // 16-bit pair planes: x ~= hi + lo with hi = round16(x), lo = round16(x - hi).
 //   kPairF16  : fp16 pair, ~22 mantissa bits for |x| >= 2^-3 (absolute error <= 2^-25 below); saturates at 65504
-//   kPairBF16 : bf16 pair, 16 mantissa bits, fp32 exponent range (gradients)
+//   kPairBF16 : bf16 pair, 16 mantissa bits, fp32 exponent range (tools/pair_test; the engine uses fp16 pairs throughout)
 #pragma once
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
