@@ -305,6 +305,21 @@ def main():
             t.copy_(v)
         extra["supervised_bs64"] = {"metric": "supervised finetune step (class labels, bs64/GPU)", "ms_per_step": ms_s / n_e,
                                     "value": SB * world * n_e / (ms_s * 1e-3), "unit": "samples/s"}
+        # stage-3 evaluation on the device: neighbours once for k = 19, then votes, confusion
+        # matrices and balanced accuracy for k = 5..19; embeddings-shaped synthetic rows resident in HBM
+        from hippie_b200 import knn as gknn
+        gk = torch.Generator(device="cpu").manual_seed(4321)
+        k_tr, k_te = torch.randn(20000, 10, generator=gk).to(dev), torch.randn(4096, 10, generator=gk).to(dev)
+        y_tr, y_te = torch.randint(0, 4, (20000,), generator=gk).to(dev), torch.randint(0, 4, (4096,), generator=gk).to(dev)
+
+        def knn_pass(_i):
+            _, nb = gknn.kneighbors(k_tr, k_te, 19, return_distance=False)
+            gknn._evaluate(nb, y_tr, y_te, 4, 5, 19)
+        knn_pass(0)
+        ms_k = timed(knn_pass, 10)
+        extra["knn_eval"] = {"metric": "KNN sweep k=5..19 (20000 train x 4096 test rows, z=10): neighbours + votes + "
+                                       "confusion + balanced accuracy", "ms_per_pass": ms_k / 10,
+                             "value": 4096 * 10 / (ms_k * 1e-3), "unit": "test rows/s"}
     except Exception as e:  # pragma: no cover
         extra["error"] = repr(e)
 

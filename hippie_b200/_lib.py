@@ -69,6 +69,10 @@ SIGNATURES = {
                                     C.c_int32, C.c_int32, C.c_int32, _f32p, C.c_void_p]),
     "hippie_preprocess_batch": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, _i64p, C.c_int32, _f32p, C.c_int32,
                                           _f32p, C.c_int32, C.c_void_p]),
+    "hippie_knn_neighbors": (C.c_int, [_f32p, C.c_int64, _f32p, C.c_int64, C.c_int32, C.c_int32, _i64p, C.c_void_p,
+                                       C.c_void_p]),
+    "hippie_knn_evaluate": (C.c_int, [_i64p, C.c_int64, C.c_int32, _i64p, _i64p, C.c_int32, C.c_int32, C.c_int32, _i64p,
+                                      _i64p, C.c_void_p, C.c_void_p]),
     "hippie_last_launch_count": (C.c_int, [_H]),
     "hippie_conv_path_in_use": (C.c_int, [_H]),
     "hippie_profile": (C.c_int, [_H, C.c_int]),

@@ -160,6 +160,26 @@ int hippie_preprocess_batch(const double* wave_raw, int32_t wave_width, const do
                             const int64_t* index, int32_t B, float* x1, int32_t len_wave, float* x2, int32_t len_isi,
                             void* stream);
 
+/* Replaces KNeighborsClassifier(n_neighbors=k).fit(train).kneighbors(query) of the stage-3 evaluation
+ * (scripts/train_model_with_multimodal.py:916-924, 929-931; scikit-learn, Euclidean metric, uniform weights): for every
+ * row of query [n_query, dim] the k <= 32 nearest rows of train [n_train, dim] by squared Euclidean distance evaluated in
+ * double (float32 inputs widened, summed in feature order), ascending, equal distances by ascending row index.
+ * out_index [n_query, k] int64; out_sqdist [n_query, k] double (may be NULL; sklearn reports its square root).
+ * Stateless (no handle). */
+int hippie_knn_neighbors(const float* train, int64_t n_train, const float* query, int64_t n_query, int32_t dim,
+                         int32_t k, int64_t* out_index, double* out_sqdist, void* stream);
+
+/* Replaces .predict(test), balanced_accuracy_score and confusion_matrix for every k in [k_lo, k_hi] at once
+ * (scripts/train_model_with_multimodal.py:919-934).  neighbors [n_query, k_stride] from hippie_knn_neighbors
+ * (k_hi <= k_stride); train_class [n_train] / true_class [n_query] are dense class indices in [0, n_classes <= 128)
+ * over the sorted union of the labels (what LabelEncoder / np.unique produce).  Majority vote, ties to the smallest
+ * class.  out_pred [nk, n_query] int64 (may be NULL); out_confusion [nk, n_classes, n_classes] int64 rows = true class
+ * (zeroed here); out_balanced_accuracy [nk] double = mean recall over the classes present in true_class, summed in
+ * numpy's order.  true_class, out_confusion, out_balanced_accuracy may be NULL together (prediction only). */
+int hippie_knn_evaluate(const int64_t* neighbors, int64_t n_query, int32_t k_stride, const int64_t* train_class,
+                        const int64_t* true_class, int32_t n_classes, int32_t k_lo, int32_t k_hi, int64_t* out_pred,
+                        int64_t* out_confusion, double* out_balanced_accuracy, void* stream);
+
 /* Number of kernel launches issued by the most recent call of each kind (bench.py gpu_launches). */
 int hippie_last_launch_count(hippie_handle h);
 

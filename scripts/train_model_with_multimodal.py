@@ -283,9 +283,9 @@ def main(argv=None):
         run.log_artifact(path, name=os.path.basename(path), type=os.path.basename(path))
 
     # ------------------------------------------------------------------ stage 3: supervised fine-tuning + KNN
-    from sklearn.metrics import balanced_accuracy_score, confusion_matrix
-    from sklearn.neighbors import KNeighborsClassifier
     from sklearn.preprocessing import LabelEncoder
+
+    from hippie_b200.knn import knn_sweep  # KNeighborsClassifier / balanced accuracy / confusion matrix on the GPU
     ds = args.dataset
     sup_wf, sup_isi = read_table(args.data_root, ds)
     labels_path = os.path.join(args.data_root, ds, "labels.csv")
@@ -330,13 +330,10 @@ def main(argv=None):
     e_all = embeddings_of(tasks, sup_modules, EphysBatchLoader(d_all, 128))
     neighbor_options = list(range(5, 20))
     for name in e_train:
-        acc = []
         for k in neighbor_options:
             print(f"KNN with {k} neighbors")
-            pred = KNeighborsClassifier(n_neighbors=k).fit(e_train[name], y_train).predict(e_val[name])
-            acc.append(balanced_accuracy_score(y_val, pred))
-        best_k = neighbor_options[int(np.argmax(acc))]
-        pred = KNeighborsClassifier(n_neighbors=best_k).fit(e_train[name], y_train).predict(e_val[name])
+        sweep = knn_sweep(e_train[name], y_train, e_val[name], y_val, neighbor_options)  # one pass for all k
+        acc, best_k, pred = sweep["balanced_accuracy"], sweep["best_neighbors"], sweep["pred"]
         knn_path = out(f"{ds}_{name}_knn.csv")
         pd.DataFrame({"pred": le.inverse_transform(pred.astype(int)),
                       "true": le.inverse_transform(y_val.astype(int))}).to_csv(knn_path)
@@ -348,7 +345,7 @@ def main(argv=None):
         run.log_artifact(emb_path, name=os.path.basename(emb_path), type=os.path.basename(emb_path))
         run.log({f"best_balanced_accuracy_{name}": float(np.max(acc))})
         print(f"{name}: best balanced accuracy {np.max(acc):.4f} with {best_k} neighbors")
-        fig = make_confmat(confusion_matrix(y_val, pred), le.classes_, best_k)
+        fig = make_confmat(sweep["confusion"], le.classes_, best_k)
         if fig is not None and hasattr(run, "wandb"):
             run.log({f"{ds}_confusion_matrix_{name}": run.wandb.Image(fig)})
     if args.upload_model:
