@@ -15,7 +15,9 @@
 //               no transposed weight copy exists)
 //
 // Per CTA (192 threads): warp 0 TMA producer, warp 1 TMEM allocator + MMA issuer, warps 2-5 epilogue
-// (TMEM -> registers -> shared staging -> coalesced stores, bias, BatchNorm (sum, centred M2) partials).
+// (TMEM -> registers -> swizzled shared staging -> ONE elected thread issues TMA tensor stores of the whole tile
+// (add-reduce when the layer accumulates into its output) while the four warps compute the BatchNorm (sum, centred M2)
+// partials from the same staging; tiles with a bias, an eval-mode fold or a ragged batch edge use per-thread stores).
 // The tensor core truncates when it adds into the fp32 accumulator; to keep that bias below the parity bound the
 // hi*hi products alternate between two accumulators and the small cross terms use a third (summed with
 // round-to-nearest in the epilogue).
@@ -66,6 +68,7 @@ struct PairConv {
   const float* dyn_scale;  // optional device scalar multiplied into out_scale
   unsigned long long* stamps;  // tools/pair_test only: %globaltimer at the phase boundaries of CTA (0, 0)
   EvalFold fold;               // eval-mode BatchNorm (+ residual, LeakyReLU, pair planes) applied in the epilogue
+  int tma_out;                 // mapC describes the fp32 output: whole tiles leave through TMA stores
 };
 __device__ __forceinline__ void stamp(const PairConv& p, int i) {
   if (p.stamps && blockIdx.x == 0 && blockIdx.y == 0) {
@@ -84,15 +87,21 @@ struct PairSmem {
   static constexpr int B_LO = B_OFF + B_PLANE;
   static constexpr int STAGE_BYTES = 2 * A_PLANE + 2 * B_PLANE;
   static constexpr int RING_BYTES = STAGES * STAGE_BYTES;
-  static constexpr int EPI_STRIDE = BN + 4;
-  static_assert(TC_BM * EPI_STRIDE * 4 <= RING_BYTES, "epilogue staging must fit in the ring");
+  // epilogue staging: BN / 32 boxes of [128 rows][32 floats] in the 128-byte swizzle a TMA store expects
+  // (16-byte chunk j of row r sits at chunk j ^ (r & 7)): row-per-thread writes and column reads are conflict-free
+  static constexpr int EPI_BOX_FLOATS = TC_BM * 32;
+  static_assert((BN / 32) * EPI_BOX_FLOATS * 4 <= RING_BYTES, "epilogue staging must fit in the ring");
+  __device__ static __forceinline__ int epi(int r, int col) {
+    return (col >> 5) * EPI_BOX_FLOATS + r * 32 + (((((col & 31) >> 2) ^ (r & 7))) << 2) + (col & 3);
+  }
   static constexpr int TOTAL = RING_BYTES + 1024 + 256;
   static constexpr int TMEM_COLS = BN == 128 ? 512 : 256;  // three accumulators of BN columns (power of two)
 };
 
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(TC_THREADS, 2)
-    conv_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, PairConv p) {
+    conv_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+                     const __grid_constant__ CUtensorMap mapC, PairConv p) {
   using S = PairSmem<BN, STAGES>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -195,7 +204,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2)
     mbar_wait(accum, 0);
     if (t == 0) stamp(p, 3);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    float* stage = reinterpret_cast<float*>(ring);  // [128][BN + 4]; the ring is idle once `accum` has fired
+    float* stage = reinterpret_cast<float*>(ring);  // swizzled boxes (PairSmem::epi); the ring is idle once `accum` has fired
     const int q = warp & 3;                         // TMEM lane quarter this warp may read
     const int row = q * 32 + lane;
     const float sc = p.dyn_scale ? p.out_scale * __ldg(p.dyn_scale) : p.out_scale;
@@ -211,14 +220,28 @@ __global__ void __launch_bounds__(TC_THREADS, 2)
         r[i] = __float_as_uint(((__uint_as_float(r[i]) + __uint_as_float(r1[i])) + __uint_as_float(r2[i])) * sc);
 #pragma unroll
       for (int i = 0; i < 8; ++i)
-        *reinterpret_cast<uint4*>(&stage[row * S::EPI_STRIDE + c * 32 + i * 4]) =
+        *reinterpret_cast<uint4*>(&stage[S::epi(row, c * 32 + i * 4)]) =
             make_uint4(r[i * 4], r[i * 4 + 1], r[i * 4 + 2], r[i * 4 + 3]);
     }
+    const int nvalid = min(rows_tile, (p.B - b0) * p.Lout);  // rows of this tile that are real outputs
+    // whole tiles without a bias / fold go out through the TMA unit (it skips the pad rows by construction of mapC)
+    const bool tma_out = p.tma_out && nvalid == rows_tile && !p.bias && !p.fold.coef;
+    if (tma_out) fence_proxy_async_smem();
     asm volatile("bar.sync 1, 128;" ::: "memory");  // the four epilogue warps only
     if (t == 0) stamp(p, 4);
 
-    const int nvalid = min(rows_tile, (p.B - b0) * p.Lout);  // rows of this tile that are real outputs
-    {  // coalesced stores: thread -> (row group, fixed column quad)
+    if (tma_out) {
+      if (t == 0) {
+#pragma unroll
+        for (int c = 0; c < BN / 32; ++c) {
+          if (p.accumulate)
+            tma_reduce_add_3d(&mapC, stage + c * S::EPI_BOX_FLOATS, n0 + c * 32, 0, b0);
+          else
+            tma_store_3d(&mapC, stage + c * S::EPI_BOX_FLOATS, n0 + c * 32, 0, b0);
+        }
+        tma_store_commit();
+      }
+    } else {  // coalesced stores: thread -> (row group, fixed column quad)
       constexpr int QUADS = BN / 4;
       const int quad = t % QUADS;
       float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -232,7 +255,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2)
       }
       for (int r = t / QUADS; r < nvalid; r += 128 / QUADS) {
         const int bs = r / p.Lout, l = r - bs * p.Lout;
-        float4 v = *reinterpret_cast<const float4*>(&stage[r * S::EPI_STRIDE + quad * 4]);
+        float4 v = *reinterpret_cast<const float4*>(&stage[S::epi(r, quad * 4)]);
         v.x += bv.x, v.y += bv.y, v.z += bv.z, v.w += bv.w;
         const int64_t off = ((int64_t)(b0 + bs) * p.out_rows + p.out_off + (int64_t)l * p.out_lstride) * p.N + n0 + quad * 4;
         float4* dst = reinterpret_cast<float4*>(p.C + off);
@@ -269,30 +292,33 @@ __global__ void __launch_bounds__(TC_THREADS, 2)
       const int col = t % BN, part_id = t / BN;
       const int r_lo = (nvalid * part_id) / TPC, r_hi = (nvalid * (part_id + 1)) / TPC;
       const int cnt = r_hi - r_lo;
-      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-      int r = r_lo;
-      for (; r + 4 <= r_hi; r += 4) {
-        s0 += stage[(r + 0) * S::EPI_STRIDE + col], s1 += stage[(r + 1) * S::EPI_STRIDE + col];
-        s2 += stage[(r + 2) * S::EPI_STRIDE + col], s3 += stage[(r + 3) * S::EPI_STRIDE + col];
+      // the thread's (at most 64) rows of its column sit in registers between the two passes: every shared-memory load
+      // is issued before the first use
+      constexpr int RMAX = TC_BM / TPC;
+      const int cbase = (col >> 5) * S::EPI_BOX_FLOATS + (col & 3), c0 = (col & 31) >> 2;
+      float v[RMAX];
+#pragma unroll
+      for (int j = 0; j < RMAX; ++j) {
+        const int r = r_lo + j;
+        v[j] = j < cnt ? stage[cbase + r * 32 + ((c0 ^ (r & 7)) << 2)] : 0.f;
       }
-      for (; r < r_hi; ++r) s0 += stage[r * S::EPI_STRIDE + col];
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+      for (int j = 0; j < RMAX; j += 4) s0 += v[j], s1 += v[j + 1], s2 += v[j + 2], s3 += v[j + 3];
       const float s = (s0 + s1) + (s2 + s3);
       const float mean = cnt > 0 ? s / (float)cnt : 0.f;
       float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
-      for (r = r_lo; r + 4 <= r_hi; r += 4) {
-        const float d0 = stage[(r + 0) * S::EPI_STRIDE + col] - mean, d1 = stage[(r + 1) * S::EPI_STRIDE + col] - mean;
-        const float d2 = stage[(r + 2) * S::EPI_STRIDE + col] - mean, d3 = stage[(r + 3) * S::EPI_STRIDE + col] - mean;
+#pragma unroll
+      for (int j = 0; j < RMAX; j += 4) {
+        const float d0 = j + 0 < cnt ? v[j + 0] - mean : 0.f, d1 = j + 1 < cnt ? v[j + 1] - mean : 0.f;
+        const float d2 = j + 2 < cnt ? v[j + 2] - mean : 0.f, d3 = j + 3 < cnt ? v[j + 3] - mean : 0.f;
         q0 = fmaf(d0, d0, q0), q1 = fmaf(d1, d1, q1), q2 = fmaf(d2, d2, q2), q3 = fmaf(d3, d3, q3);
-      }
-      for (; r < r_hi; ++r) {
-        const float d = stage[r * S::EPI_STRIDE + col] - mean;
-        q0 = fmaf(d, d, q0);
       }
       float m2 = (q0 + q1) + (q2 + q3);
       float sum = s;
       if (TPC == 2) {
         asm volatile("bar.sync 1, 128;" ::: "memory");  // every thread is done reading its rows' staging columns
-        float* xch = stage;                              // reuse: [64][2] exchange
+        float* xch = stage + (BN / 32) * S::EPI_BOX_FLOATS;  // [64][2] exchange, past the staging a TMA store may still read
         if (part_id == 1) xch[col * 2] = s, xch[col * 2 + 1] = m2;
         asm volatile("bar.sync 1, 128;" ::: "memory");
         if (part_id == 0) {
@@ -312,6 +338,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2)
             make_float2(sum + bias * (float)nvalid, m2);
       }
     }
+    if (tma_out && t == 0) tma_store_wait_read();  // the staging must outlive the bulk stores' reads
   }
 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -339,7 +366,8 @@ struct PairWgrad {
 
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(TC_THREADS, 2)
-    wgrad_pair_kernel(const __grid_constant__ CUtensorMap mapDY, const __grid_constant__ CUtensorMap mapX, PairWgrad p) {
+    wgrad_pair_kernel(const __grid_constant__ CUtensorMap mapDY, const __grid_constant__ CUtensorMap mapX,
+                      const __grid_constant__ CUtensorMap mapDW, PairWgrad p) {
   using S = PairSmem<BN, STAGES>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -441,14 +469,18 @@ __global__ void __launch_bounds__(TC_THREADS, 2)
         r[i] = __float_as_uint(((__uint_as_float(r[i]) + __uint_as_float(r1[i])) + __uint_as_float(r2[i])) * sc);
 #pragma unroll
       for (int i = 0; i < 8; ++i)
-        *reinterpret_cast<uint4*>(&stage[row * S::EPI_STRIDE + c * 32 + i * 4]) =
+        *reinterpret_cast<uint4*>(&stage[S::epi(row, c * 32 + i * 4)]) =
             make_uint4(r[i * 4], r[i * 4 + 1], r[i * 4 + 2], r[i * 4 + 3]);
     }
+    // the split-K partial tile is added into dW by the TMA unit (fp32 add-reduce; rows past Cout are clipped by the map)
+    fence_proxy_async_smem();
     asm volatile("bar.sync 1, 128;" ::: "memory");
-    const int mvalid = min(TC_BM, p.M - m0);
-    const int col = t % BN;
-    for (int r = t / BN; r < mvalid; r += 128 / BN)
-      atomicAdd(p.dW + (int64_t)(m0 + r) * p.N + n0 + col, stage[r * S::EPI_STRIDE + col]);
+    if (t == 0) {
+#pragma unroll
+      for (int c = 0; c < BN / 32; ++c) tma_reduce_add_3d(&mapDW, stage + c * S::EPI_BOX_FLOATS, n0 + c * 32, m0, 0);
+      tma_store_commit();
+      tma_store_wait_read();
+    }
   }
 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -473,12 +505,15 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 EncodeTiledFn g_enc = nullptr;
+constexpr int kMapF32 = 100;  // encode(): fp32 output tensors (the pair formats are 0 / 1)
 
 bool encode(TcMap* out, int fmt, int rank, const void* base, const cuuint64_t* dims, const cuuint64_t* strides,
             const cuuint32_t* box, CUtensorMapL2promotion promo) {
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-  CUresult r = g_enc(reinterpret_cast<CUtensorMap*>(out->opaque),
-                     fmt == kPairBF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank,
+  const CUtensorMapDataType dt = fmt == kMapF32    ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                                 : fmt == kPairBF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+                                                    : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  CUresult r = g_enc(reinterpret_cast<CUtensorMap*>(out->opaque), dt, (cuuint32_t)rank,
                      const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_128B, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -554,6 +589,24 @@ bool pair_make_rows_map(TcMap* out, const void* planes, int64_t plane_stride, in
   return encode(out, fmt, 3, planes, dims, strides, box, CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
 }
 
+// fp32 conv output [B][out_rows][N], logical rows at out_off..: (channel, row, sample), box 32 x Lout x nb -- one
+// 128-byte-swizzled staging box of the epilogue per 32 channels
+bool pair_make_out_map(TcMap* out, float* C, int N, int Lout, int out_rows, int out_off, int max_batch) {
+  const int nb = TC_BM / Lout;
+  cuuint64_t dims[3] = {(cuuint64_t)N, (cuuint64_t)Lout, (cuuint64_t)max_batch};
+  cuuint64_t strides[2] = {(cuuint64_t)N * 4, (cuuint64_t)out_rows * N * 4};
+  cuuint32_t box[3] = {32, (cuuint32_t)Lout, (cuuint32_t)nb};
+  return encode(out, kMapF32, 3, C + (int64_t)out_off * N, dims, strides, box, CU_TENSOR_MAP_L2_PROMOTION_NONE);
+}
+
+// fp32 weight gradient [M][N]: (n, m, 1), box 32 x 128 x 1
+bool pair_make_dw_map(TcMap* out, float* dW, int M, int N) {
+  cuuint64_t dims[3] = {(cuuint64_t)N, (cuuint64_t)M, 1};
+  cuuint64_t strides[2] = {(cuuint64_t)N * 4, (cuuint64_t)M * N * 4};
+  cuuint32_t box[3] = {32, (cuuint32_t)TC_BM, 1};
+  return encode(out, kMapF32, 3, dW, dims, strides, box, CU_TENSOR_MAP_L2_PROMOTION_NONE);
+}
+
 int pair_pick_bn(int, int, int, int) { return kBN; }
 
 int launch_conv_pair(const ConvGemm& g, const TcMap& mapA, const TcMap& mapB, int bn, int B, const PairOpts& o,
@@ -571,12 +624,14 @@ int launch_conv_pair(const ConvGemm& g, const TcMap& mapA, const TcMap& mapB, in
 
   const CUtensorMap& a = *reinterpret_cast<const CUtensorMap*>(mapA.opaque);
   const CUtensorMap& w = *reinterpret_cast<const CUtensorMap*>(mapB.opaque);
-  launch_pdl(conv_pair_kernel<kBN, kStages>, grid, dim3(TC_THREADS), PairSmem<kBN, kStages>::TOTAL, s, a, w, p);
+  p.tma_out = (o.out_map && g.out_lstride == 1) ? 1 : 0;
+  const CUtensorMap& c = p.tma_out ? *reinterpret_cast<const CUtensorMap*>(o.out_map->opaque) : a;
+  launch_pdl(conv_pair_kernel<kBN, kStages>, grid, dim3(TC_THREADS), PairSmem<kBN, kStages>::TOTAL, s, a, w, c, p);
   return p.nb * g.Lout;
 }
 
-void launch_wgrad_pair(const WgradGemm& g, const TcMap& mapDY, const TcMap& mapX, int bn, int sm_count, const PairOpts& o,
-                       cudaStream_t s) {
+void launch_wgrad_pair(const WgradGemm& g, const TcMap& mapDY, const TcMap& mapX, const TcMap& mapDW, int bn, int sm_count,
+                       const PairOpts& o, cudaStream_t s) {
   PairWgrad p{};
   p.dW = g.dW, p.M = g.M, p.N = g.N, p.R = g.R;
   p.out_scale = o.out_scale, p.dyn_scale = o.dyn_scale;
@@ -593,7 +648,8 @@ void launch_wgrad_pair(const WgradGemm& g, const TcMap& mapDY, const TcMap& mapX
   dim3 grid(g.N / bn, (g.M + TC_BM - 1) / TC_BM, splits);
   const CUtensorMap& a = *reinterpret_cast<const CUtensorMap*>(mapDY.opaque);
   const CUtensorMap& x = *reinterpret_cast<const CUtensorMap*>(mapX.opaque);
-  launch_pdl(wgrad_pair_kernel<kBN, kStages>, grid, dim3(TC_THREADS), PairSmem<kBN, kStages>::TOTAL, s, a, x, p);
+  const CUtensorMap& dw = *reinterpret_cast<const CUtensorMap*>(mapDW.opaque);
+  launch_pdl(wgrad_pair_kernel<kBN, kStages>, grid, dim3(TC_THREADS), PairSmem<kBN, kStages>::TOTAL, s, a, x, dw, p);
 }
 
 void launch_to_pair(const float* src, void* planes, int64_t plane_stride, int64_t n, float scale, int fmt,

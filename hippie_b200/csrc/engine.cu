@@ -58,8 +58,9 @@ struct Conv {
   int id = -1;
 };
 struct ConvMaps {  // TMA tensor maps of the tcgen05 path, built at first use after hippie_bind
-  TcMap a_fwd, w_k, a_dg, w_mn, wg_dy, wg_x;
-  bool fwd_ready = false, dg_ready = false;
+  TcMap a_fwd, w_k, a_dg, w_mn, wg_dy, wg_x, c_fwd, c_dg, dw;
+  bool fwd_ready = false, dg_ready = false, dw_ready = false;
+  const float *c_fwd_ptr = nullptr, *c_dg_ptr = nullptr;  // the output tensors the store maps describe
   int wg_B = -1;  // the wgrad maps bound the reduction rows, so they depend on the batch size
 };
 struct EncBlock {
@@ -171,6 +172,7 @@ struct hippie_engine {
     graphs.clear();
   }
   std::vector<ConvMaps> cmaps;
+  bool tma_epilogue = true;  // conv outputs leave through TMA tensor stores (HIPPIE_B200_TMA_STORE=0: per-thread stores)
   bool use_tc = false;  // tcgen05 implicit GEMMs over fp16 pair planes (conv_path 0); false = FP32 CUDA-core GEMMs
   std::string tc_note;
   int64_t wp_off = 0;     // weight pair planes: hi plane at ws + wp_off (as halfs), lo plane param_floats elements later
@@ -584,9 +586,15 @@ struct hippie_engine {
         if (!ok) return (void)(err = "cuTensorMapEncodeTiled failed (conv forward)", failed = true);
         m.fwd_ready = true;
       }
+      if (!fold && !g.bias && m.c_fwd_ptr != g.C) {  // plain fp32 output: whole tiles leave through TMA stores
+        if (!pair_make_out_map(&m.c_fwd, g.C, g.N, g.Lout, g.out_rows, g.out_off, cfg.max_batch))
+          return (void)(err = "cuTensorMapEncodeTiled failed (conv forward output)", failed = true);
+        m.c_fwd_ptr = g.C;
+      }
       const int bn_tile = pair_pick_bn(B, g.N, g.Lout, sm_count);
       PairOpts o{1.f / kWeightPairScale, kPairF16, kPairF16, 0, cv.k};
       o.fold = fold;
+      if (!fold && !g.bias && tma_epilogue) o.out_map = &m.c_fwd;
       tile = launch_conv_pair(g, m.a_fwd, m.w_k, bn_tile, B, o, br.st);
     } else {
       tile = launch_conv_gemm_simt(g, br.st);
@@ -641,9 +649,15 @@ struct hippie_engine {
         if (!ok) return (void)(err = "cuTensorMapEncodeTiled failed (conv dgrad)", failed = true);
         m.dg_ready = true;
       }
+      if (m.c_dg_ptr != g.C) {
+        if (!pair_make_out_map(&m.c_dg, g.C, g.N, g.Lout, g.out_rows, g.out_off, cfg.max_batch))
+          return (void)(err = "cuTensorMapEncodeTiled failed (conv dgrad output)", failed = true);
+        m.c_dg_ptr = g.C;
+      }
       const int bn_tile = pair_pick_bn(B, g.N, g.Lout, sm_count);
       PairOpts o{1.f / kWeightPairScale, kPairF16, kPairF16, 1, cv.k};
       o.dyn_scale = slot(dy) + 3;
+      if (tma_epilogue) o.out_map = &m.c_dg;
       launch_conv_pair(g, m.a_dg, m.w_mn, bn_tile, B, o, br.st);
     } else {
       launch_conv_gemm_simt(g, br.st);
@@ -673,9 +687,14 @@ struct hippie_engine {
         if (!ok) return (void)(err = "cuTensorMapEncodeTiled failed (conv wgrad)", failed = true);
         m.wg_B = B;
       }
+      if (!m.dw_ready) {
+        if (!pair_make_dw_map(&m.dw, g.dW, g.M, g.N))
+          return (void)(err = "cuTensorMapEncodeTiled failed (conv wgrad output)", failed = true);
+        m.dw_ready = true;
+      }
       PairOpts o{1.f, kPairF16, kPairF16, 1, cv.k};
       o.dyn_scale = slot(dy) + 3;
-      launch_wgrad_pair(g, m.wg_dy, m.wg_x, pair_pick_bn(B, g.N, 1, sm_count), sm_count, o, wst);
+      launch_wgrad_pair(g, m.wg_dy, m.wg_x, m.dw, pair_pick_bn(B, g.N, 1, sm_count), sm_count, o, wst);
     } else {
       launch_wgrad_simt(g, sm_count, wst);
     }
@@ -1175,6 +1194,7 @@ int hippie_bind(hippie_handle h, float* params, float* grads, float* exp_avg, fl
   h->bn_mean = bn_mean, h->bn_var = bn_var, h->bn_count = bn_count, h->ws = (float*)workspace;
   h->clear_graphs();
   if (const char* g = getenv("HIPPIE_B200_GRAPHS")) h->use_graphs = atoi(g) != 0;
+  if (const char* g = getenv("HIPPIE_B200_TMA_STORE")) h->tma_epilogue = atoi(g) != 0;
   if (!h->side) {
     // the branch chains are the critical path: they get the highest priority, the weight-gradient streams the lowest
     int prio_lo = 0, prio_hi = 0;

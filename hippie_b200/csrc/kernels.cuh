@@ -78,6 +78,7 @@ struct PairOpts {
   const float* dyn_scale = nullptr;  // device float multiplied into out_scale (1 / scale of a gradient pair tensor)
   unsigned long long* stamps = nullptr;  // tools/pair_test: 8 device slots for %globaltimer phase stamps of CTA (0, 0)
   const EvalFold* fold = nullptr;        // conv forward in eval mode
+  const TcMap* out_map = nullptr;        // conv: fp32 output tensor map (pair_make_out_map) -> TMA stores of whole tiles
 };
 bool pair_init(std::string* err);
 bool pair_make_act_map(TcMap* out, const void* planes, int64_t plane_stride, int fmt, int in_C, int K, int Lout,
@@ -86,11 +87,13 @@ bool pair_make_w_map(TcMap* out, const void* planes, int64_t plane_stride, int f
 bool pair_make_wmn_map(TcMap* out, const void* planes, int64_t plane_stride, int fmt, int Cout, int Cin, int k);
 bool pair_make_rows_map(TcMap* out, const void* planes, int64_t plane_stride, int fmt, int64_t row_elems, int channels,
                         int rows);
+bool pair_make_out_map(TcMap* out, float* C, int N, int Lout, int out_rows, int out_off, int max_batch);
+bool pair_make_dw_map(TcMap* out, float* dW, int M, int N);
 int pair_pick_bn(int B, int N, int Lout, int sm_count);
 int launch_conv_pair(const ConvGemm& g, const TcMap& mapA, const TcMap& mapB, int bn, int B, const PairOpts& o,
                      cudaStream_t s);
-void launch_wgrad_pair(const WgradGemm& g, const TcMap& mapDY, const TcMap& mapX, int bn, int sm_count, const PairOpts& o,
-                       cudaStream_t s);
+void launch_wgrad_pair(const WgradGemm& g, const TcMap& mapDY, const TcMap& mapX, const TcMap& mapDW, int bn, int sm_count,
+                       const PairOpts& o, cudaStream_t s);
 // planes[0 .. n) = hi(src * scale), planes[plane_stride .. plane_stride + n) = lo
 void launch_to_pair(const float* src, void* planes, int64_t plane_stride, int64_t n, float scale, int fmt, cudaStream_t s);
 

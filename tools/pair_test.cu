@@ -97,6 +97,15 @@ static void test_conv(int B, int L, int Cin, int Cout, int k, int stride, bool b
     return;
   }
   PairOpts o{1.f / wscale, a_fmt, b_fmt, 0, k};
+  TcMap mc;
+  const bool tma_out = !getenv("PT_TMA") || atoi(getenv("PT_TMA"));
+  if (tma_out) {
+    if (!pair_make_out_map(&mc, g2.C, Cout, Lout, g.out_rows, g.out_off, B)) {
+      printf("conv: output tensor map creation FAILED\n");
+      return;
+    }
+    o.out_map = &mc;
+  }
   const int tile2 = launch_conv_pair(g2, ma, mw, bn, B, o, 0);
   CK(cudaDeviceSynchronize());
   std::vector<float> r1(out_floats), r2(out_floats);
@@ -195,6 +204,14 @@ static void test_dgrad(int B, int L, int Cin, int Cout, int k, int a_fmt, int b_
     return;
   }
   PairOpts o{1.f / wscale, a_fmt, b_fmt, 1, k};
+  TcMap mc;
+  if (!getenv("PT_TMA") || atoi(getenv("PT_TMA"))) {
+    if (!pair_make_out_map(&mc, g2.C, Cin, L, g.out_rows, g.out_off, B)) {
+      printf("dgrad: output tensor map creation FAILED\n");
+      return;
+    }
+    o.out_map = &mc;
+  }
   launch_conv_pair(g2, ma, mw, bn, B, o, 0);
   CK(cudaDeviceSynchronize());
   std::vector<float> r1(gx_floats), r2(gx_floats);
@@ -232,15 +249,20 @@ static void test_wgrad(int B, int L, int Cin, int Cout, int k, int a_fmt, int b_
     printf("wgrad: tensor map creation FAILED\n");
     return;
   }
+  TcMap mdw;
+  if (!pair_make_dw_map(&mdw, dw2, Cout, N)) {
+    printf("wgrad: output tensor map creation FAILED\n");
+    return;
+  }
   PairOpts o{1.f, a_fmt, b_fmt, 1, k};
-  launch_wgrad_pair(g2, my, mx, bn, 148, o, 0);
+  launch_wgrad_pair(g2, my, mx, mdw, bn, 148, o, 0);
   CK(cudaDeviceSynchronize());
   std::vector<float> r1((size_t)Cout * N), r2((size_t)Cout * N);
   CK(cudaMemcpy(r1.data(), dw1, r1.size() * 4, cudaMemcpyDeviceToHost));
   CK(cudaMemcpy(r2.data(), dw2, r2.size() * 4, cudaMemcpyDeviceToHost));
   double mr, md = compare(r2, r1, &mr);
   const float t1 = time_ms([&] { launch_wgrad_simt(g1, 148, 0); }, 20);
-  const float t2 = time_ms([&] { launch_wgrad_pair(g2, my, mx, bn, 148, o, 0); }, 20);
+  const float t2 = time_ms([&] { launch_wgrad_pair(g2, my, mx, mdw, bn, 148, o, 0); }, 20);
   const double fl = 2.0 * Cout * (double)N * R;
   printf("wgrad B=%4d L=%3d %3d->%3d k%d a%d b%d bn%3d | rel err %.2e | simt %7.1f us %6.1f TF | pair %7.1f us %6.1f TF\n", B, L, Cin,
          Cout, k, a_fmt, b_fmt, bn, md / mr, t1 * 1e3, fl / t1 / 1e9, t2 * 1e3, fl / t2 / 1e9);
