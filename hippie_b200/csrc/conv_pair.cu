@@ -17,7 +17,7 @@
 // Per CTA (192 threads): warp 0 TMA producer, warp 1 TMEM allocator + MMA issuer, warps 2-5 epilogue
 // (TMEM -> registers -> swizzled shared staging -> ONE elected thread issues TMA tensor stores of the whole tile
 // (add-reduce when the layer accumulates into its output) while the four warps compute the BatchNorm (sum, centred M2)
-// partials from the same staging; tiles with a bias, an eval-mode fold or a ragged batch edge use per-thread stores).
+// partials from the same staging; the eval-mode fold uses per-thread stores).
 // The tensor core truncates when it adds into the fp32 accumulator; to keep that bias below the parity bound the
 // hi*hi products alternate between two accumulators and the small cross terms use a third (summed with
 // round-to-nearest in the epilogue).
@@ -218,14 +218,24 @@ __global__ void __launch_bounds__(TC_THREADS, 2)
 #pragma unroll
       for (int i = 0; i < 32; ++i)
         r[i] = __float_as_uint(((__uint_as_float(r[i]) + __uint_as_float(r1[i])) + __uint_as_float(r2[i])) * sc);
+      if (p.bias) {  // warp-uniform addresses: broadcast loads
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c * 32 + i * 4));
+          r[i * 4 + 0] = __float_as_uint(__uint_as_float(r[i * 4 + 0]) + bv.x);
+          r[i * 4 + 1] = __float_as_uint(__uint_as_float(r[i * 4 + 1]) + bv.y);
+          r[i * 4 + 2] = __float_as_uint(__uint_as_float(r[i * 4 + 2]) + bv.z);
+          r[i * 4 + 3] = __float_as_uint(__uint_as_float(r[i * 4 + 3]) + bv.w);
+        }
+      }
 #pragma unroll
       for (int i = 0; i < 8; ++i)
         *reinterpret_cast<uint4*>(&stage[S::epi(row, c * 32 + i * 4)]) =
             make_uint4(r[i * 4], r[i * 4 + 1], r[i * 4 + 2], r[i * 4 + 3]);
     }
     const int nvalid = min(rows_tile, (p.B - b0) * p.Lout);  // rows of this tile that are real outputs
-    // whole tiles without a bias / fold go out through the TMA unit (it skips the pad rows by construction of mapC)
-    const bool tma_out = p.tma_out && nvalid == rows_tile && !p.bias && !p.fold.coef;
+    // training-mode tiles go out through the TMA unit (it skips the pad rows by construction of mapC)
+    const bool tma_out = p.tma_out && !p.fold.coef;  // mapC ends at the batch size: a ragged last tile is clipped by the unit
     if (tma_out) fence_proxy_async_smem();
     asm volatile("bar.sync 1, 128;" ::: "memory");  // the four epilogue warps only
     if (t == 0) stamp(p, 4);
@@ -244,8 +254,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2)
     } else {  // coalesced stores: thread -> (row group, fixed column quad)
       constexpr int QUADS = BN / 4;
       const int quad = t % QUADS;
-      float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (p.bias) bv = *reinterpret_cast<const float4*>(p.bias + n0 + quad * 4);
+      const float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
       const EvalFold& fo = p.fold;
       float4 fsc = bv, fbe = bv, fmu = bv;
       if (fo.coef) {
@@ -256,7 +265,6 @@ __global__ void __launch_bounds__(TC_THREADS, 2)
       for (int r = t / QUADS; r < nvalid; r += 128 / QUADS) {
         const int bs = r / p.Lout, l = r - bs * p.Lout;
         float4 v = *reinterpret_cast<const float4*>(&stage[S::epi(r, quad * 4)]);
-        v.x += bv.x, v.y += bv.y, v.z += bv.z, v.w += bv.w;
         const int64_t off = ((int64_t)(b0 + bs) * p.out_rows + p.out_off + (int64_t)l * p.out_lstride) * p.N + n0 + quad * 4;
         float4* dst = reinterpret_cast<float4*>(p.C + off);
         if (p.accumulate) {
@@ -333,9 +341,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2)
         }
       }
       if (part_id == 0) {
-        const float bias = p.bias ? p.bias[n0 + col] : 0.f;
-        *reinterpret_cast<float2*>(p.part + ((int64_t)blockIdx.x * p.N + n0 + col) * 2) =
-            make_float2(sum + bias * (float)nvalid, m2);
+        *reinterpret_cast<float2*>(p.part + ((int64_t)blockIdx.x * p.N + n0 + col) * 2) = make_float2(sum, m2);
       }
     }
     if (tma_out && t == 0) tma_store_wait_read();  // the staging must outlive the bulk stores' reads
@@ -591,9 +597,9 @@ bool pair_make_rows_map(TcMap* out, const void* planes, int64_t plane_stride, in
 
 // fp32 conv output [B][out_rows][N], logical rows at out_off..: (channel, row, sample), box 32 x Lout x nb -- one
 // 128-byte-swizzled staging box of the epilogue per 32 channels
-bool pair_make_out_map(TcMap* out, float* C, int N, int Lout, int out_rows, int out_off, int max_batch) {
+bool pair_make_out_map(TcMap* out, float* C, int N, int Lout, int out_rows, int out_off, int batch) {
   const int nb = TC_BM / Lout;
-  cuuint64_t dims[3] = {(cuuint64_t)N, (cuuint64_t)Lout, (cuuint64_t)max_batch};
+  cuuint64_t dims[3] = {(cuuint64_t)N, (cuuint64_t)Lout, (cuuint64_t)batch};  // rows past the batch are clipped
   cuuint64_t strides[2] = {(cuuint64_t)N * 4, (cuuint64_t)out_rows * N * 4};
   cuuint32_t box[3] = {32, (cuuint32_t)Lout, (cuuint32_t)nb};
   return encode(out, kMapF32, 3, C + (int64_t)out_off * N, dims, strides, box, CU_TENSOR_MAP_L2_PROMOTION_NONE);

@@ -60,7 +60,8 @@ struct Conv {
 struct ConvMaps {  // TMA tensor maps of the tcgen05 path, built at first use after hippie_bind
   TcMap a_fwd, w_k, a_dg, w_mn, wg_dy, wg_x, c_fwd, c_dg, dw;
   bool fwd_ready = false, dg_ready = false, dw_ready = false;
-  const float *c_fwd_ptr = nullptr, *c_dg_ptr = nullptr;  // the output tensors the store maps describe
+  const float *c_fwd_ptr = nullptr, *c_dg_ptr = nullptr;  // the output tensors the store maps describe ...
+  int c_fwd_B = -1, c_dg_B = -1;                          // ... and the batch size they end at
   int wg_B = -1;  // the wgrad maps bound the reduction rows, so they depend on the batch size
 };
 struct EncBlock {
@@ -586,15 +587,15 @@ struct hippie_engine {
         if (!ok) return (void)(err = "cuTensorMapEncodeTiled failed (conv forward)", failed = true);
         m.fwd_ready = true;
       }
-      if (!fold && !g.bias && m.c_fwd_ptr != g.C) {  // plain fp32 output: whole tiles leave through TMA stores
-        if (!pair_make_out_map(&m.c_fwd, g.C, g.N, g.Lout, g.out_rows, g.out_off, cfg.max_batch))
+      if (!fold && (m.c_fwd_ptr != g.C || m.c_fwd_B != B)) {  // fp32 output: tiles leave through TMA stores
+        if (!pair_make_out_map(&m.c_fwd, g.C, g.N, g.Lout, g.out_rows, g.out_off, B))
           return (void)(err = "cuTensorMapEncodeTiled failed (conv forward output)", failed = true);
-        m.c_fwd_ptr = g.C;
+        m.c_fwd_ptr = g.C, m.c_fwd_B = B;
       }
       const int bn_tile = pair_pick_bn(B, g.N, g.Lout, sm_count);
       PairOpts o{1.f / kWeightPairScale, kPairF16, kPairF16, 0, cv.k};
       o.fold = fold;
-      if (!fold && !g.bias && tma_epilogue) o.out_map = &m.c_fwd;
+      if (!fold && tma_epilogue) o.out_map = &m.c_fwd;
       tile = launch_conv_pair(g, m.a_fwd, m.w_k, bn_tile, B, o, br.st);
     } else {
       tile = launch_conv_gemm_simt(g, br.st);
@@ -649,10 +650,10 @@ struct hippie_engine {
         if (!ok) return (void)(err = "cuTensorMapEncodeTiled failed (conv dgrad)", failed = true);
         m.dg_ready = true;
       }
-      if (m.c_dg_ptr != g.C) {
-        if (!pair_make_out_map(&m.c_dg, g.C, g.N, g.Lout, g.out_rows, g.out_off, cfg.max_batch))
+      if (m.c_dg_ptr != g.C || m.c_dg_B != B) {
+        if (!pair_make_out_map(&m.c_dg, g.C, g.N, g.Lout, g.out_rows, g.out_off, B))
           return (void)(err = "cuTensorMapEncodeTiled failed (conv dgrad output)", failed = true);
-        m.c_dg_ptr = g.C;
+        m.c_dg_ptr = g.C, m.c_dg_B = B;
       }
       const int bn_tile = pair_pick_bn(B, g.N, g.Lout, sm_count);
       PairOpts o{1.f / kWeightPairScale, kPairF16, kPairF16, 1, cv.k};

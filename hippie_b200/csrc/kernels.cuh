@@ -87,7 +87,7 @@ bool pair_make_w_map(TcMap* out, const void* planes, int64_t plane_stride, int f
 bool pair_make_wmn_map(TcMap* out, const void* planes, int64_t plane_stride, int fmt, int Cout, int Cin, int k);
 bool pair_make_rows_map(TcMap* out, const void* planes, int64_t plane_stride, int fmt, int64_t row_elems, int channels,
                         int rows);
-bool pair_make_out_map(TcMap* out, float* C, int N, int Lout, int out_rows, int out_off, int max_batch);
+bool pair_make_out_map(TcMap* out, float* C, int N, int Lout, int out_rows, int out_off, int batch);
 bool pair_make_dw_map(TcMap* out, float* dW, int M, int N);
 int pair_pick_bn(int B, int N, int Lout, int sm_count);
 int launch_conv_pair(const ConvGemm& g, const TcMap& mapA, const TcMap& mapB, int bn, int B, const PairOpts& o,
