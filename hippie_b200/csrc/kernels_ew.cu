@@ -331,6 +331,7 @@ __device__ __forceinline__ float block_max(float v, float* red) {  // 256 thread
 
 // part[chunk][C][3] = (S1, S2, S2s);  slot = (max|g_pre|, max|xhat|, max|gamma*invstd|, 1/scale) as atomicMax targets
 // (non-negative floats order like their bit patterns; the slots are zeroed once per step by the engine)
+template <int U>
 __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(BnBwd a, int rows_per_cta) {
   __shared__ float4 red[3][256];
   __shared__ float mred[8];
@@ -360,7 +361,6 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(BnBwd a, int rows_pe
                             make_float4(ga.x * iss.x, ga.y * iss.y, ga.z * iss.z, ga.w * iss.w)));
       }
     }
-    constexpr int U = 2;
     for (int m0 = m_begin + rl; m0 < m_end; m0 += RL * U) {
       float4 gv[U], ov[U], xv[U], xsv[U];
 #pragma unroll
@@ -1022,7 +1022,7 @@ void launch_bn_bwd(const BnBwd& a, int sm_count, cudaStream_t s) {
   int rows = (M + kBnBwdMaxChunks - 1) / kBnBwdMaxChunks;
   if (rows < 16) rows = 16;
   const int nchunks = (M + rows - 1) / rows;
-  launch_pdl(bn_bwd_reduce_kernel, dim3(nchunks), dim3(256), 0, s, a, rows);
+  launch_pdl(bn_bwd_reduce_kernel<4>, dim3(nchunks), dim3(256), 0, s, a, rows);
   dim3 grid(a.C / kSlab, slab_row_chunks(M, a.C, sm_count));
   launch_pdl(bn_bwd_apply_kernel, grid, dim3(256), 0, s, a, nchunks);
 }
