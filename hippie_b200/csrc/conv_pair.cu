@@ -98,7 +98,9 @@ struct PairSmem {
   static constexpr int TMEM_COLS = BN == 128 ? 512 : 256;  // three accumulators of BN columns (power of two)
 };
 
-template <int BN, int STAGES>
+// EVAL = true: the eval-mode instantiation (BatchNorm folded into the epilogue, per-thread stores, no statistics);
+// false: training forward / dgrad (TMA stores, BatchNorm partials).  Two instantiations keep each epilogue's code lean.
+template <int BN, int STAGES, bool EVAL>
 __global__ void __launch_bounds__(TC_THREADS, 2)
     conv_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                      const __grid_constant__ CUtensorMap mapC, PairConv p) {
@@ -235,7 +237,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2)
     }
     const int nvalid = min(rows_tile, (p.B - b0) * p.Lout);  // rows of this tile that are real outputs
     // training-mode tiles go out through the TMA unit (it skips the pad rows by construction of mapC)
-    const bool tma_out = p.tma_out && !p.fold.coef;  // mapC ends at the batch size: a ragged last tile is clipped by the unit
+    const bool tma_out = !EVAL && p.tma_out;  // mapC ends at the batch size: a ragged last tile is clipped by the unit
     if (tma_out) fence_proxy_async_smem();
     asm volatile("bar.sync 1, 128;" ::: "memory");  // the four epilogue warps only
     if (t == 0) stamp(p, 4);
@@ -257,7 +259,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2)
       const float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
       const EvalFold& fo = p.fold;
       float4 fsc = bv, fbe = bv, fmu = bv;
-      if (fo.coef) {
+      if (EVAL && fo.coef) {
         fsc = *reinterpret_cast<const float4*>(fo.coef + 0 * p.N + n0 + quad * 4);
         fbe = *reinterpret_cast<const float4*>(fo.coef + 1 * p.N + n0 + quad * 4);
         fmu = *reinterpret_cast<const float4*>(fo.coef + 2 * p.N + n0 + quad * 4);
@@ -271,7 +273,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2)
           const float4 o = *dst;
           v.x += o.x, v.y += o.y, v.z += o.z, v.w += o.w;
         }
-        if (fo.coef) {  // same expressions as bn_apply_kernel: the folded result is bit-identical to conv + apply
+        if (EVAL && fo.coef) {  // same expressions as bn_apply_kernel: the folded result is bit-identical to conv + apply
           float4 y;
           y.x = fmaf(v.x - fmu.x, fsc.x, fbe.x), y.y = fmaf(v.y - fmu.y, fsc.y, fbe.y);
           y.z = fmaf(v.z - fmu.z, fsc.z, fbe.z), y.w = fmaf(v.w - fmu.w, fsc.w, fbe.w);
@@ -294,7 +296,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2)
       }
     }
     if (t == 0) stamp(p, 5);
-    if (p.part) {  // BatchNorm statistics of this tile: (sum, centred sum of squares) per column
+    if (!EVAL && p.part) {  // BatchNorm statistics of this tile: (sum, centred sum of squares) per column
       // BN == 64: two threads per column (rows split in halves, combined with Chan's formula through shared memory)
       constexpr int TPC = 128 / BN;  // threads per column
       const int col = t % BN, part_id = t / BN;
@@ -548,7 +550,9 @@ bool pair_init(std::string* err) {
     g_enc = reinterpret_cast<EncodeTiledFn>(fn);
   }
   // function attributes belong to the current device's context: set them on every bind
-  cudaFuncSetAttribute(conv_pair_kernel<kBN, kStages>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  cudaFuncSetAttribute(conv_pair_kernel<kBN, kStages, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                       PairSmem<kBN, kStages>::TOTAL);
+  cudaFuncSetAttribute(conv_pair_kernel<kBN, kStages, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                        PairSmem<kBN, kStages>::TOTAL);
   cudaFuncSetAttribute(wgrad_pair_kernel<kBN, kStages>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                        PairSmem<kBN, kStages>::TOTAL);
@@ -632,7 +636,10 @@ int launch_conv_pair(const ConvGemm& g, const TcMap& mapA, const TcMap& mapB, in
   const CUtensorMap& w = *reinterpret_cast<const CUtensorMap*>(mapB.opaque);
   p.tma_out = (o.out_map && g.out_lstride == 1) ? 1 : 0;
   const CUtensorMap& c = p.tma_out ? *reinterpret_cast<const CUtensorMap*>(o.out_map->opaque) : a;
-  launch_pdl(conv_pair_kernel<kBN, kStages>, grid, dim3(TC_THREADS), PairSmem<kBN, kStages>::TOTAL, s, a, w, c, p);
+  if (o.fold)
+    launch_pdl(conv_pair_kernel<kBN, kStages, true>, grid, dim3(TC_THREADS), PairSmem<kBN, kStages>::TOTAL, s, a, w, c, p);
+  else
+    launch_pdl(conv_pair_kernel<kBN, kStages, false>, grid, dim3(TC_THREADS), PairSmem<kBN, kStages>::TOTAL, s, a, w, c, p);
   return p.nb * g.Lout;
 }
 
