@@ -98,12 +98,16 @@ struct PairSmem {
   static constexpr int TMEM_COLS = BN == 128 ? 512 : 256;  // three accumulators of BN columns (power of two)
 };
 
-// EVAL = true: the eval-mode instantiation (BatchNorm folded into the epilogue, per-thread stores, no statistics);
-// false: training forward / dgrad (TMA stores, BatchNorm partials).  Two instantiations keep each epilogue's code lean.
-template <int BN, int STAGES, bool EVAL>
+// MODE: kConvTrain = training forward (K-major weights, bias, BatchNorm partials, TMA stores), kConvEval = eval forward
+// (BatchNorm folded into the epilogue, per-thread stores, no statistics), kConvDgrad = dgrad (MN-major weights, dynamic
+// scale, TMA store / add-reduce).  One instantiation per mode keeps each pipeline's code lean: with all three in one
+// kernel the eval epilogue ran 30 % slower (register allocation), measured on the embedding pass.
+constexpr int kConvTrain = 0, kConvEval = 1, kConvDgrad = 2;
+template <int BN, int STAGES, int MODE>
 __global__ void __launch_bounds__(TC_THREADS, 2)
     conv_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                      const __grid_constant__ CUtensorMap mapC, PairConv p) {
+  constexpr bool EVAL = MODE == kConvEval, B_MN = MODE == kConvDgrad;
   using S = PairSmem<BN, STAGES>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -155,7 +159,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2)
         mbar_expect_tx(&full[s], tx_bytes);
         tma_load_4d(st, &mapA, &full[s], kb * PK, 0, b0, 0);
         tma_load_4d(st + S::A_LO, &mapA, &full[s], kb * PK, 0, b0, 1);
-        if (!p.b_mn) {
+        if (!B_MN) {
           tma_load_3d(st + S::B_OFF, &mapB, &full[s], kb * PK, n0, 0);
           tma_load_3d(st + S::B_LO, &mapB, &full[s], kb * PK, n0, 1);
         } else {
@@ -181,7 +185,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2)
         const uint32_t st = smem_u32(ring + s * S::STAGE_BYTES);
         const uint64_t a_hi = umma_desc(st, 16, 1024, 2), a_lo = umma_desc(st + S::A_LO, 16, 1024, 2);
         uint64_t b_hi, b_lo, badv;
-        if (!p.b_mn) {  // K-major: 8-row groups 1024 B apart, 16 halfs = 32 B along the swizzled row per step
+        if (!B_MN) {  // K-major: 8-row groups 1024 B apart, 16 halfs = 32 B along the swizzled row per step
           b_hi = umma_desc(st + S::B_OFF, 16, 1024, 2), b_lo = umma_desc(st + S::B_LO, 16, 1024, 2);
           badv = 32 >> 4;
         } else {  // MN-major: groups of 64 columns 8 KB apart (LBO), 8 k-rows 1024 B apart (SBO), 16 k-rows per step
@@ -220,7 +224,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2)
 #pragma unroll
       for (int i = 0; i < 32; ++i)
         r[i] = __float_as_uint(((__uint_as_float(r[i]) + __uint_as_float(r1[i])) + __uint_as_float(r2[i])) * sc);
-      if (p.bias) {  // warp-uniform addresses: broadcast loads
+      if (!B_MN && p.bias) {  // warp-uniform addresses: broadcast loads
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c * 32 + i * 4));
@@ -246,7 +250,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2)
       if (t == 0) {
 #pragma unroll
         for (int c = 0; c < BN / 32; ++c) {
-          if (p.accumulate)
+          if (B_MN && p.accumulate)
             tma_reduce_add_3d(&mapC, stage + c * S::EPI_BOX_FLOATS, n0 + c * 32, 0, b0);
           else
             tma_store_3d(&mapC, stage + c * S::EPI_BOX_FLOATS, n0 + c * 32, 0, b0);
@@ -269,7 +273,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2)
         float4 v = *reinterpret_cast<const float4*>(&stage[S::epi(r, quad * 4)]);
         const int64_t off = ((int64_t)(b0 + bs) * p.out_rows + p.out_off + (int64_t)l * p.out_lstride) * p.N + n0 + quad * 4;
         float4* dst = reinterpret_cast<float4*>(p.C + off);
-        if (p.accumulate) {
+        if (B_MN && p.accumulate) {
           const float4 o = *dst;
           v.x += o.x, v.y += o.y, v.z += o.z, v.w += o.w;
         }
@@ -296,7 +300,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2)
       }
     }
     if (t == 0) stamp(p, 5);
-    if (!EVAL && p.part) {  // BatchNorm statistics of this tile: (sum, centred sum of squares) per column
+    if (MODE == kConvTrain && p.part) {  // BatchNorm statistics of this tile: (sum, centred sum of squares) per column
       // BN == 64: two threads per column (rows split in halves, combined with Chan's formula through shared memory)
       constexpr int TPC = 128 / BN;  // threads per column
       const int col = t % BN, part_id = t / BN;
@@ -550,9 +554,11 @@ bool pair_init(std::string* err) {
     g_enc = reinterpret_cast<EncodeTiledFn>(fn);
   }
   // function attributes belong to the current device's context: set them on every bind
-  cudaFuncSetAttribute(conv_pair_kernel<kBN, kStages, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  cudaFuncSetAttribute(conv_pair_kernel<kBN, kStages, kConvTrain>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                        PairSmem<kBN, kStages>::TOTAL);
-  cudaFuncSetAttribute(conv_pair_kernel<kBN, kStages, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  cudaFuncSetAttribute(conv_pair_kernel<kBN, kStages, kConvEval>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                       PairSmem<kBN, kStages>::TOTAL);
+  cudaFuncSetAttribute(conv_pair_kernel<kBN, kStages, kConvDgrad>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                        PairSmem<kBN, kStages>::TOTAL);
   cudaFuncSetAttribute(wgrad_pair_kernel<kBN, kStages>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                        PairSmem<kBN, kStages>::TOTAL);
@@ -636,10 +642,12 @@ int launch_conv_pair(const ConvGemm& g, const TcMap& mapA, const TcMap& mapB, in
   const CUtensorMap& w = *reinterpret_cast<const CUtensorMap*>(mapB.opaque);
   p.tma_out = (o.out_map && g.out_lstride == 1) ? 1 : 0;
   const CUtensorMap& c = p.tma_out ? *reinterpret_cast<const CUtensorMap*>(o.out_map->opaque) : a;
-  if (o.fold)
-    launch_pdl(conv_pair_kernel<kBN, kStages, true>, grid, dim3(TC_THREADS), PairSmem<kBN, kStages>::TOTAL, s, a, w, c, p);
+  if (o.b_mn)
+    launch_pdl(conv_pair_kernel<kBN, kStages, kConvDgrad>, grid, dim3(TC_THREADS), PairSmem<kBN, kStages>::TOTAL, s, a, w, c, p);
+  else if (o.fold)
+    launch_pdl(conv_pair_kernel<kBN, kStages, kConvEval>, grid, dim3(TC_THREADS), PairSmem<kBN, kStages>::TOTAL, s, a, w, c, p);
   else
-    launch_pdl(conv_pair_kernel<kBN, kStages, false>, grid, dim3(TC_THREADS), PairSmem<kBN, kStages>::TOTAL, s, a, w, c, p);
+    launch_pdl(conv_pair_kernel<kBN, kStages, kConvTrain>, grid, dim3(TC_THREADS), PairSmem<kBN, kStages>::TOTAL, s, a, w, c, p);
   return p.nb * g.Lout;
 }
 
