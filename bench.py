@@ -171,6 +171,9 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        # stdout carries exactly one JSON line: NCCL's own banner ("NCCL version ...", printed when NCCL_DEBUG is set in
+        # the environment) goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     from hippie_b200.model import MultiModalCVAE, MultiModalCVAETrainModule
     from hippie_b200.parallel import train_step_overlapped
@@ -350,7 +353,7 @@ def main():
         "1.4 PFLOP/s sustained (of fallback, B200_PROFILING.md)"
     step_tflops = value / world * F_TRAIN / 1e12
     roofline = {"bound": "tensor", "achieved": None, "peak": peak_tf, "unit": "TFLOP/s", "frac": None, "traffic": None,
-                "kernel": "conv_pair_kernel<64,2> (conv forward + dgrad implicit GEMM, tcgen05 kind::f16 on fp16 pair planes)",
+                "kernel": "conv_pair_kernel<64,2,mode> (conv forward + dgrad implicit GEMM, tcgen05 kind::f16 on fp16 pair planes; one instantiation per mode)",
                 "peak_source": peak_src,
                 "note": "achieved = algorithmic FLOP / CUDA-event time of the kernel's launches in one step; the kernel issues 3 "
                         "MMAs per algorithmic product (hi*hi + hi*lo + lo*hi), so frac <= 1/3 by construction",
