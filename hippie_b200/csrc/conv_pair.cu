@@ -57,6 +57,7 @@ struct PairConv {
   float* C;
   const float* bias;
   float* part;
+  double* tot;
   int B, N, K;
   int Lout, nb;
   int out_rows, out_off, out_lstride, accumulate;
@@ -300,7 +301,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2)
       }
     }
     if (t == 0) stamp(p, 5);
-    if (MODE == kConvTrain && p.part) {  // BatchNorm statistics of this tile: (sum, centred sum of squares) per column
+    if (MODE == kConvTrain && (p.part || p.tot)) {  // BatchNorm statistics of this tile: (sum, centred sum of squares) per column
       // BN == 64: two threads per column (rows split in halves, combined with Chan's formula through shared memory)
       constexpr int TPC = 128 / BN;  // threads per column
       const int col = t % BN, part_id = t / BN;
@@ -347,7 +348,13 @@ __global__ void __launch_bounds__(TC_THREADS, 2)
         }
       }
       if (part_id == 0) {
-        *reinterpret_cast<float2*>(p.part + ((int64_t)blockIdx.x * p.N + n0 + col) * 2) = make_float2(sum, m2);
+        if (p.tot) {  // per-channel totals (sum x, sum x^2): exact enough in double, no per-tile partials to re-read
+          const double sd = (double)sum;
+          atomicAdd(p.tot + n0 + col, sd);
+          atomicAdd(p.tot + p.N + n0 + col, (double)m2 + sd * sd / (double)nvalid);
+        } else {
+          *reinterpret_cast<float2*>(p.part + ((int64_t)blockIdx.x * p.N + n0 + col) * 2) = make_float2(sum, m2);
+        }
       }
     }
     if (tma_out && t == 0) tma_store_wait_read();  // the staging must outlive the bulk stores' reads
@@ -628,7 +635,7 @@ int pair_pick_bn(int, int, int, int) { return kBN; }
 int launch_conv_pair(const ConvGemm& g, const TcMap& mapA, const TcMap& mapB, int bn, int B, const PairOpts& o,
                      cudaStream_t s) {
   PairConv p{};
-  p.C = g.C, p.bias = g.bias, p.part = g.part, p.B = B, p.N = g.N, p.K = g.K, p.Lout = g.Lout;
+  p.C = g.C, p.bias = g.bias, p.part = g.part, p.tot = g.tot, p.B = B, p.N = g.N, p.K = g.K, p.Lout = g.Lout;
   p.nb = TC_BM / g.Lout;
   p.out_rows = g.out_rows, p.out_off = g.out_off, p.out_lstride = g.out_lstride, p.accumulate = g.accumulate;
   p.out_scale = o.out_scale;

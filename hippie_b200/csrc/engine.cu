@@ -40,7 +40,9 @@ struct BNInfo {
   int64_t run_off = 0;        // offset into bn_mean / bn_var
   int64_t coef_off = 0;       // workspace offset of the 8*C coefficient block
   int64_t part_off = -1;      // workspace offset of this BatchNorm's statistics partials [tiles][C][2]
+  int64_t tot_off = -1;       // workspace offset of its totals: forward [2][C] doubles, then backward [C][3] doubles
   int ntiles = 0, tile_rows = 0, M = 0;  // shape of the partials the producing conv left (set at launch time)
+  bool totals = false;                   // the producing conv accumulated totals instead of per-tile partials
 };
 struct Act {
   std::string name;
@@ -119,7 +121,7 @@ struct hippie_engine {
   Decoder dec[2];
   HeadParams headp{};
   int64_t head_scratch = 0, scal_off = 0, part_off[2] = {0, 0}, bpart_off[2] = {0, 0}, adam_part = 0;
-  int64_t part_floats = 0, bpart_floats = 0;
+  int64_t part_floats = 0, bpart_floats = 0, tot_off = 0, tot_floats = 0;
   int64_t wt_table_off = 0, bn_table_off = 0;
   std::vector<WtEntry> wt_table;
   std::vector<BnEvalEntry> bn_table;
@@ -527,6 +529,13 @@ struct hippie_engine {
       part_floats = std::max<int64_t>(part_floats, (((int64_t)cfg.max_batch * a.L + 63) / 64 + 1) * a.C * 2);
     bpart_floats = (int64_t)(kBnBwdMaxChunks + 1) * 512 * 6;
     for (int i = 0; i < 2; ++i) part_off[i] = take(part_floats), bpart_off[i] = take(bpart_floats);
+    {  // per-channel BatchNorm totals (double atomics), one contiguous region zeroed once per step
+      int64_t n = 0;
+      for (auto& b : bns) b.tot_off = n, n += 10 * (int64_t)b.C;  // (2 + 3) * C doubles = 10 * C floats
+      tot_floats = n;
+      tot_off = take(tot_floats);
+      for (auto& b : bns) b.tot_off += tot_off;
+    }
     adam_part = take(1024);
     {
       const int64_t mb = cfg.max_batch;
@@ -572,6 +581,7 @@ struct hippie_engine {
     ConvGemm g{};
     g.A = A(in), g.W = Pp(cv.w), g.bias = cv.b >= 0 ? Pp(cv.b) : nullptr, g.C = A(out);
     g.part = (train && bn >= 0) ? ws + bns[bn].part_off : nullptr;
+    if (train && bn >= 0 && use_tc) g.tot = reinterpret_cast<double*>(ws + bns[bn].tot_off), bns[bn].totals = true;
     g.M = B * acts[out].L, g.N = cv.cout, g.K = cv.k * cv.cin, g.Lout = acts[out].L;
     g.in_rows = acts[in].L + 2, g.in_stride = cv.stride, g.in_off = cv.k == 3 ? 0 : 1, g.in_C = cv.cin;
     g.out_rows = acts[out].L + 2, g.out_off = 1, g.out_lstride = 1, g.accumulate = 0;
@@ -608,6 +618,7 @@ struct hippie_engine {
   BnFinalize finalize_args(int bn) {
     BnFinalize f{};
     f.part = ws + bns[bn].part_off, f.C = bns[bn].C;
+    if (bns[bn].totals) f.tot = reinterpret_cast<const double*>(ws + bns[bn].tot_off);
     f.set_shape(bns[bn].ntiles, bns[bn].tile_rows, bns[bn].M);
     f.gamma = Pp(bns[bn].gamma), f.beta = Pp(bns[bn].beta);
     f.run_mean = bn_mean + bns[bn].run_off, f.run_var = bn_var + bns[bn].run_off, f.run_count = bn_count + bn;
@@ -709,6 +720,7 @@ struct hippie_engine {
     a.g = A(g), a.g_up = g_up ? 1 : 0, a.out = A(out), a.c = A(c), a.coef = coef(bn);
     a.cs = cs >= 0 ? A(cs) : nullptr, a.coef_s = cs >= 0 ? coef(bnsi) : nullptr;
     a.part = br.bpart, a.B = B, a.L = acts[out].L, a.C = acts[out].C, a.slope = kSlopeBackbone;
+    a.tot = reinterpret_cast<double*>(ws + bns[bn].tot_off) + 2 * (int64_t)bns[bn].C;
     a.inv_n = 1.0 / ((double)B * acts[out].L);
     a.gamma = Pp(bns[bn].gamma), a.dgamma = Gp(bns[bn].gamma), a.dbeta = Gp(bns[bn].beta);
     if (cs >= 0) a.gamma_s = Pp(bns[bnsi].gamma), a.dgamma_s = Gp(bns[bnsi].gamma), a.dbeta_s = Gp(bns[bnsi].beta);
@@ -940,6 +952,7 @@ struct hippie_engine {
     float* dec_out[2] = {out_dec1, out_dec2};
     const float lw[2] = {cfg.multimodal ? w1 : 1.f, w2};
     cudaMemsetAsync(ws + scal_off, 0, 64 * sizeof(float), main);
+    if (train) cudaMemsetAsync(ws + tot_off, 0, tot_floats * sizeof(float), main);
     if (backward) {
       cudaMemsetAsync(G, 0, param_floats * sizeof(float), main);
       if (use_tc) cudaMemsetAsync(ws + slots_off, 0, 4 * kMaxSlots * sizeof(float), main);

@@ -26,6 +26,8 @@ struct ConvGemm {
   const float* bias;  // [N] or null
   float* C;           // output tensor base (row 0)
   float* part;        // BatchNorm statistics partials [mtile][N][2] = (sum, centred M2), or null
+  double* tot = nullptr;  // tcgen05 path: per-channel totals [2][N] = (sum x, sum x^2), added with double atomics
+                          // (zeroed once per step); replaces `part`
   int M, N, K;        // M = B * Lout logical rows
   int Lout;           // logical rows per sample
   int in_rows;        // padded rows per sample of A  (Lin + 2)
@@ -111,6 +113,7 @@ void launch_reduce_partials(const float* part, int nparts, int n, float* out, in
 // coef layout per BatchNorm: 8 arrays of C floats: [0]=scale [1]=shift [2]=mean [3]=invstd [4]=k [5]=m1 [6]=m2 [7]=spare
 struct BnFinalize {
   const float* part;  // [ntiles][C][2]
+  const double* tot = nullptr;  // [2][C] totals (sum x, sum x^2) when the conv epilogue accumulated them; `part` unused
   int ntiles, tile_rows, M, C;
   // host-computed reciprocals (double division / sqrt are ~0.2 us software sequences on the device, and the finalize
   // phase sits on the critical path of every BatchNorm): 1/M, 1/max(M-1,1), 1/tile_rows, 1/(rows of the last tile)
@@ -170,6 +173,7 @@ struct BnBwd {
   const float* cs;  // shortcut conv output or null
   float* coef_s;
   float* part;  // [nchunks][C][3] = (S1, S2, S2s)
+  double* tot = nullptr;  // [C][3] totals added with double atomics by the reduce kernel (zeroed once per step)
   int B, L, C;
   float slope;
   // finalize: parameter gradients

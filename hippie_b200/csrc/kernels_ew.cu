@@ -149,6 +149,9 @@ __device__ __forceinline__ void bn_finalize_slab(const BnFinalize& f, int c0, bo
   }
   // 8 tiles in flight per thread: the loop is a chain of L2 round trips otherwise (up to 32 tiles per thread)
   constexpr int FL = 8;
+  if (f.tot) {  // the conv epilogues accumulated (sum x, sum x^2) per channel: nothing to re-sum
+    if (slice == 0) S = __ldcg(f.tot + c0 + c), Q = __ldcg(f.tot + f.C + c0 + c);
+  } else
   for (int t0 = slice; t0 < f.ntiles; t0 += 8 * FL) {
     float2 pv[FL];
 #pragma unroll
@@ -164,10 +167,13 @@ __device__ __forceinline__ void bn_finalize_slab(const BnFinalize& f, int c0, bo
       Q += (double)pv[u].y + st * st * (t == last ? inv_last : inv_full);
     }
   }
-  acc[slice][c] = ChanAcc{S, Q};
-  __syncthreads();
+  if (!f.tot) {
+    acc[slice][c] = ChanAcc{S, Q};
+    __syncthreads();
+  }
   if (slice == 0) {
-    for (int k = 1; k < 8; ++k) S += acc[k][c].s, Q += acc[k][c].q;
+    if (!f.tot)
+      for (int k = 1; k < 8; ++k) S += acc[k][c].s, Q += acc[k][c].q;
     const double mean = S * f.inv_M;
     double m2 = Q - S * mean;
     m2 = m2 > 0.0 ? m2 : 0.0;
@@ -401,14 +407,20 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(BnBwd a, int rows_pe
   red[0][threadIdx.x] = s1, red[1][threadIdx.x] = s2, red[2][threadIdx.x] = s3;
   __syncthreads();
   if (threadIdx.x < C4) {
-    for (int k = 0; k < 3; ++k) {
+    for (int k = 0; k < (a.cs ? 3 : 2); ++k) {
       float4 t = red[k][cq];
       for (int r = 1; r < RL; ++r) {
         float4 u = red[k][r * C4 + cq];
         t.x += u.x, t.y += u.y, t.z += u.z, t.w += u.w;
       }
-      float* dst = a.part + ((int64_t)blockIdx.x * a.C + cq * 4) * 3;
-      dst[0 * 3 + k] = t.x, dst[1 * 3 + k] = t.y, dst[2 * 3 + k] = t.z, dst[3 * 3 + k] = t.w;
+      if (a.tot) {  // per-channel totals: the apply kernel has nothing to re-sum
+        double* dst = a.tot + (int64_t)cq * 4 * 3;
+        atomicAdd(dst + 0 * 3 + k, (double)t.x), atomicAdd(dst + 1 * 3 + k, (double)t.y);
+        atomicAdd(dst + 2 * 3 + k, (double)t.z), atomicAdd(dst + 3 * 3 + k, (double)t.w);
+      } else {
+        float* dst = a.part + ((int64_t)blockIdx.x * a.C + cq * 4) * 3;
+        dst[0 * 3 + k] = t.x, dst[1 * 3 + k] = t.y, dst[2 * 3 + k] = t.z, dst[3 * 3 + k] = t.w;
+      }
     }
   }
   if (a.dc_slot) {  // uniform branch
@@ -453,6 +465,12 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(BnBwd a, int nchunks)
   {
     const int c = threadIdx.x & (kSlab - 1), slice = threadIdx.x >> 5;
     double s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    if (a.tot) {
+      if (slice == 0) {
+        const double* p = a.tot + (int64_t)(c0 + c) * 3;
+        s1 = __ldcg(p), s2 = __ldcg(p + 1), s3 = __ldcg(p + 2);
+      }
+    } else
     for (int t0 = slice; t0 < nchunks; t0 += 64) {  // 8 chunks (24 loads) in flight per thread
       float v[8][3];
 #pragma unroll
@@ -465,10 +483,13 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(BnBwd a, int nchunks)
 #pragma unroll
       for (int u = 0; u < 8; ++u) s1 += (double)v[u][0], s2 += (double)v[u][1], s3 += (double)v[u][2];
     }
-    s_sum[slice][c][0] = s1, s_sum[slice][c][1] = s2, s_sum[slice][c][2] = s3;
-    __syncthreads();
+    if (!a.tot) {
+      s_sum[slice][c][0] = s1, s_sum[slice][c][1] = s2, s_sum[slice][c][2] = s3;
+      __syncthreads();
+    }
     if (slice == 0) {
-      for (int k = 1; k < 8; ++k) s1 += s_sum[k][c][0], s2 += s_sum[k][c][1], s3 += s_sum[k][c][2];
+      if (!a.tot)
+        for (int k = 1; k < 8; ++k) s1 += s_sum[k][c][0], s2 += s_sum[k][c][1], s3 += s_sum[k][c][2];
       const double inv_n = a.inv_n;
       s_m1[c] = (float)(s1 * inv_n), s_m2[c] = (float)(s2 * inv_n), s_m3[c] = (float)(s3 * inv_n);
       if (blockIdx.y == 0) {
