@@ -174,6 +174,8 @@ def main():
         # stdout carries exactly one JSON line: NCCL's own banner ("NCCL version ...", printed when NCCL_DEBUG is set in
         # the environment) goes to stderr
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":  # the version banner is a bare printf to stdout
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
     from hippie_b200.model import MultiModalCVAE, MultiModalCVAETrainModule
     from hippie_b200.parallel import train_step_overlapped
