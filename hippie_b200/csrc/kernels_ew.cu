@@ -642,10 +642,20 @@ __global__ void __launch_bounds__(256) linear_wgrad_rows_kernel(const float* __r
   const int j = idx / (nin + 1), i = idx - j * (nin + 1);
   float s = 0.f;
   if (j < nout) {
-    if (i < nin) {
-      for (int b = bg; b < B; b += 4) s = fmaf(__ldg(dy + (int64_t)b * ldy + j), __ldg(x + (int64_t)b * ldx + i), s);
-    } else {
-      for (int b = bg; b < B; b += 4) s += __ldg(dy + (int64_t)b * ldy + j);
+    // 16 samples per thread in flight: the loop is a chain of L2 round trips otherwise (54 us -> measured below)
+    constexpr int U = 16;
+    const bool bias = i >= nin;
+    for (int b0 = bg; b0 < B; b0 += 4 * U) {
+      float dv[U], xv[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int b = b0 + 4 * u;
+        const bool ok = b < B;
+        dv[u] = ok ? __ldg(dy + (int64_t)b * ldy + j) : 0.f;
+        xv[u] = (ok && !bias) ? __ldg(x + (int64_t)b * ldx + i) : 1.f;
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) s = fmaf(dv[u], xv[u], s);
     }
   }
   red[bg][o] = s;
