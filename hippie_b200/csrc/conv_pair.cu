@@ -47,7 +47,8 @@ constexpr int PK = 64;  // K elements per k-block = one 128-byte swizzle row of 
 // the bs512 step: 4.77 ms (128x128 + 128x64 tiles, 1 CTA/SM) -> 4.36 ms; the step is bound by the chain of short
 // dependent kernels, not by tile efficiency.
 // Phase stamps of one CTA (tools/pair_test, PT_STAMPS=1): prologue 0.26 us, first fill 0.67 us, main loop 0.53 us per
-// k-block (ANY layer, any grid), epilogue 3.3 us.  The k-block period is set by the TMA unit's ROW rate, not by bytes:
+// k-block (ANY layer, any grid), epilogue 3.3 us with per-thread stores and 1.8 us with TMA stores (TMEM -> staging
+// 0.45, store issue 0.16, BatchNorm partials 1.2).  The k-block period is set by the TMA unit's ROW rate, not by bytes:
 // a k-block is 384 box rows of 128 B; halving the rows to 64 B (32-wide k-blocks, 64-byte swizzle, 4 stages: tried)
 // costs 0.38 us per half block, i.e. the same ~1.4 ns per row.  More MACs per fetched row (wider tiles, 2-CTA pairs)
 // is the way to a faster main loop; deeper rings are not.
