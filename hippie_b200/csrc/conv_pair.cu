@@ -351,8 +351,9 @@ __global__ void __launch_bounds__(TC_THREADS, 2)
       if (part_id == 0) {
         if (p.tot) {  // per-channel totals (sum x, sum x^2): exact enough in double, no per-tile partials to re-read
           const double sd = (double)sum;
-          atomicAdd(p.tot + n0 + col, sd);
-          atomicAdd(p.tot + p.N + n0 + col, (double)m2 + sd * sd / (double)nvalid);
+          double* tot = p.tot + (int64_t)(blockIdx.x % kBnFwdTotCopies) * 2 * p.N;  // spread the collisions
+          atomicAdd(tot + n0 + col, sd);
+          atomicAdd(tot + p.N + n0 + col, (double)m2 + sd * sd / (double)nvalid);
         } else {
           *reinterpret_cast<float2*>(p.part + ((int64_t)blockIdx.x * p.N + n0 + col) * 2) = make_float2(sum, m2);
         }

@@ -531,7 +531,7 @@ struct hippie_engine {
     for (int i = 0; i < 2; ++i) part_off[i] = take(part_floats), bpart_off[i] = take(bpart_floats);
     {  // per-channel BatchNorm totals (double atomics), one contiguous region zeroed once per step
       int64_t n = 0;
-      for (auto& b : bns) b.tot_off = n, n += 10 * (int64_t)b.C;  // (2 + 3) * C doubles = 10 * C floats
+      for (auto& b : bns) b.tot_off = n, n += (4 * kBnFwdTotCopies + 6 * kBnBwdTotCopies) * (int64_t)b.C;  // (2 + 3) x copies x C doubles
       tot_floats = n;
       tot_off = take(tot_floats);
       for (auto& b : bns) b.tot_off += tot_off;
@@ -720,7 +720,7 @@ struct hippie_engine {
     a.g = A(g), a.g_up = g_up ? 1 : 0, a.out = A(out), a.c = A(c), a.coef = coef(bn);
     a.cs = cs >= 0 ? A(cs) : nullptr, a.coef_s = cs >= 0 ? coef(bnsi) : nullptr;
     a.part = br.bpart, a.B = B, a.L = acts[out].L, a.C = acts[out].C, a.slope = kSlopeBackbone;
-    a.tot = reinterpret_cast<double*>(ws + bns[bn].tot_off) + 2 * (int64_t)bns[bn].C;
+    a.tot = reinterpret_cast<double*>(ws + bns[bn].tot_off) + 2 * kBnFwdTotCopies * (int64_t)bns[bn].C;
     a.inv_n = 1.0 / ((double)B * acts[out].L);
     a.gamma = Pp(bns[bn].gamma), a.dgamma = Gp(bns[bn].gamma), a.dbeta = Gp(bns[bn].beta);
     if (cs >= 0) a.gamma_s = Pp(bns[bnsi].gamma), a.dgamma_s = Gp(bns[bnsi].gamma), a.dbeta_s = Gp(bns[bnsi].beta);

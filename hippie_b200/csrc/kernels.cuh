@@ -26,8 +26,8 @@ struct ConvGemm {
   const float* bias;  // [N] or null
   float* C;           // output tensor base (row 0)
   float* part;        // BatchNorm statistics partials [mtile][N][2] = (sum, centred M2), or null
-  double* tot = nullptr;  // tcgen05 path: per-channel totals [2][N] = (sum x, sum x^2), added with double atomics
-                          // (zeroed once per step); replaces `part`
+  double* tot = nullptr;  // tcgen05 path: per-channel totals [copies][2][N] = (sum x, sum x^2), added with double
+                          // atomics (zeroed once per step); replaces `part`
   int M, N, K;        // M = B * Lout logical rows
   int Lout;           // logical rows per sample
   int in_rows;        // padded rows per sample of A  (Lin + 2)
@@ -113,7 +113,7 @@ void launch_reduce_partials(const float* part, int nparts, int n, float* out, in
 // coef layout per BatchNorm: 8 arrays of C floats: [0]=scale [1]=shift [2]=mean [3]=invstd [4]=k [5]=m1 [6]=m2 [7]=spare
 struct BnFinalize {
   const float* part;  // [ntiles][C][2]
-  const double* tot = nullptr;  // [2][C] totals (sum x, sum x^2) when the conv epilogue accumulated them; `part` unused
+  const double* tot = nullptr;  // [copies][2][C] totals (sum x, sum x^2) when the conv epilogues accumulated them
   int ntiles, tile_rows, M, C;
   // host-computed reciprocals (double division / sqrt are ~0.2 us software sequences on the device, and the finalize
   // phase sits on the critical path of every BatchNorm): 1/M, 1/max(M-1,1), 1/tile_rows, 1/(rows of the last tile)
@@ -202,6 +202,8 @@ struct BnBwd {
 };
 void launch_bn_bwd(const BnBwd& a, int sm_count, cudaStream_t s);  // reduce + apply (2 launches)
 constexpr int kBnBwdLaunches = 2;
+constexpr int kBnBwdTotCopies = 8;  // the reduce CTAs spread their atomics over this many copies of the [C][3] totals
+constexpr int kBnFwdTotCopies = 1;  // copies of the conv epilogues' [2][C] totals (copy = M-tile index mod copies); 8 measured no gain
 constexpr int kBnBwdMaxChunks = 128;  // every apply CTA re-sums the partials of its 32 channels
 
 // dst[b,l,c] += src[b,2l,c] + src[b,2l+1,c]     (backward of nearest x2 up-sampling)

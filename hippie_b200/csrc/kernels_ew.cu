@@ -150,7 +150,16 @@ __device__ __forceinline__ void bn_finalize_slab(const BnFinalize& f, int c0, bo
   // 8 tiles in flight per thread: the loop is a chain of L2 round trips otherwise (up to 32 tiles per thread)
   constexpr int FL = 8;
   if (f.tot) {  // the conv epilogues accumulated (sum x, sum x^2) per channel: nothing to re-sum
-    if (slice == 0) S = __ldcg(f.tot + c0 + c), Q = __ldcg(f.tot + f.C + c0 + c);
+    if (slice == 0) {
+      double v[kBnFwdTotCopies][2];
+#pragma unroll
+      for (int k = 0; k < kBnFwdTotCopies; ++k) {
+        const double* p = f.tot + (int64_t)k * 2 * f.C + c0 + c;
+        v[k][0] = __ldcg(p), v[k][1] = __ldcg(p + f.C);
+      }
+#pragma unroll
+      for (int k = 0; k < kBnFwdTotCopies; ++k) S += v[k][0], Q += v[k][1];
+    }
   } else
   for (int t0 = slice; t0 < f.ntiles; t0 += 8 * FL) {
     float2 pv[FL];
@@ -414,7 +423,7 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(BnBwd a, int rows_pe
         t.x += u.x, t.y += u.y, t.z += u.z, t.w += u.w;
       }
       if (a.tot) {  // per-channel totals: the apply kernel has nothing to re-sum
-        double* dst = a.tot + (int64_t)cq * 4 * 3;
+        double* dst = a.tot + ((int64_t)(blockIdx.x % kBnBwdTotCopies) * a.C + cq * 4) * 3;
         atomicAdd(dst + 0 * 3 + k, (double)t.x), atomicAdd(dst + 1 * 3 + k, (double)t.y);
         atomicAdd(dst + 2 * 3 + k, (double)t.z), atomicAdd(dst + 3 * 3 + k, (double)t.w);
       } else {
@@ -467,8 +476,14 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(BnBwd a, int nchunks)
     double s1 = 0.0, s2 = 0.0, s3 = 0.0;
     if (a.tot) {
       if (slice == 0) {
-        const double* p = a.tot + (int64_t)(c0 + c) * 3;
-        s1 = __ldcg(p), s2 = __ldcg(p + 1), s3 = __ldcg(p + 2);
+        double v[kBnBwdTotCopies][3];
+#pragma unroll
+        for (int k = 0; k < kBnBwdTotCopies; ++k) {
+          const double* p = a.tot + ((int64_t)k * a.C + c0 + c) * 3;
+          v[k][0] = __ldcg(p), v[k][1] = __ldcg(p + 1), v[k][2] = __ldcg(p + 2);
+        }
+#pragma unroll
+        for (int k = 0; k < kBnBwdTotCopies; ++k) s1 += v[k][0], s2 += v[k][1], s3 += v[k][2];
       }
     } else
     for (int t0 = slice; t0 < nchunks; t0 += 64) {  // 8 chunks (24 loads) in flight per thread
