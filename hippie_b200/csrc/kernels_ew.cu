@@ -41,6 +41,8 @@ __device__ __forceinline__ float xin(const float* x, int Lin, int i) { return (i
 __global__ void __launch_bounds__(256) stem_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                        float* __restrict__ c0, float* __restrict__ part, int B,
                                                        int Lin, int Lout) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float red[4][64];
   __shared__ float smean[64];
   const int co = threadIdx.x & 63, rg = threadIdx.x >> 6;
@@ -86,6 +88,8 @@ __global__ void __launch_bounds__(256) stem_fwd_kernel(const float* __restrict__
 
 __global__ void __launch_bounds__(256) stem_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dc0,
                                                          float* __restrict__ part, int B, int Lin, int Lout) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float red[4][192];
   const int co = threadIdx.x & 63, rg = threadIdx.x >> 6;
   const int M = B * Lout, m0 = blockIdx.x * 128;
@@ -110,6 +114,8 @@ __global__ void __launch_bounds__(256) stem_wgrad_kernel(const float* __restrict
 
 __global__ void reduce_partials_kernel(const float* __restrict__ part, int nparts, int n, float* __restrict__ out,
                                        int accumulate) {
+  pdl_trigger();
+  pdl_wait();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   double s = 0.0;
@@ -609,6 +615,8 @@ __global__ void __launch_bounds__(128) pool_linear_fwd_kernel(const float* __res
                                                               const float* __restrict__ W,
                                                               const float* __restrict__ bias, int F,
                                                               float* __restrict__ pooled, float* __restrict__ h) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float sp[];  // [C]
   const int b = blockIdx.x;
   const float inv = 1.f / (float)L;
@@ -632,6 +640,8 @@ __global__ void __launch_bounds__(128) pool_linear_fwd_kernel(const float* __res
 __global__ void __launch_bounds__(128) pool_linear_bwd_x_kernel(const float* __restrict__ dh,
                                                                 const float* __restrict__ W, int L, int C, int F,
                                                                 float* __restrict__ g_x4) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float sd[];  // [F]
   const int b = blockIdx.x;
   for (int f = threadIdx.x; f < F; f += blockDim.x) sd[f] = dh[(int64_t)b * F + f];
@@ -651,6 +661,8 @@ __global__ void __launch_bounds__(256) linear_wgrad_rows_kernel(const float* __r
                                                                 const float* __restrict__ x, int ldx, int B, int nin,
                                                                 int nout, float* __restrict__ dW,
                                                                 float* __restrict__ db) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float red[4][64];
   const int o = threadIdx.x & 63, bg = threadIdx.x >> 6;
   const int idx = blockIdx.x * 64 + o;
@@ -692,6 +704,8 @@ __global__ void __launch_bounds__(256) dec_linear_fwd_kernel(const float* __rest
                                                              const float* __restrict__ bias, int C,
                                                              float* __restrict__ t0, uint16_t* __restrict__ t0_p,
                                                              int64_t t0_ps) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float sd[];  // [F]
   const int b = blockIdx.x;
   for (int f = threadIdx.x; f < F; f += blockDim.x) sd[f] = d[(int64_t)b * F + f];
@@ -718,6 +732,8 @@ __global__ void __launch_bounds__(256) dec_linear_fwd_kernel(const float* __rest
 __global__ void __launch_bounds__(256) dec_linear_bwd_x_kernel(const float* __restrict__ g_t0,
                                                                const float* __restrict__ W, int F, int C,
                                                                float* __restrict__ gx0, float* __restrict__ dd) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float sg[];  // [C]
   const int b = blockIdx.x;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
@@ -743,6 +759,8 @@ __global__ void __launch_bounds__(256) dec_linear_bwd_x_kernel(const float* __re
 // ------------------------------------------------------------------------------------------------
 constexpr int kTailSPB = 4;  // samples per CTA
 __global__ void __launch_bounds__(256) dec_tail_kernel(DecTail t) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float sm[];
   float* xs = sm;                      // [34][65]
   float* Wos = xs + 34 * 65;           // [Lo][65]
@@ -854,6 +872,8 @@ __global__ void __launch_bounds__(256) dec_tail_kernel(DecTail t) {
 // grid = Lo + 1.  block o < Lo: dWo[o][p] = sum_b ddec[b][o] * y[b][p], dbo[o];  last block: partials.
 __global__ void __launch_bounds__(256) dec_tail_reduce_kernel(DecTail t, int ncta, float* dwc, float* dbc, float* dWo,
                                                               float* dbo, float* sse) {
+  pdl_trigger();
+  pdl_wait();
   const int o = blockIdx.x, tid = threadIdx.x;
   if (o < t.Lo) {
     if (!t.train) return;
@@ -890,6 +910,8 @@ __global__ void __launch_bounds__(256) dec_tail_reduce_kernel(DecTail t, int nct
 __global__ void loss_finalize_kernel(const float* sse1, const float* sse2, const float* kl_parts, int n_kl, int B, int Lo1,
                                      int Lo2,
                                      float beta, float w1, float w2, int multimodal, float* scalars) {
+  pdl_trigger();
+  pdl_wait();
   const float mse1 = *sse1 / ((float)B * (float)Lo1);
   const float mse2 = multimodal ? *sse2 / ((float)B * (float)Lo2) : 0.f;
   float kl_sum = 0.f;
@@ -908,6 +930,8 @@ __global__ void loss_finalize_kernel(const float* sse1, const float* sse2, const
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g, int64_t n, float scale,
                                                     float* __restrict__ partials) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float red[8];
   float s = 0.f;
   const int64_t n4 = n >> 2;
@@ -928,6 +952,8 @@ __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g,
 
 __global__ void __launch_bounds__(256) clip_coef_kernel(const float* __restrict__ partials, int n, float max_norm,
                                                         float* __restrict__ scalars) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ double red[8];
   double s = 0.0;
   for (int i = threadIdx.x; i < n; i += blockDim.x) s += (double)partials[i];
@@ -947,6 +973,8 @@ __global__ void __launch_bounds__(256) clip_coef_kernel(const float* __restrict_
 
 __global__ void __launch_bounds__(256) adamw_kernel(AdamArgs a, float decay, float step_size, float bc2_sqrt,
                                                     float step_size_cls, float bc2_sqrt_cls) {
+  pdl_trigger();
+  pdl_wait();
   const float coef = a.scalars[5];
   const float omb1 = 1.f - a.beta1, omb2 = 1.f - a.beta2;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -1033,15 +1061,15 @@ static inline int ew_grid(int64_t work_items, int block = 256) {
 
 void launch_stem_fwd(const float* x, const float* w, float* c0, float* part, int B, int Lin, int Lout, cudaStream_t s) {
   int grid = (B * Lout + 127) / 128;
-  stem_fwd_kernel<<<grid, 256, 0, s>>>(x, w, c0, part, B, Lin, Lout);
+  launch_pdl(stem_fwd_kernel, dim3(grid), dim3(256), 0, s, x, w, c0, part, B, Lin, Lout);
 }
 int launch_stem_wgrad(const float* x, const float* dc0, float* part, int B, int Lin, int Lout, cudaStream_t s) {
   int grid = (B * Lout + 127) / 128;
-  stem_wgrad_kernel<<<grid, 256, 0, s>>>(x, dc0, part, B, Lin, Lout);
+  launch_pdl(stem_wgrad_kernel, dim3(grid), dim3(256), 0, s, x, dc0, part, B, Lin, Lout);
   return grid;
 }
 void launch_reduce_partials(const float* part, int nparts, int n, float* out, int accumulate, cudaStream_t s) {
-  reduce_partials_kernel<<<(n + 127) / 128, 128, 0, s>>>(part, nparts, n, out, accumulate);
+  launch_pdl(reduce_partials_kernel, dim3((n + 127) / 128), dim3(128), 0, s, part, nparts, n, out, accumulate);
 }
 void launch_bn_eval_coefs(const BnEvalEntry* table_dev, int n, const float* params, const float* run_mean,
                           const float* run_var, float* ws, cudaStream_t s) {
@@ -1077,22 +1105,22 @@ void launch_pairsum_acc(const float* src, float* dst, int B, int L, int C, cudaS
 }
 void launch_pool_linear_fwd(const float* x4, int B, int L, int C, const float* W, const float* bias, int F,
                             float* pooled, float* h, cudaStream_t s) {
-  pool_linear_fwd_kernel<<<B, 128, C * sizeof(float), s>>>(x4, L, C, W, bias, F, pooled, h);
+  launch_pdl(pool_linear_fwd_kernel, dim3(B), dim3(128), C * sizeof(float), s, x4, L, C, W, bias, F, pooled, h);
 }
 void launch_pool_linear_bwd_x(const float* dh, const float* W, int B, int L, int C, int F, float* g_x4, cudaStream_t s) {
-  pool_linear_bwd_x_kernel<<<B, 128, F * sizeof(float), s>>>(dh, W, L, C, F, g_x4);
+  launch_pdl(pool_linear_bwd_x_kernel, dim3(B), dim3(128), F * sizeof(float), s, dh, W, L, C, F, g_x4);
 }
 void launch_linear_wgrad(const float* dy, int ldy, const float* x, int ldx, int B, int nin, int nout, float* dW, float* db,
                          cudaStream_t s) {
-  linear_wgrad_rows_kernel<<<(nout * (nin + 1) + 63) / 64, 256, 0, s>>>(dy, ldy, x, ldx, B, nin, nout, dW, db);
+  launch_pdl(linear_wgrad_rows_kernel, dim3((nout * (nin + 1) + 63) / 64), dim3(256), 0, s, dy, ldy, x, ldx, B, nin, nout, dW, db);
 }
 void launch_dec_linear_fwd(const float* d, int B, int F, const float* W, const float* bias, int C, float* t0,
                            uint16_t* t0_p, int64_t t0_ps, cudaStream_t s) {
-  dec_linear_fwd_kernel<<<B, 256, F * sizeof(float), s>>>(d, F, W, bias, C, t0, t0_p, t0_ps);
+  launch_pdl(dec_linear_fwd_kernel, dim3(B), dim3(256), F * sizeof(float), s, d, F, W, bias, C, t0, t0_p, t0_ps);
 }
 void launch_dec_linear_bwd_x(const float* g_t0, const float* W, int B, int F, int C, float* gx0, float* dd,
                              cudaStream_t s) {
-  dec_linear_bwd_x_kernel<<<B, 256, C * sizeof(float), s>>>(g_t0, W, F, C, gx0, dd);
+  launch_pdl(dec_linear_bwd_x_kernel, dim3(B), dim3(256), C * sizeof(float), s, g_t0, W, F, C, gx0, dd);
 }
 static size_t dec_tail_smem(int Lo) { return (size_t)(34 * 65 + Lo * 65 + 64 + ((Lo + 3) & ~3) + 68 + 192) * sizeof(float); }
 int launch_dec_tail(const DecTail& t, cudaStream_t s) {
@@ -1103,27 +1131,27 @@ int launch_dec_tail(const DecTail& t, cudaStream_t s) {
     cudaFuncSetAttribute(dec_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     configured = smem;
   }
-  dec_tail_kernel<<<ncta, 256, smem, s>>>(t);
+  launch_pdl(dec_tail_kernel, dim3(ncta), dim3(256), smem, s, t);
   return ncta;
 }
 void launch_dec_tail_reduce(const DecTail& t, int ncta, float* dwc, float* dbc, float* dWo, float* dbo, float* sse,
                             cudaStream_t s) {
-  dec_tail_reduce_kernel<<<t.Lo + 1, 256, 0, s>>>(t, ncta, dwc, dbc, dWo, dbo, sse);
+  launch_pdl(dec_tail_reduce_kernel, dim3(t.Lo + 1), dim3(256), 0, s, t, ncta, dwc, dbc, dWo, dbo, sse);
 }
 void launch_loss_finalize(const float* sse1, const float* sse2, const float* kl_parts, int n_kl, int B, int Lo1, int Lo2,
                           float beta, float w1, float w2, int multimodal, float* scalars, cudaStream_t s) {
-  loss_finalize_kernel<<<1, 1, 0, s>>>(sse1, sse2, kl_parts, n_kl, B, Lo1, Lo2, beta, w1, w2, multimodal, scalars);
+  launch_pdl(loss_finalize_kernel, dim3(1), dim3(1), 0, s, sse1, sse2, kl_parts, n_kl, B, Lo1, Lo2, beta, w1, w2, multimodal, scalars);
 }
 void launch_clip_adamw(const AdamArgs& a, cudaStream_t s) {
   const int nblk = 1024;
-  sumsq_kernel<<<nblk, 256, 0, s>>>(a.g, a.n, a.grad_scale, a.partials);
-  clip_coef_kernel<<<1, 256, 0, s>>>(a.partials, nblk, a.max_norm, a.scalars);
+  launch_pdl(sumsq_kernel, dim3(nblk), dim3(256), 0, s, a.g, a.n, a.grad_scale, a.partials);
+  launch_pdl(clip_coef_kernel, dim3(1), dim3(256), 0, s, a.partials, nblk, a.max_norm, a.scalars);
   // scalar factors exactly as torch.optim.adam._single_tensor_adam computes them (python doubles -> fp32)
   const double bc1 = 1.0 - pow((double)a.beta1, (double)a.step), bc2 = 1.0 - pow((double)a.beta2, (double)a.step);
   const int sc = a.step_cls > 0 ? a.step_cls : 1;
   const double bc1c = 1.0 - pow((double)a.beta1, (double)sc), bc2c = 1.0 - pow((double)a.beta2, (double)sc);
   const float decay = (float)(1.0 - (double)a.lr * (double)a.wd);
-  adamw_kernel<<<ew_grid(a.n), 256, 0, s>>>(a, decay, (float)((double)a.lr / bc1), (float)sqrt(bc2),
+  launch_pdl(adamw_kernel, dim3(ew_grid(a.n)), dim3(256), 0, s, a, decay, (float)((double)a.lr / bc1), (float)sqrt(bc2),
                                             (float)((double)a.lr / bc1c), (float)sqrt(bc2c));
 }
 void launch_preprocess(const double* raw, int width, const int64_t* index, int B, int size, int take_log, float* out,
