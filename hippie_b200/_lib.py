@@ -60,6 +60,7 @@ SIGNATURES = {
     "hippie_train_fwd_bwd_part": (C.c_int, [_H, _f32p, _f32p, _i64p, _i64p, _f32p, C.c_int32, C.c_float, C.c_float,
                                             C.c_float, _f32p, C.c_int32, C.c_void_p]),
     "hippie_grad_split": (C.c_int64, [_H]),
+    "hippie_grad_bounds": (C.c_int, [_H, C.POINTER(C.c_int64)]),
     "hippie_eval_forward": (C.c_int, [_H, _f32p, _f32p, _i64p, _i64p, _f32p, C.c_int32, C.c_float, C.c_float,
                                       C.c_float, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, C.c_void_p]),
     "hippie_train_forward": (C.c_int, [_H, _f32p, _f32p, _i64p, _i64p, _f32p, C.c_int32, C.c_float, C.c_float,

@@ -116,6 +116,10 @@ struct hippie_engine {
   std::map<int, int> gact;  // activation index -> gradient tensor index
   int64_t param_floats = 0, bn_floats = 0, ws_floats = 0;
   int64_t grad_split = 0;  // first parameter offset that does not belong to an encoder backbone
+  // gradient ranges in the order the backward pass completes them (hippie_grad_bounds): encoder e owns
+  // [enc_begin[e], enc_deep[e]) = stem + layer1 + layer2 (final after part 3) and [enc_deep[e], enc_end[e]) = layer3 +
+  // layer4 + linear (final after part 2)
+  int64_t enc_begin[2] = {0, 0}, enc_deep[2] = {0, 0}, enc_end[2] = {0, 0};
   int n_enc = 0, n_dec = 0;
   Encoder enc[2];
   Decoder dec[2];
@@ -142,7 +146,7 @@ struct hippie_engine {
   bool failed = false;  // a tensor-map encode failed while launching (reported by the entry point)
   // ---- CUDA graphs: one instantiated graph per call signature, replayed from staged inputs ----------------
   struct CallArgs {
-    int mode;  // 0 train_fwd_bwd, 1 train_forward, 2 eval_forward, 3 embed, 4 / 5 = parts 0 / 1 of a split train_fwd_bwd
+    int mode;  // 0 train_fwd_bwd, 1 train_forward, 2 eval_forward, 3 embed, 4 + p = part p (0..3) of a split train_fwd_bwd
     const float *x1, *x2;
     const int64_t *src, *cls;
     const float* eps;
@@ -503,6 +507,15 @@ struct hippie_engine {
     const std::string f = cfg.multimodal ? "fusion_encoder" : "encoder_fc";
     H.f0_w = off_of(f + ".0.weight"), H.f0_b = off_of(f + ".0.bias");
     grad_split = H.f0_w;
+    for (int e = 0; e < 2; ++e) {
+      if (e < n_enc) {
+        const std::string pre = cfg.multimodal ? "encoder_mod" + std::to_string(e + 1) : "encoder";
+        enc_begin[e] = off_of(pre + ".conv1.weight"), enc_deep[e] = off_of(pre + ".layer3.0.conv1.weight");
+      } else {
+        enc_begin[e] = enc_deep[e] = grad_split;
+      }
+    }
+    enc_end[0] = n_enc == 2 ? enc_begin[1] : grad_split, enc_end[1] = grad_split;
     H.fbn_g = off_of(f + ".1.weight"), H.fbn_b = off_of(f + ".1.bias");
     H.f3_w = off_of(f + ".3.weight"), H.f3_b = off_of(f + ".3.bias");
     H.fbn_run = bns[bidx.at(f + ".1")].run_off, H.fbn_cnt = bidx.at(f + ".1");
@@ -767,16 +780,20 @@ struct hippie_engine {
     prof_end(pe8, 8, 0.0, br);
     ++launches;
   }
-  void encoder_bwd(Encoder& E, const float* x, int B, Branch& br) {
+  // phase 0 = whole backward; 1 = deep half (Linear, layer4, layer3); 2 = shallow half (layer2, layer1, stem)
+  void encoder_bwd(Encoder& E, const float* x, int B, Branch& br, int phase = 0) {
     const int last = E.blk[7].out;
-    cudaEvent_t pe9 = prof_begin(br);
-    side_wait(br);  // dh and pooled are final: the Linear's weight gradient runs beside the backbone backward
-    launch_linear_wgrad(ws + E.dh, 2 * cfg.z_dim, ws + E.pooled, 512, B, 512, 2 * cfg.z_dim, Gp(E.lin_w), Gp(E.lin_b),
-                        br.wst ? br.wst : br.st);
-    launch_pool_linear_bwd_x(ws + E.dh, Pp(E.lin_w), B, acts[last].L, 512, 2 * cfg.z_dim, A(gact.at(last)), br.st);
-    prof_end(pe9, 9, 0.0, br);
-    launches += 2;
-    for (int i = 7; i >= 0; --i) {
+    if (phase != 2) {
+      cudaEvent_t pe9 = prof_begin(br);
+      side_wait(br);  // dh and pooled are final: the Linear's weight gradient runs beside the backbone backward
+      launch_linear_wgrad(ws + E.dh, 2 * cfg.z_dim, ws + E.pooled, 512, B, 512, 2 * cfg.z_dim, Gp(E.lin_w), Gp(E.lin_b),
+                          br.wst ? br.wst : br.st);
+      launch_pool_linear_bwd_x(ws + E.dh, Pp(E.lin_w), B, acts[last].L, 512, 2 * cfg.z_dim, A(gact.at(last)), br.st);
+      prof_end(pe9, 9, 0.0, br);
+      launches += 2;
+    }
+    const int i_hi = phase == 2 ? 3 : 7, i_lo = phase == 1 ? 4 : 0;
+    for (int i = i_hi; i >= i_lo; --i) {
       EncBlock& b = E.blk[i];
       const int gx = gact.at(b.x), gout = gact.at(b.out);
       bn_bwd(gout, false, b.out, b.c2o, b.bn2, b.down ? b.cso : -1, b.bns, b.dc2, 1, b.dcs, 2, b.down ? -1 : gx, B, br);
@@ -790,6 +807,7 @@ struct hippie_engine {
       dgrad(b.c1, b.dc1, gx, true, B, br);
       wgrad(b.c1, b.dc1, b.x, B, br);
     }
+    if (phase == 1) return;
     bn_bwd(gact.at(E.a0), false, E.a0, E.c0, E.bn0, -1, -1, E.dc0, 1, -1, 1, -1, B, br);
     cudaEvent_t pe10 = prof_begin(br);
     const int np = launch_stem_wgrad(x, A(E.dc0), br.part, B, E.Lin, E.L0, br.st);
@@ -944,10 +962,10 @@ struct hippie_engine {
     Branch b0{main, ws + part_off[0], ws + bpart_off[0]}, b1{profiling ? main : side, ws + part_off[1], ws + bpart_off[1]};
     if (backward && !profiling) b0.wst = wside[0], b1.wst = wside[1];
     const float* xin[2] = {x1, x2};
-    if (part == 1) {  // second part of a split step: the encoders' backward pass only
-      encoders_bwd(xin, B, b0, b1, main);
+    if (part >= 1) {  // later parts of a split step: the encoders' backward pass (1 = whole, 2 = deep half, 3 = shallow half)
+      encoders_bwd(xin, B, b0, b1, main, part == 1 ? 0 : part - 1);
       if (failed) return fail(-9, err);
-      return check("train_fwd_bwd (part 1)");
+      return check("train_fwd_bwd (part >= 1)");
     }
     float* dec_out[2] = {out_dec1, out_dec2};
     const float lw[2] = {cfg.multimodal ? w1 : 1.f, w2};
@@ -1009,12 +1027,12 @@ struct hippie_engine {
       cudaStreamWaitEvent(main, e, 0);
     }
   }
-  void encoders_bwd(const float* const* xin, int B, Branch& b0, Branch& b1, cudaStream_t main) {
+  void encoders_bwd(const float* const* xin, int B, Branch& b0, Branch& b1, cudaStream_t main, int phase = 0) {
     const bool two = n_enc == 2;
     if (two) fork(main);
-    encoder_bwd(enc[0], xin[0], B, b0);
+    encoder_bwd(enc[0], xin[0], B, b0, phase);
     if (two) {
-      encoder_bwd(enc[1], xin[1], B, b1);
+      encoder_bwd(enc[1], xin[1], B, b1, phase);
       join(main);
     }
     join_wgrad(main);
@@ -1256,7 +1274,7 @@ int hippie_train_fwd_bwd_part(hippie_handle h, const float* x1, const float* x2,
   if (!h) return -1;
   if (int rc = h->validate(B, x1, x2, src)) return rc;
   if (h->cfg.inference_only) return h->fail(-7, "inference-only engine");
-  if (part != 0 && part != 1) return h->fail(-3, "part must be 0 or 1");
+  if (part < 0 || part > 3) return h->fail(-3, "part must be 0..3");
   if (!eps) return h->fail(-4, "eps is required for training (reparameterisation noise)");
   if (B < 2) return h->fail(-3, "training-mode BatchNorm needs B >= 2");
   hippie_engine::CallArgs a{4 + part, x1, x2, src, cls, eps, B, beta, w1, w2, -1, part == 0 ? scalars_out : nullptr,
@@ -1265,6 +1283,12 @@ int hippie_train_fwd_bwd_part(hippie_handle h, const float* x1, const float* x2,
 }
 
 int64_t hippie_grad_split(hippie_handle h) { return h ? h->grad_split : -1; }
+
+int hippie_grad_bounds(hippie_handle h, int64_t* bounds) {
+  if (!h || !bounds) return -1;
+  for (int e = 0; e < 2; ++e) bounds[3 * e] = h->enc_begin[e], bounds[3 * e + 1] = h->enc_deep[e], bounds[3 * e + 2] = h->enc_end[e];
+  return 0;
+}
 
 int hippie_eval_forward(hippie_handle h, const float* x1, const float* x2, const int64_t* src, const int64_t* cls,
                         const float* eps, int32_t B, float beta, float w1, float w2, float* scalars_out, float* out_enc,

@@ -183,7 +183,8 @@ class Engine:
     def train_fwd_bwd_part(self, part: int, x1, x2, src, cls, eps, beta: float, w1: float = 1.0, w2: float = 1.0,
                            scalars=None):
         """Part 0 (forward, loss, decoder + head backward) or part 1 (encoder backward) of the train step; after part 0
-        `flat_grads[grad_split:]` is final, after part 1 `flat_grads[:grad_split]` (hippie_train_fwd_bwd_part)."""
+        `flat_grads[grad_split:]` is final, after part 1 `flat_grads[:grad_split]`; parts 2 + 3 replace part 1 with the
+        deep / shallow halves of the encoders (`grad_bounds`) (hippie_train_fwd_bwd_part)."""
         B = x1.shape[0]
         self._io(x1, x2, src, cls, eps, B)
         if scalars is None and part == 0:
@@ -195,6 +196,15 @@ class Engine:
     @property
     def grad_split(self) -> int:
         return int(self._L.hippie_grad_split(self._h))
+
+    @property
+    def grad_bounds(self):
+        """[(begin, deep, end)] per encoder: flat_grads[deep:end] is final after part 2, flat_grads[begin:deep] after
+        part 3 (hippie_grad_bounds); empty ranges are dropped."""
+        import ctypes as C
+        b = (C.c_int64 * 6)()
+        self._check(self._L.hippie_grad_bounds(self._h, b))
+        return [tuple(int(v) for v in b[3 * e:3 * e + 3]) for e in range(2) if b[3 * e + 2] > b[3 * e]]
 
     def train_forward(self, x1, x2, src, cls, eps, beta: float = 1.0, w1: float = 1.0, w2: float = 1.0, scalars=None):
         return self.eval_forward(x1, x2, src, cls, eps, beta, w1, w2, scalars, _fn="hippie_train_forward")

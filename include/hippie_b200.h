@@ -111,11 +111,19 @@ int hippie_train_fwd_bwd(hippie_handle h, const float* x1, const float* x2, cons
  *   part 0 = forward + loss + decoder backward + latent-head backward; when it completes, grads[hippie_grad_split(h) ..
  *            hippie_param_floats(h)) are final (latent head + both decoders, 52 % of the parameters);
  *   part 1 = encoder backward; afterwards grads[0 .. hippie_grad_split(h)) are final.
- * Calling part 0 then part 1 with the same arguments is equivalent to hippie_train_fwd_bwd. */
+ * Calling part 0 then part 1 with the same arguments is equivalent to hippie_train_fwd_bwd (parts 2, 3: below). */
 int hippie_train_fwd_bwd_part(hippie_handle h, const float* x1, const float* x2, const int64_t* src, const int64_t* cls,
                               const float* eps, int32_t B, float beta, float w1, float w2, float* scalars_out,
                               int32_t part, void* stream);
 int64_t hippie_grad_split(hippie_handle h);
+
+/* A finer split of the encoder backward for the same purpose: instead of part 1 call
+ *   part 2 = the deep half of every encoder (Linear, layer4, layer3: 94 % of an encoder's parameters), then
+ *   part 3 = the shallow half (layer2, layer1, stem).
+ * hippie_grad_bounds fills bounds[6] = {begin, deep, end} per encoder (second triple empty for the unimodal model):
+ * grads[deep .. end) are final after part 2, grads[begin .. deep) after part 3.  Parts 0, 2, 3 in this order are
+ * equivalent to hippie_train_fwd_bwd. */
+int hippie_grad_bounds(hippie_handle h, int64_t* bounds);
 
 /* Replaces Lightning's gradient_clip_val (scripts/train_model_with_multimodal.py:55,701 ->
  * torch.nn.utils.clip_grad_norm_) followed by torch.optim.AdamW.step (hippie/model.py:447).

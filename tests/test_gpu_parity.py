@@ -229,6 +229,26 @@ def test_split_step_equals_whole_step():
         assert rel <= 1e-5, rel
     assert 0 < split < eng.param_floats
     assert eng.params[[p.offset for p in eng.params].index(split)].name == "fusion_encoder.0.weight"
+    # parts 0, 2, 3: the encoder backward in its deep and shallow halves (hippie_grad_bounds)
+    bounds = eng.grad_bounds
+    names = {p.offset: p.name for p in eng.params}
+    assert [names[b] for b, _, _ in bounds] == ["encoder_mod1.conv1.weight", "encoder_mod2.conv1.weight"]
+    assert [names[d] for _, d, _ in bounds] == ["encoder_mod1.layer3.0.conv1.weight", "encoder_mod2.layer3.0.conv1.weight"]
+    assert bounds[0][2] == bounds[1][0] and bounds[1][2] == split
+    for _ in range(3):
+        eng.load_named(st)
+        s0 = eng.train_fwd_bwd_part(0, x1, x2, src, None, eps, 0.5, 1.0, 1.0)
+        eng.train_fwd_bwd_part(2, x1, x2, src, None, eps, 0.5, 1.0, 1.0)
+        deep = [eng.flat_grads[d:e].clone() for _, d, e in bounds]
+        for b, d, e in bounds:
+            assert eng.flat_grads[b:d].abs().max().item() == 0.0  # shallow halves untouched so far
+            assert eng.flat_grads[d:e].abs().max().item() > 0.0
+        eng.train_fwd_bwd_part(3, x1, x2, src, None, eps, 0.5, 1.0, 1.0)
+        for (b, d, e), saved in zip(bounds, deep):
+            assert torch.equal(eng.flat_grads[d:e], saved)  # part 3 does not touch the deep halves
+        assert torch.equal(s_whole[:4], s0[:4])
+        rel = ((eng.flat_grads - g_whole).norm() / g_whole.norm()).item()
+        assert rel <= 1e-5, rel
 
 
 def test_fp32_cuda_core_path_is_the_yardstick():

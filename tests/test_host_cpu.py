@@ -179,22 +179,30 @@ allv = [None, None]
 dist.all_gather_object(allv, mine)
 assert allv == [[0, 1, 2], [3, 4, 5]]
 
-class StubEngine:  # the host logic of the overlapped exchange, without a GPU: part 0 fills the tail, part 1 the head
+class StubEngine:  # the host logic of the overlapped exchange, without a GPU: every part fills its gradient ranges
     grad_split = 5
+    grad_bounds = [(0, 1, 3), (3, 4, 5)]  # (begin, deep, end) per encoder
     def __init__(self, rank):
         self.flat_grads = torch.zeros(12)
         self.rank, self.calls = rank, []
     def train_fwd_bwd_part(self, part, *a, **k):
         self.calls.append(part)
+        head = torch.arange(5, dtype=torch.float32) * (self.rank + 1)
         if part == 0:
             self.flat_grads.zero_()
             self.flat_grads[self.grad_split:] = torch.arange(7, dtype=torch.float32) + 10 * self.rank
+        elif part == 2:
+            for _, d, e in self.grad_bounds:
+                self.flat_grads[d:e] += head[d:e]
+        elif part == 3:
+            for b, d, _ in self.grad_bounds:
+                self.flat_grads[b:d] += head[b:d]
         else:
-            self.flat_grads[:self.grad_split] += torch.arange(5, dtype=torch.float32) * (self.rank + 1)
+            raise AssertionError("the overlapped step uses parts 0, 2, 3")
         return None
 eng = StubEngine(r)
 scale = train_step_overlapped(eng, None, None, None, None, None, 0.5)
-assert scale == 0.5 and eng.calls == [0, 1]
+assert scale == 0.5 and eng.calls == [0, 2, 3]
 assert torch.equal(eng.flat_grads[5:], 2 * torch.arange(7, dtype=torch.float32) + 10), eng.flat_grads
 assert torch.equal(eng.flat_grads[:5], 3 * torch.arange(5, dtype=torch.float32)), eng.flat_grads
 dist.destroy_process_group()
