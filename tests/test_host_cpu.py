@@ -50,6 +50,34 @@ def test_layout_matches_reference_construction_order(cfg):
                                                  if not O.is_buffer(k))
 
 
+@pytest.mark.parametrize("multimodal", [True, False])
+def test_gradient_exchange_ranges_cover_the_buffer_in_completion_order(multimodal):
+    """hippie_grad_split / hippie_grad_bounds: the ranges the data-parallel step all-reduces after parts 0, 2 and 3 are
+    disjoint, cover every parameter, start at parameter boundaries and follow the order the backward pass completes
+    them (latent head + decoders, then layer3 / layer4 / Linear of every encoder, then its stem / layer1 / layer2)."""
+    from hippie_b200.engine import Engine
+    cfg = O.CVAEConfig(z_dim=10) if multimodal else O.CVAEConfig(z_dim=10, multimodal=False, output_size_wave=50)
+    e = Engine(cfg.z_dim, cfg.output_size_wave, cfg.output_size_isi, cfg.class_hidden_dim, cfg.num_sources,
+               cfg.num_classes, cfg.multimodal, 64)
+    names = {p.offset: p.name for p in e.params}
+    split, bounds = e.grad_split, e.grad_bounds
+    assert len(bounds) == (2 if multimodal else 1)
+    pre = ["encoder_mod1", "encoder_mod2"] if multimodal else ["encoder"]
+    cover = []
+    for (b, d, end), name in zip(bounds, pre):
+        assert names[b] == name + ".conv1.weight" and names[d] == name + ".layer3.0.conv1.weight"
+        assert b < d < end
+        deep = [p for p in e.params if d <= p.offset < end]
+        assert all(p.name.startswith(name + ".layer3") or p.name.startswith(name + ".layer4")
+                   or p.name.startswith(name + ".linear") for p in deep)
+        assert sum(p.numel for p in deep) > 0.9 * sum(p.numel for p in e.params if b <= p.offset < end)
+        cover += [(b, d), (d, end)]
+    cover.append((split, e.param_floats))
+    cover.sort()
+    assert cover[0][0] == 0 and all(a[1] == b[0] for a, b in zip(cover, cover[1:])) and cover[-1][1] == e.param_floats
+    assert names[split] == ("fusion_encoder.0.weight" if multimodal else "encoder_fc.0.weight")
+
+
 def test_error_codes_without_gpu():
     from hippie_b200.engine import Engine
     with pytest.raises(ValueError):
