@@ -97,37 +97,76 @@ class ClockSampler(threading.Thread):
                 "samples": len(sm), "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
+def _reference_stepper():
+    """One optimisation step of the UNMODIFIED reference classes (baseline/_ref, the offline install of /root/reference;
+    loaded by oracle/ref_loader.py) in Lightning's call order: training_step -> zero_grad ->
+    backward -> clip_grad_norm_(1.0) -> AdamW.step.  Returns (step(x1, x2, src), kind) or None when baseline/_ref did
+    not travel (then the oracle port is timed)."""
+    import torch
+    try:
+        from oracle.ref_loader import load_reference
+        R = load_reference()
+    except Exception:
+        return None
+    torch.manual_seed(42)
+    base = R.model.MultiModalCVAE(Z, 50, 100, 5, 5, 5)
+    mod = R.model.MultiModalCVAETrainModule(base, learning_rate=1e-3, weight_decay=0.01, beta=0.5)
+    mod.train()
+
+    def step(x1, x2, src, i):
+        loss = mod.training_step((x1, x2, src), i)
+        mod.optimizer.zero_grad()
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(mod.parameters(), 1.0)
+        mod.optimizer.step()
+        return float(loss)
+    return step
+
+
 def cpu_reference_run(steps, warmup, budget_s=150.0):
-    """The reference's CPU arithmetic for the same step (oracle/cvae_oracle.py: torch CPU conv/BN/linear + autograd
-    + clip_grad_norm_ + AdamW in the reference's order), all host threads.  Returns (samples/s, cores, sample)."""
+    """The reference's CPU implementation of the same step on all host threads: the reference's own classes from
+    baseline/_ref (`kind` "reference"), else the oracle port (oracle/cvae_oracle.py, `kind` "port").  Each step is a
+    bounded sample of the bs512 workload.  Returns (samples/s, cores, sample, s/step, kind)."""
     import torch
     from oracle import cvae_oracle as O
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    cfg = O.CVAEConfig(z_dim=Z)
-    st = O.init_state(cfg, seed=42)
-    opt = O.new_opt_state(st, cfg)
     B = BS
     x1, x2, src = synth(B)
-    eps = torch.randn(B, Z, generator=torch.Generator().manual_seed(7))
+    ref_step = _reference_stepper()
+    if ref_step is not None:
+        kind = "reference"
 
-    def one(st, opt, B):
-        t0 = time.perf_counter()
-        st, opt, _ = O.train_step(st, opt, cfg, x1[:B], x2[:B], src[:B], eps[:B], lr=1e-3, weight_decay=0.01, beta=0.5,
-                                  max_norm=1.0)
-        return st, opt, time.perf_counter() - t0
+        def one(B, i=[0]):
+            t0 = time.perf_counter()
+            ref_step(x1[:B], x2[:B], src[:B], i[0])
+            i[0] += 1
+            return time.perf_counter() - t0
+    else:
+        kind = "port"
+        cfg = O.CVAEConfig(z_dim=Z)
+        state = [O.init_state(cfg, seed=42)]
+        state.append(O.new_opt_state(state[0], cfg))
+        eps = torch.randn(B, Z, generator=torch.Generator().manual_seed(7))
 
-    st, opt, t_first = one(st, opt, B)
+        def one(B):
+            t0 = time.perf_counter()
+            state[0], state[1], _ = O.train_step(state[0], state[1], cfg, x1[:B], x2[:B], src[:B], eps[:B], lr=1e-3,
+                                                 weight_decay=0.01, beta=0.5, max_norm=1.0)
+            return time.perf_counter() - t0
+
+    t_first = one(B)
     # bound the sample so that warmup + steps fit the budget
     while B > 32 and t_first * (steps + warmup) * (B / BS) > budget_s:
         B //= 2
     for _ in range(max(warmup - 1, 0)):
-        st, opt, _ = one(st, opt, B)
+        one(B)
     total = 0.0
     for _ in range(steps):
-        st, opt, dt = one(st, opt, B)
-        total += dt
-    return B * steps / total, cores, f"{steps} steps of bs{B} (fp32, torch CPU {torch.__version__}, {cores} threads)", total / steps
+        total += one(B)
+    what = "the reference's own classes (baseline/_ref)" if kind == "reference" else "oracle port"
+    return (B * steps / total, cores, f"{steps} steps of bs{B} ({what}, fp32, torch CPU {torch.__version__}, {cores} threads)",
+            total / steps, kind)
 
 
 def main():
@@ -152,15 +191,17 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        v, cores, sample, spp = cpu_reference_run(args.steps, max(args.warmup, 1))
+        v, cores, sample, spp, kind = cpu_reference_run(args.steps, max(args.warmup, 1))
         line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "samples/s", "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": spp * 1e3, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
-                "cpu_baseline": {"value": v, "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample},
+                "cpu_baseline": {"value": v, "unit": "samples/s", "cores": cores, "kind": kind, "sample": sample},
                 "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0,
-                "note": "reference = HIPPIE's own PyTorch CPU arithmetic restated in oracle/cvae_oracle.py (pytorch_lightning "
-                        "is not installable offline; /root/reference does not travel to the GPU box)"}
+                "note": "kind=reference: the UNMODIFIED reference classes (MultiModalCVAETrainModule.training_step + backward + "
+                        "clip_grad_norm_ + AdamW.step) from baseline/_ref = pip install --no-deps --target of /root/reference, "
+                        "driven in Lightning's call order (pytorch_lightning itself is not installable offline: 10-line "
+                        "LightningModule stand-in, oracle/_plstub); kind=port: oracle/cvae_oracle.py when baseline/_ref is absent"}
         print(json.dumps(line))
         return
 
@@ -383,8 +424,8 @@ def main():
 
     cpu = None
     if not args.no_cpu_baseline and world == 1:
-        v, cores, sample, _ = cpu_reference_run(8, 1, budget_s=30.0)
-        cpu = {"value": v, "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample}
+        v, cores, sample, _, kind = cpu_reference_run(8, 1, budget_s=30.0)
+        cpu = {"value": v, "unit": "samples/s", "cores": cores, "kind": kind, "sample": sample}
 
     line = {"metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,

@@ -12,7 +12,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libhippie_b200.so")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 
 class HippieCfg(C.Structure):
@@ -66,6 +66,11 @@ SIGNATURES = {
     "hippie_train_forward": (C.c_int, [_H, _f32p, _f32p, _i64p, _i64p, _f32p, C.c_int32, C.c_float, C.c_float,
                                        C.c_float, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, C.c_void_p]),
     "hippie_embed": (C.c_int, [_H, _f32p, _f32p, _i64p, _i64p, C.c_int32, C.c_int32, _f32p, _f32p, _f32p, C.c_void_p]),
+    "hippie_encoder_forward": (C.c_int, [_H, C.c_int32, _f32p, C.c_int32, C.c_int32, _f32p, C.c_void_p]),
+    "hippie_decoder_forward": (C.c_int, [_H, C.c_int32, _f32p, C.c_int32, C.c_int32, _f32p, C.c_void_p]),
+    "hippie_encode": (C.c_int, [_H, _f32p, _f32p, _f32p, _f32p, C.c_int32, C.c_int32, _f32p, _f32p, _f32p, C.c_void_p]),
+    "hippie_decode": (C.c_int, [_H, _f32p, _f32p, _f32p, C.c_int32, C.c_int32, _f32p, _f32p, C.c_void_p]),
+    "hippie_device_flags": (C.c_int, [_H, C.POINTER(C.c_uint32), C.c_int32, C.c_void_p]),
     "hippie_clip_adamw": (C.c_int, [_H, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
                                     C.c_int32, C.c_int32, C.c_int32, _f32p, C.c_void_p]),
     "hippie_preprocess_batch": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, _i64p, C.c_int32, _f32p, C.c_int32,

@@ -52,7 +52,18 @@ constexpr int PK = 64;  // K elements per k-block = one 128-byte swizzle row of 
 // a k-block is 384 box rows of 128 B; halving the rows to 64 B (32-wide k-blocks, 64-byte swizzle, 4 stages: tried)
 // costs 0.38 us per half block, i.e. the same ~1.4 ns per row.  More MACs per fetched row (wider tiles, 2-CTA pairs)
 // is the way to a faster main loop; deeper rings are not.
-constexpr int kBN = 64, kStages = 2;
+#ifndef HP_KBN
+#define HP_KBN 64
+#endif
+#ifndef HP_KSTAGES
+#define HP_KSTAGES 2
+#endif
+constexpr int kBN = HP_KBN, kStages = HP_KSTAGES;  // overridable for tools/pair_test experiments
+// Grids of at most one CTA per SM run a deeper ring (kStagesAlone, one CTA per SM by its shared-memory footprint):
+// the block scheduler otherwise packs part of such a grid two to an SM, and those CTAs share one SM's ~64 B/clk of
+// L2 -> shared-memory ingest while other SMs idle (512->512 L=4, 128 CTAs: 21.0 -> 16.1 us, tools/pair_test).
+constexpr int kStagesAlone = HP_KSTAGES > 3 ? HP_KSTAGES : 3;
+constexpr int ctas_per_sm(int bn, int stages) { return (PK * 2 * (128 + bn) * 2 * stages <= 100 * 1024 && bn <= 64) ? 2 : 1; }
 
 struct PairConv {
   float* C;
@@ -105,8 +116,10 @@ struct PairSmem {
 // scale, TMA store / add-reduce).  One instantiation per mode keeps each pipeline's code lean: with all three in one
 // kernel the eval epilogue ran 30 % slower (register allocation), measured on the embedding pass.
 constexpr int kConvTrain = 0, kConvEval = 1, kConvDgrad = 2;
+constexpr int kConvProducers = 4;   // TMA-issuing threads of conv_pair_kernel (warps 0, 2, 3, 4)
+constexpr int kWgradProducers = 5;  // of wgrad_pair_kernel (warps 0, 2, 3, 4, 5)
 template <int BN, int STAGES, int MODE>
-__global__ void __launch_bounds__(TC_THREADS, 2)
+__global__ void __launch_bounds__(TC_THREADS, ctas_per_sm(BN, STAGES))
     conv_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                      const __grid_constant__ CUtensorMap mapC, PairConv p) {
   constexpr bool EVAL = MODE == kConvEval, B_MN = MODE == kConvDgrad;
@@ -130,7 +143,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2)
     tma_prefetch_desc(&mapA);
     tma_prefetch_desc(&mapB);
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full[s], 1);
+      mbar_init(&full[s], kConvProducers);
       mbar_init(&empty[s], 1);
     }
     mbar_init(accum, 1);
@@ -149,41 +162,48 @@ __global__ void __launch_bounds__(TC_THREADS, 2)
   pdl_wait();  // everything above touched only shared / tensor memory
   if (threadIdx.x == 0) stamp(p, 1);
 
-  if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
-      const uint32_t tx_bytes = (uint32_t)(2 * rows_tile * 128 + 2 * S::B_PLANE);
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
-        mbar_wait(&empty[s], ph ^ 1u);
-        uint8_t* st = ring + s * S::STAGE_BYTES;
-        mbar_expect_tx(&full[s], tx_bytes);
-        tma_load_4d(st, &mapA, &full[s], kb * PK, 0, b0, 0);
-        tma_load_4d(st + S::A_LO, &mapA, &full[s], kb * PK, 0, b0, 1);
-        if (!B_MN) {
-          tma_load_3d(st + S::B_OFF, &mapB, &full[s], kb * PK, n0, 0);
-          tma_load_3d(st + S::B_LO, &mapB, &full[s], kb * PK, n0, 1);
-        } else {
-          const int u = kb / p.kb_per_tap, cob = kb - u * p.kb_per_tap;
-          const int tap = p.taps - 1 - u;
+  // ===================== TMA producers =====================
+  // One thread issues its tensor loads one after the other: a box costs ~235 cycles + 0.9 per 128-byte row whatever the
+  // ring depth (tools/tma_bw: 47 B/clk from one thread, up to ~90 B/clk per SM from several), and a k-block is four
+  // boxes.  So each of the four operand planes gets its own issuing thread in its own warp (warp 0 and the first three
+  // epilogue warps, which have nothing to do until the accumulator is complete).
+  if (warp != 1 && warp <= kConvProducers && lane == 0) {
+    const int pid = warp == 0 ? 0 : warp - 1;  // 0: A hi, 1: A lo, 2: B hi, 3: B lo
+    const uint32_t tx_bytes = pid < 2 ? (uint32_t)(rows_tile * 128) : (uint32_t)S::B_PLANE;
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int s = kb % STAGES;
+      const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
+      mbar_wait(&empty[s], ph ^ 1u);
+      uint8_t* st = ring + s * S::STAGE_BYTES;
+      mbar_expect_tx(&full[s], tx_bytes);
+      if (pid < 2) {
+        tma_load_4d(st + pid * S::A_LO, &mapA, &full[s], kb * PK, 0, b0, pid);
+      } else if (!B_MN) {
+        tma_load_3d(st + (pid == 2 ? S::B_OFF : S::B_LO), &mapB, &full[s], kb * PK, n0, pid - 2);
+      } else {
+        const int u = kb / p.kb_per_tap, cob = kb - u * p.kb_per_tap;
+        const int tap = p.taps - 1 - u;
 #pragma unroll
-          for (int g = 0; g < BN / 64; ++g) {  // one [64 co][64 ci] box per group of 64 output columns
-            tma_load_4d(st + S::B_OFF + g * 8192, &mapB, &full[s], n0 + g * 64, tap, cob * 64, 0);
-            tma_load_4d(st + S::B_LO + g * 8192, &mapB, &full[s], n0 + g * 64, tap, cob * 64, 1);
-          }
-        }
+        for (int g = 0; g < BN / 64; ++g)  // one [64 co][64 ci] box per group of 64 output columns
+          tma_load_4d(st + (pid == 2 ? S::B_OFF : S::B_LO) + g * 8192, &mapB, &full[s], n0 + g * 64, tap, cob * 64, pid - 2);
       }
     }
+  }
+  __syncwarp();
+
+  if (warp == 0) {
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
-        mbar_wait(&full[s], ph);
-        if (kb == 0) stamp(p, 2);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    // The whole warp walks the loop and an elected lane issues: inside an `if (lane == 0)` branch the compiler wraps
+    // every UTCHMMA in an ELECT / R2UR / BRA.U.ANY loop (~90 cycles per MMA instead of the 48 of the tensor pipe at
+    // N = 64, tools/mma_rate2).
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int s = kb % STAGES;
+      const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
+      mbar_wait(&full[s], ph);
+      if (kb == 0 && lane == 0) stamp(p, 2);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (elect_one()) {
         const uint32_t st = smem_u32(ring + s * S::STAGE_BYTES);
         const uint64_t a_hi = umma_desc(st, 16, 1024, 2), a_lo = umma_desc(st + S::A_LO, 16, 1024, 2);
         uint64_t b_hi, b_lo, badv;
@@ -204,8 +224,10 @@ __global__ void __launch_bounds__(TC_THREADS, 2)
         }
         umma_commit(&empty[s]);
       }
-      umma_commit(accum);
+      __syncwarp();
     }
+    if (elect_one()) umma_commit(accum);
+    __syncwarp();
   } else {
     // ===================== epilogue =====================
     const int t = threadIdx.x - 64;  // 0..127
@@ -290,7 +312,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2)
           y.x = y.x > 0.f ? y.x : y.x * fo.slope, y.y = y.y > 0.f ? y.y : y.y * fo.slope;
           y.z = y.z > 0.f ? y.z : y.z * fo.slope, y.w = y.w > 0.f ? y.w : y.w * fo.slope;
           if (fo.write_f32) *dst = y;
-          if (fo.out_p) store_pair4(fo.out_p, fo.out_ps, off, y);
+          if (fo.out_p) store_pair4(fo.out_p, fo.out_ps, off, y, fo.flags);
           if (fo.up_p) {
             const int64_t ou = ((int64_t)(b0 + bs) * (2 * p.Lout + 2) + 1 + 2 * l) * p.N + n0 + quad * 4;
             store_pair4(fo.up_p, fo.up_ps, ou, y);
@@ -386,7 +408,7 @@ struct PairWgrad {
 };
 
 template <int BN, int STAGES>
-__global__ void __launch_bounds__(TC_THREADS, 2)
+__global__ void __launch_bounds__(TC_THREADS, ctas_per_sm(BN, STAGES))
     wgrad_pair_kernel(const __grid_constant__ CUtensorMap mapDY, const __grid_constant__ CUtensorMap mapX,
                       const __grid_constant__ CUtensorMap mapDW, PairWgrad p) {
   using S = PairSmem<BN, STAGES>;
@@ -409,7 +431,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2)
     tma_prefetch_desc(&mapDY);
     tma_prefetch_desc(&mapX);
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full[s], 1);
+      mbar_init(&full[s], kWgradProducers);
       mbar_init(&empty[s], 1);
     }
     mbar_init(accum, 1);
@@ -427,20 +449,22 @@ __global__ void __launch_bounds__(TC_THREADS, 2)
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();  // everything above touched only shared / tensor memory
 
-  if (warp == 0) {
-    if (lane == 0) {
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
-        mbar_wait(&empty[s], ph ^ 1u);
-        uint8_t* st = ring + s * S::STAGE_BYTES;
-        mbar_expect_tx(&full[s], (uint32_t)S::STAGE_BYTES);
-        const int r0 = r_begin + kb * PK;
-#pragma unroll
-        for (int g = 0; g < TC_BM / 64; ++g) {
-          tma_load_3d(st + g * 8192, &mapDY, &full[s], m0 + g * 64, r0, 0);
-          tma_load_3d(st + S::A_LO + g * 8192, &mapDY, &full[s], m0 + g * 64, r0, 1);
-        }
+  // TMA producers: a k-block is 4 + 2 * (BN / 64) boxes of [64 rows][64 channels]; five issuing threads, one per warp
+  // (see conv_pair_kernel): 0..3 = dY (group, plane), 4 = X (both planes)
+  if (warp != 1 && lane == 0) {
+    const int pid = warp == 0 ? 0 : warp - 1;
+    const uint32_t tx_bytes = pid < 4 ? 8192u : (uint32_t)(2 * S::B_PLANE);
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int s = kb % STAGES;
+      const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
+      mbar_wait(&empty[s], ph ^ 1u);
+      uint8_t* st = ring + s * S::STAGE_BYTES;
+      mbar_expect_tx(&full[s], tx_bytes);
+      const int r0 = r_begin + kb * PK;
+      if (pid < 4) {
+        const int g = pid >> 1, pl = pid & 1;
+        tma_load_3d(st + pl * S::A_LO + g * 8192, &mapDY, &full[s], m0 + g * 64, r0, pl);
+      } else {
 #pragma unroll
         for (int g = 0; g < BN / 64; ++g) {
           tma_load_3d(st + S::B_OFF + g * 8192, &mapX, &full[s], n0 + g * 64, r0, 0);
@@ -448,13 +472,18 @@ __global__ void __launch_bounds__(TC_THREADS, 2)
         }
       }
     }
+  }
+  __syncwarp();
+
+  if (warp == 0) {
   } else if (warp == 1) {
-    if (lane == 0) {
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
-        mbar_wait(&full[s], ph);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    // MMA issuer: warp-uniform loop, elected lane (see conv_pair_kernel)
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int s = kb % STAGES;
+      const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
+      mbar_wait(&full[s], ph);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (elect_one()) {
         const uint32_t st = smem_u32(ring + s * S::STAGE_BYTES);
         const uint64_t a_hi = umma_desc(st, 8192, 1024, 2), a_lo = umma_desc(st + S::A_LO, 8192, 1024, 2);
         const uint64_t b_hi = umma_desc(st + S::B_OFF, 8192, 1024, 2), b_lo = umma_desc(st + S::B_LO, 8192, 1024, 2);
@@ -468,8 +497,10 @@ __global__ void __launch_bounds__(TC_THREADS, 2)
         }
         umma_commit(&empty[s]);
       }
-      umma_commit(accum);
+      __syncwarp();
     }
+    if (elect_one()) umma_commit(accum);
+    __syncwarp();
   } else {
     const int t = threadIdx.x - 64;
     mbar_wait(accum, 0);
@@ -514,12 +545,16 @@ __global__ void __launch_bounds__(TC_THREADS, 2)
 // fp32 -> pair planes (tools/pair_test and the weight refresh)
 template <int FMT>
 __global__ void to_pair_kernel(const float* __restrict__ src, uint16_t* __restrict__ hi, uint16_t* __restrict__ lo,
-                               int64_t n, float scale) {
+                               int64_t n, float scale, unsigned* __restrict__ flags) {
+  bool sat = false;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     uint16_t h, l;
-    pair_split<FMT>(src[i] * scale, h, l);
+    const float x = src[i] * scale;
+    pair_split<FMT>(x, h, l);
+    if (FMT == kPairF16) sat |= !(fabsf(x) < kPairF16Max);
     hi[i] = h, lo[i] = l;
   }
+  if (flags && sat) atomicOr(flags, kFlagWeightSaturated);
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -551,6 +586,17 @@ bool encode(TcMap* out, int fmt, int rank, const void* base, const cuuint64_t* d
 
 }  // namespace
 
+template <int STAGES>
+static void set_smem_attrs() {
+  const int bytes = PairSmem<kBN, STAGES>::TOTAL;
+  cudaFuncSetAttribute(conv_pair_kernel<kBN, STAGES, kConvTrain>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  cudaFuncSetAttribute(conv_pair_kernel<kBN, STAGES, kConvEval>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  cudaFuncSetAttribute(conv_pair_kernel<kBN, STAGES, kConvDgrad>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  cudaFuncSetAttribute(wgrad_pair_kernel<kBN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+}
+static int g_variant = 0, g_wgrad_variant = 1;
+static int g_sm_count = 148, g_alone_max = 74;
+
 bool pair_init(std::string* err) {
   if (!g_enc) {
     void* fn = nullptr;
@@ -563,14 +609,18 @@ bool pair_init(std::string* err) {
     g_enc = reinterpret_cast<EncodeTiledFn>(fn);
   }
   // function attributes belong to the current device's context: set them on every bind
-  cudaFuncSetAttribute(conv_pair_kernel<kBN, kStages, kConvTrain>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                       PairSmem<kBN, kStages>::TOTAL);
-  cudaFuncSetAttribute(conv_pair_kernel<kBN, kStages, kConvEval>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                       PairSmem<kBN, kStages>::TOTAL);
-  cudaFuncSetAttribute(conv_pair_kernel<kBN, kStages, kConvDgrad>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                       PairSmem<kBN, kStages>::TOTAL);
-  cudaFuncSetAttribute(wgrad_pair_kernel<kBN, kStages>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                       PairSmem<kBN, kStages>::TOTAL);
+  set_smem_attrs<kStages>();
+  set_smem_attrs<kStagesAlone>();
+  if (const char* v = getenv("HIPPIE_B200_PAIR_VARIANT")) g_variant = atoi(v);  // 0 auto, 1 always shared, 2 always alone
+  if (const char* v = getenv("HIPPIE_B200_WGRAD_VARIANT")) g_wgrad_variant = atoi(v);  // 1 shared (two CTAs per SM), 2 alone
+  int dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
+  // "alone" variant for grids of at most half the SMs: two such kernels (the two branches of the model) still run side
+  // by side; larger grids keep two CTAs per SM so that the chains and the weight gradients share every SM (bs512 step:
+  // 3.11 ms vs 3.24 ms with every grid <= 148 CTAs alone; bs64 step 1.70 -> 1.52 ms, gpurun_out/r02_variants_step.txt)
+  g_alone_max = g_sm_count / 2;
+  if (const char* v = getenv("HIPPIE_B200_ALONE_MAX")) g_alone_max = atoi(v);
   if (cudaGetLastError() != cudaSuccess) {
     if (err) *err = "cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed";
     return false;
@@ -634,6 +684,18 @@ bool pair_make_dw_map(TcMap* out, float* dW, int M, int N) {
 
 int pair_pick_bn(int, int, int, int) { return kBN; }
 
+template <int STAGES>
+static void launch_conv_variant(const PairOpts& o, dim3 grid, cudaStream_t s, const CUtensorMap& a, const CUtensorMap& w,
+                                const CUtensorMap& c, const PairConv& p) {
+  constexpr int smem = PairSmem<kBN, STAGES>::TOTAL;
+  if (o.b_mn)
+    launch_pdl(conv_pair_kernel<kBN, STAGES, kConvDgrad>, grid, dim3(TC_THREADS), smem, s, a, w, c, p);
+  else if (o.fold)
+    launch_pdl(conv_pair_kernel<kBN, STAGES, kConvEval>, grid, dim3(TC_THREADS), smem, s, a, w, c, p);
+  else
+    launch_pdl(conv_pair_kernel<kBN, STAGES, kConvTrain>, grid, dim3(TC_THREADS), smem, s, a, w, c, p);
+}
+
 int launch_conv_pair(const ConvGemm& g, const TcMap& mapA, const TcMap& mapB, int bn, int B, const PairOpts& o,
                      cudaStream_t s) {
   PairConv p{};
@@ -651,12 +713,11 @@ int launch_conv_pair(const ConvGemm& g, const TcMap& mapA, const TcMap& mapB, in
   const CUtensorMap& w = *reinterpret_cast<const CUtensorMap*>(mapB.opaque);
   p.tma_out = (o.out_map && g.out_lstride == 1) ? 1 : 0;
   const CUtensorMap& c = p.tma_out ? *reinterpret_cast<const CUtensorMap*>(o.out_map->opaque) : a;
-  if (o.b_mn)
-    launch_pdl(conv_pair_kernel<kBN, kStages, kConvDgrad>, grid, dim3(TC_THREADS), PairSmem<kBN, kStages>::TOTAL, s, a, w, c, p);
-  else if (o.fold)
-    launch_pdl(conv_pair_kernel<kBN, kStages, kConvEval>, grid, dim3(TC_THREADS), PairSmem<kBN, kStages>::TOTAL, s, a, w, c, p);
+  const bool alone = g_variant == 2 || (g_variant == 0 && (int)(grid.x * grid.y) <= g_alone_max);
+  if (alone)
+    launch_conv_variant<kStagesAlone>(o, grid, s, a, w, c, p);
   else
-    launch_pdl(conv_pair_kernel<kBN, kStages, kConvTrain>, grid, dim3(TC_THREADS), PairSmem<kBN, kStages>::TOTAL, s, a, w, c, p);
+    launch_conv_variant<kStages>(o, grid, s, a, w, c, p);
   return p.nb * g.Lout;
 }
 
@@ -668,7 +729,8 @@ void launch_wgrad_pair(const WgradGemm& g, const TcMap& mapDY, const TcMap& mapX
   bn = kBN;
   p.idesc = umma_idesc_16(bn, o.a_fmt, o.b_fmt, 1, 1);
   const int tiles = ((g.M + TC_BM - 1) / TC_BM) * (g.N / bn);
-  int splits = (2 * sm_count) / tiles;  // two CTAs per SM
+  const bool alone = g_wgrad_variant == 2;
+  int splits = ((alone ? 1 : 2) * sm_count) / tiles;  // one or two CTAs per SM
   const int kblocks = (g.R + PK - 1) / PK;
   if (splits > (kblocks + 3) / 4) splits = (kblocks + 3) / 4;  // at least 4 k-blocks (256 rows) per CTA
   if (splits < 1) splits = 1;
@@ -679,19 +741,22 @@ void launch_wgrad_pair(const WgradGemm& g, const TcMap& mapDY, const TcMap& mapX
   const CUtensorMap& a = *reinterpret_cast<const CUtensorMap*>(mapDY.opaque);
   const CUtensorMap& x = *reinterpret_cast<const CUtensorMap*>(mapX.opaque);
   const CUtensorMap& dw = *reinterpret_cast<const CUtensorMap*>(mapDW.opaque);
-  launch_pdl(wgrad_pair_kernel<kBN, kStages>, grid, dim3(TC_THREADS), PairSmem<kBN, kStages>::TOTAL, s, a, x, dw, p);
+  if (alone)
+    launch_pdl(wgrad_pair_kernel<kBN, kStagesAlone>, grid, dim3(TC_THREADS), PairSmem<kBN, kStagesAlone>::TOTAL, s, a, x, dw, p);
+  else
+    launch_pdl(wgrad_pair_kernel<kBN, kStages>, grid, dim3(TC_THREADS), PairSmem<kBN, kStages>::TOTAL, s, a, x, dw, p);
 }
 
 void launch_to_pair(const float* src, void* planes, int64_t plane_stride, int64_t n, float scale, int fmt,
-                    cudaStream_t s) {
+                    cudaStream_t s, unsigned* flags) {
   uint16_t* hi = static_cast<uint16_t*>(planes);
   int blocks = (int)((n + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
   if (blocks < 1) blocks = 1;
   if (fmt == kPairBF16)
-    to_pair_kernel<kPairBF16><<<blocks, 256, 0, s>>>(src, hi, hi + plane_stride, n, scale);
+    to_pair_kernel<kPairBF16><<<blocks, 256, 0, s>>>(src, hi, hi + plane_stride, n, scale, flags);
   else
-    to_pair_kernel<kPairF16><<<blocks, 256, 0, s>>>(src, hi, hi + plane_stride, n, scale);
+    to_pair_kernel<kPairF16><<<blocks, 256, 0, s>>>(src, hi, hi + plane_stride, n, scale, flags);
 }
 
 }  // namespace hp

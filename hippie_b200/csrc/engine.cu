@@ -182,6 +182,8 @@ struct hippie_engine {
   bool tma_epilogue = true;  // conv outputs leave through TMA tensor stores (HIPPIE_B200_TMA_STORE=0: per-thread stores)
   bool use_tc = false;  // tcgen05 implicit GEMMs over fp16 pair planes (conv_path 0); false = FP32 CUDA-core GEMMs
   std::string tc_note;
+  int64_t flags_off = 0;  // device error flags (HIPPIE_FLAG_*), sticky until hippie_device_flags clears them
+  unsigned* flags() { return reinterpret_cast<unsigned*>(ws + flags_off); }
   int64_t wp_off = 0;     // weight pair planes: hi plane at ws + wp_off (as halfs), lo plane param_floats elements later
   int64_t slots_off = 0;  // (max|g|, max|xhat|, max|k|, 1/scale) per gradient pair tensor, zeroed once per step
   int n_slots = 0;
@@ -215,7 +217,12 @@ struct hippie_engine {
     ws_floats += (floats + 63) & ~(int64_t)63;
     return r;
   }
-  int add_param(const std::string& name, int ndim, int64_t s0, int64_t s1, int64_t s2, int layout) {
+  // stand-alone backbones (cfg.multimodal = 2 / 3) have no module prefix: ".conv1.weight" -> "conv1.weight"
+  static std::string nm(const std::string& s) { return (!s.empty() && s[0] == '.') ? s.substr(1) : s; }
+  int pix(const std::string& name) const { return pidx.at(nm(name)); }
+  int bix(const std::string& name) const { return bidx.at(nm(name)); }
+  int add_param(const std::string& name_, int ndim, int64_t s0, int64_t s1, int64_t s2, int layout) {
+    const std::string name = nm(name_);
     Param p;
     p.name = name, p.ndim = ndim, p.shape[0] = s0, p.shape[1] = s1, p.shape[2] = s2, p.layout = layout;
     p.numel = s0 * (ndim > 1 ? s1 : 1) * (ndim > 2 ? s2 : 1);
@@ -229,7 +236,8 @@ struct hippie_engine {
     add_param(n + ".weight", 3, cout, cin, k, HIPPIE_LAYOUT_CONV_OKI);
     if (bias) add_param(n + ".bias", 1, cout, 0, 0, HIPPIE_LAYOUT_NATIVE);
   }
-  void spec_bn(const std::string& n, int c) {
+  void spec_bn(const std::string& n_, int c) {
+    const std::string n = nm(n_);
     BNInfo b;
     b.name = n, b.C = c;
     b.gamma = add_param(n + ".weight", 1, c, 0, 0, HIPPIE_LAYOUT_NATIVE);
@@ -291,9 +299,14 @@ struct hippie_engine {
     spec_conv(p + ".conv1.conv", 1, 64, 3, true);
     spec_linear(p + ".linear_out", output_size, 64);
   }
+  bool full_model() const { return cfg.multimodal == 0 || cfg.multimodal == 1; }
   void build_spec() {
     const int z = cfg.z_dim, h = cfg.class_hidden_dim;
-    if (cfg.multimodal) {  // MultiModalCVAE.__init__ (hippie/model.py:352-395)
+    if (cfg.multimodal == HIPPIE_KIND_ENCODER) {  // ResNet18Enc as a module of its own (hippie/backbones.py:73-103)
+      spec_encoder("", z);
+    } else if (cfg.multimodal == HIPPIE_KIND_DECODER) {  // ResNet18Dec (hippie/backbones.py:106-141)
+      spec_decoder("", z, cfg.len_wave);
+    } else if (cfg.multimodal) {  // MultiModalCVAE.__init__ (hippie/model.py:352-395)
       spec_encoder("encoder_mod1", z);
       spec_encoder("encoder_mod2", z);
       spec_linear("fusion_encoder.0", 2 * z, 4 * z + 2 * h);
@@ -330,7 +343,11 @@ struct hippie_engine {
 
   bool pair_mode() const { return cfg.conv_path != 1; }
   // kinds: kF32 = fp32 tensor, kPlanes = fp16 pair planes (only materialised on the tcgen05 path), kSlot = scale slot
-  int act(const std::string& name, int L, int C, int kinds = kF32) {
+  int act(const std::string& name_, int L, int C, int kinds = kF32) {
+    std::string name = name_;
+    for (const char* pre : {"g:.", "d:."})  // gradient tensors of a prefix-less backbone
+      if (name.rfind(pre, 0) == 0) name = name.substr(0, 2) + name.substr(3);
+    name = nm(name);
     Act a;
     a.name = name, a.L = L, a.C = C;
     const int64_t rows = (int64_t)cfg.max_batch * (L + 2) + 2;  // + one finite guard row on either side
@@ -360,8 +377,8 @@ struct hippie_engine {
   int gact_or(int a) { return cfg.inference_only ? -1 : act("d:" + acts[a].name, acts[a].L, acts[a].C); }
   Conv mkconv(const std::string& n, int cout, int cin, int k, int stride, bool bias, bool need_wt) {
     Conv c;
-    c.w = pidx.at(n + ".weight");
-    c.b = bias ? pidx.at(n + ".bias") : -1;
+    c.w = pix(n + ".weight");
+    c.b = bias ? pix(n + ".bias") : -1;
     c.cin = cin, c.cout = cout, c.k = k, c.stride = stride;
     c.id = n_convs++;
     if (need_wt && !cfg.inference_only && !pair_mode()) {
@@ -377,8 +394,8 @@ struct hippie_engine {
   void build_encoder(Encoder& E, const std::string& p, int Lin, bool train_tensors) {
     const int z = cfg.z_dim;
     E.prefix = p, E.Lin = Lin, E.L0 = conv_len(Lin, 3, 2, 1);
-    E.stem_w = pidx.at(p + ".conv1.weight");
-    E.bn0 = bidx.at(p + ".bn1");
+    E.stem_w = pix(p + ".conv1.weight");
+    E.bn0 = bix(p + ".bn1");
     E.c0 = act(p + ".conv1", E.L0, 64);
     bn_attach(E.bn0, E.c0);
     E.a0 = act(p + ".stem", E.L0, 64, kF32 | kPlanes);
@@ -394,14 +411,14 @@ struct hippie_engine {
         b.down = s != 1;
         b.c1 = mkconv(q + ".conv1", out, in_planes, 3, s, false, true);
         b.c2 = mkconv(q + ".conv2", out, out, 3, 1, false, true);
-        b.bn1 = bidx.at(q + ".bn1"), b.bn2 = bidx.at(q + ".bn2");
+        b.bn1 = bix(q + ".bn1"), b.bn2 = bix(q + ".bn2");
         b.x = x;
         b.c1o = act(q + ".conv1", Lout, out);
         b.a1 = act(q + ".a1", Lout, out, kF32 | kPlanes);
         b.c2o = act(q + ".conv2", Lout, out);
         if (b.down) {
           b.cs = mkconv(q + ".shortcut.0", out, in_planes, 1, s, false, true);
-          b.bns = bidx.at(q + ".shortcut.1");
+          b.bns = bix(q + ".shortcut.1");
           b.cso = act(q + ".shortcut", Lout, out);
         }
         b.out = act(q, Lout, out, (li * 2 + bi) < 7 ? (kF32 | kPlanes) : kF32);  // the last block feeds the pooling only
@@ -419,7 +436,7 @@ struct hippie_engine {
         }
         x = b.out, L = Lout, in_planes = planes[li];
       }
-    E.lin_w = pidx.at(p + ".linear.weight"), E.lin_b = pidx.at(p + ".linear.bias");
+    E.lin_w = pix(p + ".linear.weight"), E.lin_b = pix(p + ".linear.bias");
     E.pooled = take((int64_t)cfg.max_batch * 512);
     E.h = take((int64_t)cfg.max_batch * 2 * z);
     E.dh = take((int64_t)cfg.max_batch * 2 * z);
@@ -428,7 +445,7 @@ struct hippie_engine {
   void build_decoder(Decoder& D, const std::string& p, int Lo, bool train_tensors) {
     const int z = cfg.z_dim;
     D.prefix = p, D.Lo = Lo;
-    D.lin_w = pidx.at(p + ".linear.weight"), D.lin_b = pidx.at(p + ".linear.bias");
+    D.lin_w = pix(p + ".linear.weight"), D.lin_b = pix(p + ".linear.bias");
     D.t0 = act(p + ".linear", 4, 512, kF32 | kPlanes);
     int x = D.t0, L = 4, in_planes = 512;
     const int lis[4] = {4, 3, 2, 1}, planes[4] = {256, 128, 64, 64}, strides[4] = {2, 2, 2, 1};
@@ -441,13 +458,13 @@ struct hippie_engine {
         const int Lout = L * s;
         b.x = x;
         b.c2 = mkconv(q + ".conv2", in_planes, in_planes, 3, 1, false, true);
-        b.bn2 = bidx.at(q + ".bn2"), b.bn1 = bidx.at(q + ".bn1");
+        b.bn2 = bix(q + ".bn2"), b.bn1 = bix(q + ".bn1");
         b.c2o = act(q + ".conv2", L, in_planes);
         b.a2 = act(q + ".a2", L, in_planes, b.up ? kF32 : (kF32 | kPlanes));
         if (b.up) {
           b.c1 = mkconv(q + ".conv1.conv", out, in_planes, 3, 1, true, true);
           b.cs = mkconv(q + ".shortcut.0.conv", out, in_planes, 3, 1, true, true);
-          b.bns = bidx.at(q + ".shortcut.1");
+          b.bns = bix(q + ".shortcut.1");
           // the up-sampled copies are conv inputs only: pair planes, no fp32 tensor, on the tcgen05 path
           b.a2_up = act(q + ".a2_up", Lout, in_planes, kPlanes);
           b.x_up = act(q + ".x_up", Lout, in_planes, kPlanes);
@@ -477,61 +494,71 @@ struct hippie_engine {
     }
     for (int k = 0; k + 1 < 8; ++k)
       if (D.blk[k + 1].up) D.blk[k].out_up = D.blk[k + 1].x_up;
-    D.wc = pidx.at(p + ".conv1.conv.weight"), D.bc = pidx.at(p + ".conv1.conv.bias");
-    D.lo_w = pidx.at(p + ".linear_out.weight"), D.lo_b = pidx.at(p + ".linear_out.bias");
+    D.wc = pix(p + ".conv1.conv.weight"), D.bc = pix(p + ".conv1.conv.bias");
+    D.lo_w = pix(p + ".linear_out.weight"), D.lo_b = pix(p + ".linear_out.bias");
     const int64_t mb = cfg.max_batch;
     D.d = take(mb * 2 * z), D.dd = take(mb * 2 * z), D.gx0 = take(mb * 512);
     D.y = take(mb * 64), D.ddec = take(mb * Lo), D.dy = take(mb * 64), D.dec = take(mb * Lo);
     D.part = take(((mb + 3) / 4 + 1) * 196);
   }
 
-  int64_t off_of(const std::string& n) { return params[pidx.at(n)].off; }
+  int64_t off_of(const std::string& n) { return params[pix(n)].off; }
   void build() {
     build_spec();
     slots_off = take(4 * kMaxSlots);
-    const bool tr = !cfg.inference_only;
+    const bool tr = !cfg.inference_only && full_model();  // stand-alone backbones are forward-only
     const int z = cfg.z_dim;
-    n_enc = cfg.multimodal ? 2 : 1, n_dec = n_enc;
-    if (cfg.multimodal) {
+    flags_off = take(64);
+    if (cfg.multimodal == HIPPIE_KIND_ENCODER) {
+      n_enc = 1, n_dec = 0;
+      build_encoder(enc[0], "", cfg.len_wave, false);
+    } else if (cfg.multimodal == HIPPIE_KIND_DECODER) {
+      n_enc = 0, n_dec = 1;
+      build_decoder(dec[0], "", cfg.len_wave, false);
+    } else if (cfg.multimodal) {
+      n_enc = n_dec = 2;
       build_encoder(enc[0], "encoder_mod1", cfg.len_wave, tr);
       build_encoder(enc[1], "encoder_mod2", cfg.len_isi, tr);
       build_decoder(dec[0], "decoder_mod1", cfg.len_wave, tr);
       build_decoder(dec[1], "decoder_mod2", cfg.len_isi, tr);
     } else {
+      n_enc = n_dec = 1;
       build_encoder(enc[0], "encoder", cfg.len_wave, tr);
       build_decoder(dec[0], "decoder", cfg.len_wave, tr);
     }
     // head parameter map
     HeadParams& H = headp;
     memset(&H, 0xff, sizeof(H));  // all -1
-    const std::string f = cfg.multimodal ? "fusion_encoder" : "encoder_fc";
-    H.f0_w = off_of(f + ".0.weight"), H.f0_b = off_of(f + ".0.bias");
-    grad_split = H.f0_w;
-    for (int e = 0; e < 2; ++e) {
-      if (e < n_enc) {
-        const std::string pre = cfg.multimodal ? "encoder_mod" + std::to_string(e + 1) : "encoder";
-        enc_begin[e] = off_of(pre + ".conv1.weight"), enc_deep[e] = off_of(pre + ".layer3.0.conv1.weight");
-      } else {
-        enc_begin[e] = enc_deep[e] = grad_split;
+    if (full_model()) {
+      const std::string f = cfg.multimodal ? "fusion_encoder" : "encoder_fc";
+      H.f0_w = off_of(f + ".0.weight"), H.f0_b = off_of(f + ".0.bias");
+      grad_split = H.f0_w;
+      for (int e = 0; e < 2; ++e) {
+        if (e < n_enc) {
+          const std::string pre = cfg.multimodal ? "encoder_mod" + std::to_string(e + 1) : "encoder";
+          enc_begin[e] = off_of(pre + ".conv1.weight"), enc_deep[e] = off_of(pre + ".layer3.0.conv1.weight");
+        } else {
+          enc_begin[e] = enc_deep[e] = grad_split;
+        }
       }
-    }
-    enc_end[0] = n_enc == 2 ? enc_begin[1] : grad_split, enc_end[1] = grad_split;
-    H.fbn_g = off_of(f + ".1.weight"), H.fbn_b = off_of(f + ".1.bias");
-    H.f3_w = off_of(f + ".3.weight"), H.f3_b = off_of(f + ".3.bias");
-    H.fbn_run = bns[bidx.at(f + ".1")].run_off, H.fbn_cnt = bidx.at(f + ".1");
-    if (!cfg.multimodal) {
-      H.ebn_g = off_of(f + ".4.weight"), H.ebn_b = off_of(f + ".4.bias");
-      H.ebn_run = bns[bidx.at(f + ".4")].run_off, H.ebn_cnt = bidx.at(f + ".4");
-    }
-    H.src_emb = off_of("source_embedding.weight"), H.cls_emb = off_of("class_embedding.weight");
-    H.zm_w = off_of("z_mean.weight"), H.zm_b = off_of("z_mean.bias");
-    H.zv_w = off_of("z_log_var.weight"), H.zv_b = off_of("z_log_var.bias");
-    for (int m = 0; m < n_dec; ++m) {
-      const std::string d = cfg.multimodal ? "decoder_fc_mod" + std::to_string(m + 1) : "decoder_fc";
-      H.d0_w[m] = off_of(d + ".0.weight"), H.d0_b[m] = off_of(d + ".0.bias");
-      H.d2_w[m] = off_of(d + ".2.weight"), H.d2_b[m] = off_of(d + ".2.bias");
-      H.dbn_g[m] = off_of(d + ".3.weight"), H.dbn_b[m] = off_of(d + ".3.bias");
-      H.dbn_run[m] = bns[bidx.at(d + ".3")].run_off, H.dbn_cnt[m] = bidx.at(d + ".3");
+      enc_end[0] = n_enc == 2 ? enc_begin[1] : grad_split, enc_end[1] = grad_split;
+      H.fbn_g = off_of(f + ".1.weight"), H.fbn_b = off_of(f + ".1.bias");
+      H.f3_w = off_of(f + ".3.weight"), H.f3_b = off_of(f + ".3.bias");
+      H.fbn_run = bns[bix(f + ".1")].run_off, H.fbn_cnt = bix(f + ".1");
+      if (!cfg.multimodal) {
+        H.ebn_g = off_of(f + ".4.weight"), H.ebn_b = off_of(f + ".4.bias");
+        H.ebn_run = bns[bix(f + ".4")].run_off, H.ebn_cnt = bix(f + ".4");
+      }
+      H.src_emb = off_of("source_embedding.weight"), H.cls_emb = off_of("class_embedding.weight");
+      H.zm_w = off_of("z_mean.weight"), H.zm_b = off_of("z_mean.bias");
+      H.zv_w = off_of("z_log_var.weight"), H.zv_b = off_of("z_log_var.bias");
+      for (int m = 0; m < n_dec; ++m) {
+        const std::string d = cfg.multimodal ? "decoder_fc_mod" + std::to_string(m + 1) : "decoder_fc";
+        H.d0_w[m] = off_of(d + ".0.weight"), H.d0_b[m] = off_of(d + ".0.bias");
+        H.d2_w[m] = off_of(d + ".2.weight"), H.d2_b[m] = off_of(d + ".2.bias");
+        H.dbn_g[m] = off_of(d + ".3.weight"), H.dbn_b[m] = off_of(d + ".3.bias");
+        H.dbn_run[m] = bns[bix(d + ".3")].run_off, H.dbn_cnt[m] = bix(d + ".3");
+      }
     }
     head_scratch = take(head_scratch_floats(z, cfg.class_hidden_dim, cfg.max_batch));
     scal_off = take(64 + kHeadMaxCtas);  // [0],[1] squared-error sums, [64..) KL partials per head CTA
@@ -586,6 +613,7 @@ struct hippie_engine {
                        Branch& br) {
     EvalFold f{};
     f.coef = coef(bn), f.res = res >= 0 ? A(res) : nullptr, f.slope = slope, f.write_f32 = write_f32 ? 1 : 0;
+    f.flags = flags();
     if (acts[out].poff >= 0) f.out_p = PL(out), f.out_ps = acts[out].pstride;
     if (out_up >= 0 && acts[out_up].poff >= 0) f.up_p = PL(out_up), f.up_ps = acts[out_up].pstride;
     conv_fwd(cv, in, out, -1, B, false, br, &f);
@@ -648,6 +676,7 @@ struct hippie_engine {
     a.c = A(c), a.coef = coef(bn), a.r = r >= 0 ? A(r) : nullptr, a.rcoef = rbn >= 0 ? coef(rbn) : nullptr;
     a.out = A(out), a.out_up = out_up >= 0 ? A(out_up) : nullptr;
     a.B = B, a.L = acts[c].L, a.C = acts[c].C, a.slope = kSlopeBackbone;
+    a.flags = flags();
     if (use_tc) {
       if (acts[out].poff >= 0) a.out_p = PL(out), a.out_ps = acts[out].pstride;
       if (out_up >= 0 && acts[out_up].poff >= 0) a.up_p = PL(out_up), a.up_ps = acts[out_up].pstride;
@@ -819,7 +848,7 @@ struct hippie_engine {
   void decoder_fwd(Decoder& D, int B, bool train, Branch& br) {
     cudaEvent_t pe11 = prof_begin(br);
     launch_dec_linear_fwd(ws + D.d, B, 2 * cfg.z_dim, Pp(D.lin_w), Pp(D.lin_b), 512, A(D.t0),
-                          use_tc ? PL(D.t0) : nullptr, acts[D.t0].pstride, br.st);
+                          use_tc ? PL(D.t0) : nullptr, acts[D.t0].pstride, flags(), br.st);
     prof_end(pe11, 11, 0.0, br);
     ++launches;
     for (int i = 0; i < 8; ++i) {
@@ -916,6 +945,7 @@ struct hippie_engine {
     a.out_enc = out_enc, a.out_mu = out_mu, a.out_logvar = out_logvar;
     a.kl_sum = ws + scal_off + 64, a.train = train ? 1 : 0, a.decode = decode ? 1 : 0, a.zscore_ddof = zscore;
     a.beta = beta;
+    a.flags = flags();
     return a;
   }
 
@@ -923,7 +953,7 @@ struct hippie_engine {
   // MN-major by dgrad.  FP32 path: transposed + tap-flipped copies for dgrad.
   void refresh_weights(bool backward, cudaStream_t main) {
     if (use_tc) {
-      launch_to_pair(P, WP(), param_floats, param_floats, kWeightPairScale, kPairF16, main);
+      launch_to_pair(P, WP(), param_floats, param_floats, kWeightPairScale, kPairF16, main, flags());
       ++launches;
     } else if (backward && !wt_table.empty()) {
       launch_refresh_wt(reinterpret_cast<const WtEntry*>(ws + wt_table_off), (int)wt_table.size(), P, ws, main);
@@ -949,8 +979,15 @@ struct hippie_engine {
   }
   int validate(int B, const void* x1, const void* x2, const void* src) {
     if (!bound) return fail(-2, "hippie_bind has not been called");
+    if (!full_model()) return fail(-7, "stand-alone backbone engine: only hippie_encoder_forward / hippie_decoder_forward apply");
     if (B < 1 || B > cfg.max_batch) return fail(-3, "B outside [1, max_batch]");
     if (!x1 || !src || (cfg.multimodal && !x2)) return fail(-4, "null input pointer");
+    return 0;
+  }
+  int validate_module_call(int B, bool train) {
+    if (!bound) return fail(-2, "hippie_bind has not been called");
+    if (B < 1 || B > cfg.max_batch) return fail(-3, "B outside [1, max_batch]");
+    if (train && B < 2) return fail(-3, "training-mode BatchNorm needs B >= 2");
     return 0;
   }
 
@@ -1062,6 +1099,78 @@ struct hippie_engine {
     return check("hippie_embed");
   }
 
+  // ---- module-level API (eager launches; not on the training hot path) -----------------------------------------
+  void prepare_forward(bool train, cudaStream_t main) {
+    launches = 0;
+    if (train) cudaMemsetAsync(ws + tot_off, 0, tot_floats * sizeof(float), main);
+    refresh_weights(false, main);
+    if (!train) {
+      launch_bn_eval_coefs(reinterpret_cast<const BnEvalEntry*>(ws + bn_table_off), (int)bn_table.size(), P, bn_mean,
+                           bn_var, ws, main);
+      ++launches;
+    }
+  }
+  // ResNet18Enc.forward (hippie/backbones.py:94-103): x [B,1,Lin] -> [B,2z]
+  int run_encoder(int which, const float* x, int B, bool train, float* out, cudaStream_t main) {
+    prepare_forward(train, main);
+    Branch b0{main, ws + part_off[0], ws + bpart_off[0]};
+    encoder_fwd(enc[which], x, B, train, b0);
+    cudaMemcpyAsync(out, ws + enc[which].h, (size_t)B * 2 * cfg.z_dim * sizeof(float), cudaMemcpyDeviceToDevice, main);
+    if (failed) return fail(-9, err);
+    return check("hippie_encoder_forward");
+  }
+  // ResNet18Dec.forward (hippie/backbones.py:128-141): d [B,2z] -> [B,1,Lo]
+  int run_decoder(int which, const float* d, int B, bool train, float* out, cudaStream_t main) {
+    prepare_forward(train, main);
+    Branch b0{main, ws + part_off[0], ws + bpart_off[0]};
+    Decoder& D = dec[which];
+    cudaMemcpyAsync(ws + D.d, d, (size_t)B * 2 * cfg.z_dim * sizeof(float), cudaMemcpyDeviceToDevice, main);
+    decoder_fwd(D, B, train, b0);
+    decoder_tail(D, which, nullptr, out, B, false, 1.f, b0);
+    if (failed) return fail(-9, err);
+    return check("hippie_decoder_forward");
+  }
+  // MultiModalCVAE.encode (hippie/model.py:402-408) / hippieUnimodalCVAE.encode (:50-56): embeddings are inputs
+  int run_encode(const float* x1, const float* x2, const float* emb_src, const float* emb_cls, int B, bool train,
+                 float* out_enc, float* out_mu, float* out_logvar, cudaStream_t main) {
+    prepare_forward(train, main);
+    Branch b0{main, ws + part_off[0], ws + bpart_off[0]}, b1{side, ws + part_off[1], ws + bpart_off[1]};
+    const bool two = n_enc == 2;
+    if (two) fork(main);
+    encoder_fwd(enc[0], x1, B, train, b0);
+    if (two) {
+      encoder_fwd(enc[1], x2, B, train, b1);
+      join(main);
+    }
+    HeadArgs ha = head_args(B, nullptr, nullptr, nullptr, train, false, out_enc, out_mu, out_logvar, 0.f, -1);
+    ha.kl_sum = nullptr, ha.emb_src_in = emb_src, ha.emb_cls_in = emb_cls;
+    launch_head_fwd(ha, main);
+    ++launches;
+    if (failed) return fail(-9, err);
+    return check("hippie_encode");
+  }
+  // MultiModalCVAE.decode (hippie/model.py:410-422) / hippieUnimodalCVAE.decode (:58-61): z is an input
+  int run_decode(const float* z_in, const float* emb_src, const float* emb_cls, int B, bool train, float* out_dec1,
+                 float* out_dec2, cudaStream_t main) {
+    prepare_forward(train, main);
+    Branch b0{main, ws + part_off[0], ws + bpart_off[0]}, b1{side, ws + part_off[1], ws + bpart_off[1]};
+    HeadArgs ha = head_args(B, nullptr, nullptr, nullptr, train, true, nullptr, nullptr, nullptr, 0.f, -1);
+    ha.kl_sum = nullptr, ha.emb_src_in = emb_src, ha.emb_cls_in = emb_cls, ha.z_in = z_in, ha.stage = kHeadDecodeOnly;
+    launch_head_fwd(ha, main);
+    ++launches;
+    const bool two = n_dec == 2;
+    float* dec_out[2] = {out_dec1, out_dec2};
+    if (two) fork(main);
+    for (int m = 0; m < n_dec; ++m) {
+      Branch& br = m == 0 ? b0 : b1;
+      decoder_fwd(dec[m], B, train, br);
+      decoder_tail(dec[m], m, nullptr, dec_out[m], B, false, 1.f, br);
+    }
+    if (two) join(main);
+    if (failed) return fail(-9, err);
+    return check("hippie_decode");
+  }
+
   int exec(const CallArgs& a, cudaStream_t main) {
     if (a.mode == 3) return run_embed(a.x1, a.x2, a.src, a.cls, a.B, a.zscore, a.enc, a.mu, a.lv, main);
     const bool backward = a.mode == 0 || a.mode >= 4;
@@ -1140,13 +1249,14 @@ struct hippie_engine {
 // ------------------------------------------------------------------------------------------------
 extern "C" {
 
-int hippie_abi_version(void) { return 1; }
+int hippie_abi_version(void) { return 2; }
 
 int hippie_create(const hippie_cfg* cfg, hippie_handle* out) {
   if (!cfg || !out) return -1;
   *out = nullptr;
   if (cfg->z_dim < 1 || cfg->z_dim > 256 || cfg->class_hidden_dim < 1 || cfg->num_sources < 1 || cfg->num_classes < 1 ||
-      cfg->len_wave < 4 || (cfg->multimodal && cfg->len_isi < 4) || cfg->max_batch < 1)
+      cfg->len_wave < 4 || (cfg->multimodal == 1 && cfg->len_isi < 4) || cfg->max_batch < 1 || cfg->multimodal < 0 ||
+      cfg->multimodal > HIPPIE_KIND_DECODER)
     return -1;
   hippie_engine* e = new hippie_engine();
   e->cfg = *cfg;
@@ -1212,7 +1322,8 @@ int hippie_bind(hippie_handle h, float* params, float* grads, float* exp_avg, fl
                 float* bn_var, int64_t* bn_count, void* workspace, size_t workspace_bytes, void* stream) {
   if (!h) return -1;
   if (!params || !bn_mean || !bn_var || !bn_count || !workspace) return h->fail(-4, "null buffer");
-  if (!h->cfg.inference_only && (!grads || !exp_avg || !exp_avg_sq)) return h->fail(-4, "training engine needs grads and AdamW state");
+  if (!h->cfg.inference_only && h->full_model() && (!grads || !exp_avg || !exp_avg_sq))
+    return h->fail(-4, "training engine needs grads and AdamW state");
   if (workspace_bytes < (size_t)h->ws_floats * sizeof(float)) return h->fail(-5, "workspace too small");
   int dev = 0;
   cudaError_t ce = cudaGetDevice(&dev);
@@ -1317,12 +1428,56 @@ int hippie_embed(hippie_handle h, const float* x1, const float* x2, const int64_
   return h->call(a, (cudaStream_t)stream);
 }
 
+int hippie_encoder_forward(hippie_handle h, int32_t which, const float* x, int32_t B, int32_t train, float* out, void* stream) {
+  if (!h) return -1;
+  if (int rc = h->validate_module_call(B, train != 0)) return rc;
+  if (which < 0 || which >= h->n_enc) return h->fail(-3, "no such encoder");
+  if (!x || !out) return h->fail(-4, "null pointer");
+  return h->run_encoder(which, x, B, train != 0, out, (cudaStream_t)stream);
+}
+
+int hippie_decoder_forward(hippie_handle h, int32_t which, const float* d, int32_t B, int32_t train, float* out, void* stream) {
+  if (!h) return -1;
+  if (int rc = h->validate_module_call(B, train != 0)) return rc;
+  if (which < 0 || which >= h->n_dec) return h->fail(-3, "no such decoder");
+  if (!d || !out) return h->fail(-4, "null pointer");
+  return h->run_decoder(which, d, B, train != 0, out, (cudaStream_t)stream);
+}
+
+int hippie_encode(hippie_handle h, const float* x1, const float* x2, const float* source_emb, const float* class_emb,
+                  int32_t B, int32_t train, float* out_enc, float* out_mu, float* out_logvar, void* stream) {
+  if (!h) return -1;
+  if (int rc = h->validate_module_call(B, train != 0)) return rc;
+  if (!h->full_model()) return h->fail(-7, "stand-alone backbone engine");
+  if (!x1 || (h->cfg.multimodal && !x2) || !source_emb || !class_emb) return h->fail(-4, "null input pointer");
+  return h->run_encode(x1, x2, source_emb, class_emb, B, train != 0, out_enc, out_mu, out_logvar, (cudaStream_t)stream);
+}
+
+int hippie_decode(hippie_handle h, const float* z, const float* source_emb, const float* class_emb, int32_t B, int32_t train,
+                  float* out_dec1, float* out_dec2, void* stream) {
+  if (!h) return -1;
+  if (int rc = h->validate_module_call(B, train != 0)) return rc;
+  if (!h->full_model()) return h->fail(-7, "stand-alone backbone engine");
+  if (!z || !source_emb || !class_emb || !out_dec1 || (h->cfg.multimodal && !out_dec2)) return h->fail(-4, "null pointer");
+  return h->run_decode(z, source_emb, class_emb, B, train != 0, out_dec1, out_dec2, (cudaStream_t)stream);
+}
+
+int hippie_device_flags(hippie_handle h, uint32_t* flags_out, int32_t clear, void* stream) {
+  if (!h || !flags_out) return -1;
+  if (!h->bound) return h->fail(-2, "hippie_bind has not been called");
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t ce = cudaMemcpyAsync(flags_out, h->flags(), sizeof(uint32_t), cudaMemcpyDeviceToHost, st);
+  if (ce == cudaSuccess && clear) ce = cudaMemsetAsync(h->flags(), 0, sizeof(uint32_t), st);
+  if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);  // a diagnostic call: this one does wait for the stream
+  return ce == cudaSuccess ? 0 : h->fail((int)ce, std::string("hippie_device_flags: ") + cudaGetErrorString(ce));
+}
+
 int hippie_clip_adamw(hippie_handle h, float lr, float beta1, float beta2, float eps, float weight_decay, float max_norm,
                       float grad_scale, int32_t step, int32_t step_cls, int32_t has_cls_grad, float* scalars_out,
                       void* stream) {
   if (!h) return -1;
   if (!h->bound) return h->fail(-2, "hippie_bind has not been called");
-  if (h->cfg.inference_only) return h->fail(-7, "inference-only engine");
+  if (h->cfg.inference_only || !h->full_model()) return h->fail(-7, "inference-only engine");
   if (!scalars_out) return h->fail(-4, "scalars_out is required");
   if (step < 1) return h->fail(-3, "step is 1-based");
   AdamArgs a{};

@@ -396,16 +396,38 @@ __global__ void __launch_bounds__(THREADS) head_fwd_kernel(HeadArgs a) {
   for (int idx = tc.t0; idx < nb * D0; idx += tc.ts) {
     const int b = b_lo + idx / D0, j = idx % D0;
     float v;
-    if (j < E)
-      v = a.hin[j / Z2][(int64_t)b * Z2 + (j % Z2)];
-    else if (j < E + h)
-      v = W[P.src_emb + a.src[b] * h + (j - E)];
-    else
-      v = a.cls ? W[P.cls_emb + a.cls[b] * h + (j - E - h)] : 0.f;
+    if (j < E) {
+      v = a.stage == kHeadDecodeOnly ? 0.f : a.hin[j / Z2][(int64_t)b * Z2 + (j % Z2)];
+    } else if (j < E + h) {
+      if (a.emb_src_in) {  // encode() / decode() of the module API: the caller passes the embedding rows themselves
+        v = a.emb_src_in[(int64_t)b * h + (j - E)];
+      } else {  // nn.Embedding raises IndexError for such a label; here: flag it (hippie_device_flags) and read row 0
+        int64_t r = a.src[b];
+        if (r < 0 || r >= a.num_sources) {
+          if (a.flags) atomicOr(a.flags, kFlagSourceLabel);
+          r = 0;
+        }
+        v = W[P.src_emb + r * h + (j - E)];
+      }
+    } else {
+      if (a.emb_cls_in) {
+        v = a.emb_cls_in[(int64_t)b * h + (j - E - h)];
+      } else if (a.cls) {
+        int64_t r = a.cls[b];
+        if (r < 0 || r >= a.num_classes) {
+          if (a.flags) atomicOr(a.flags, kFlagClassLabel);
+          r = 0;
+        }
+        v = W[P.cls_emb + r * h + (j - E - h)];
+      } else {
+        v = 0.f;
+      }
+    }
     S[L.cat + (int64_t)b * D0 + j] = v;
   }
   __syncthreads();
   hstamp(1);  // S
+  if (a.stage != kHeadDecodeOnly) {
   ph_linear(tc, S + L.cat, D0, W + P.f0_w, W + P.f0_b, S + L.f0, Z2, D0, Z2, b_lo, b_hi, -1.f);
   __syncthreads();
   hstamp(2);  // S
@@ -493,6 +515,13 @@ __global__ void __launch_bounds__(THREADS) head_fwd_kernel(HeadArgs a) {
     a.kl_sum[blockIdx.x] = s;
   }
   if (!a.decode) return;
+  }  // stage != kHeadDecodeOnly
+  if (a.stage == kHeadDecodeOnly) {  // decode(z, source_emb, class_emb): z is an input
+    for (int idx = tc.t0; idx < nb * z; idx += tc.ts) {
+      const int b = b_lo + idx / z, i = idx % z;
+      S[L.zc + (int64_t)b * DZ + i] = a.z_in[(int64_t)b * z + i];
+    }
+  }
 
   // zc = [z, source_emb, class_emb]   (hippie/model.py:412-413)
   for (int idx = tc.t0; idx < nb * 2 * h; idx += tc.ts) {
@@ -686,6 +715,7 @@ __global__ void __launch_bounds__(THREADS) head_bwd_kernel(HeadArgs a) {
     if (is_cls && !a.cls) continue;
     const int k = is_cls ? k2 - h : k2;
     const int64_t row = is_cls ? a.cls[b] : a.src[b];
+    if (row < 0 || row >= (is_cls ? a.num_classes : a.num_sources)) continue;  // flagged by the forward kernel
     const float v = S[L.dcat + (int64_t)b * D0 + E + k2] + S[L.dzc + (int64_t)b * DZ + z + k2];
     atomicAdd(G + (is_cls ? P.cls_emb : P.src_emb) + row * h + k, v);
   }

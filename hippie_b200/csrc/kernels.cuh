@@ -71,6 +71,7 @@ struct EvalFold {
   int64_t out_ps = 0;
   uint16_t* up_p = nullptr;  // planes of the up-sampled copy: rows 2l, 2l+1 of a [B][2L+2][C] tensor
   int64_t up_ps = 0;
+  unsigned* flags = nullptr;  // device error flags (kFlagPairSaturated)
 };
 struct PairOpts {
   float out_scale;   // applied to the accumulator sum in the epilogue (2^-8 when B holds scaled weights)
@@ -97,7 +98,8 @@ int launch_conv_pair(const ConvGemm& g, const TcMap& mapA, const TcMap& mapB, in
 void launch_wgrad_pair(const WgradGemm& g, const TcMap& mapDY, const TcMap& mapX, const TcMap& mapDW, int bn, int sm_count,
                        const PairOpts& o, cudaStream_t s);
 // planes[0 .. n) = hi(src * scale), planes[plane_stride .. plane_stride + n) = lo
-void launch_to_pair(const float* src, void* planes, int64_t plane_stride, int64_t n, float scale, int fmt, cudaStream_t s);
+void launch_to_pair(const float* src, void* planes, int64_t plane_stride, int64_t n, float scale, int fmt, cudaStream_t s,
+                    unsigned* flags = nullptr);
 
 
 // ---- stem conv (Cin = 1, k3, s2, p1)  reference hippie/backbones.py:78,95 -----------------------------
@@ -159,6 +161,7 @@ struct BnApply {
   uint16_t* up_p = nullptr;
   int64_t up_ps = 0;
   unsigned long long* stamps = nullptr;  // tools/bn_test: %globaltimer phase stamps of CTA (0, 0)
+  unsigned* flags = nullptr;             // device error flags: kFlagPairSaturated when |out| exceeds the fp16 range
 };
 void launch_bn_apply(const BnApply& a, int sm_count, cudaStream_t s);
 
@@ -221,7 +224,7 @@ void launch_linear_wgrad(const float* dy, int ldy, const float* x, int ldx, int 
 
 // ---- decoder head: Linear(F -> 512) + unsqueeze + nearest x4   reference hippie/backbones.py:129-131 ---
 void launch_dec_linear_fwd(const float* d, int B, int F, const float* W, const float* bias, int C, float* t0,
-                           uint16_t* t0_p /*fp16 pair planes or null*/, int64_t t0_ps, cudaStream_t s);
+                           uint16_t* t0_p /*fp16 pair planes or null*/, int64_t t0_ps, unsigned* flags, cudaStream_t s);
 void launch_dec_linear_bwd_x(const float* g_t0, const float* W, int B, int F, int C, float* gx0, float* dd,
                              cudaStream_t s);
 
@@ -282,11 +285,21 @@ struct HeadArgs {
   int train;          // batch statistics + running update
   int decode;         // 0 = stop after mu/logvar (embedding pass)
   int zscore_ddof;    // -1 none; else z-score out_enc rows in place
+  // module API (MultiModalCVAE.encode / .decode, hippie/model.py:402-422): explicit embedding rows [B][h] instead of the
+  // label gathers, z [B][z] as an input, and which part of the head runs
+  const float* emb_src_in = nullptr;
+  const float* emb_cls_in = nullptr;
+  const float* z_in = nullptr;
+  int stage = 0;               // kHeadAll (decode = 0 stops after mu / logvar) or kHeadDecodeOnly
+  unsigned* flags = nullptr;   // device error flags (kFlag*), sticky until hippie_device_flags reads them
   // backward only
   const float* dd[2];  // gradients w.r.t. decoder_fc outputs
   float* dh[2];        // gradients w.r.t. encoder outputs
   float beta;
 };
+constexpr int kHeadAll = 0, kHeadDecodeOnly = 2;
+// device error flags (include/hippie_b200.h: HIPPIE_FLAG_*)
+constexpr unsigned kFlagSourceLabel = 1u, kFlagClassLabel = 2u, kFlagPairSaturated = 4u, kFlagWeightSaturated = 8u;
 int64_t head_scratch_floats(int z, int h, int B);
 constexpr int kHeadMaxCtas = 592;
 int launch_head_fwd(const HeadArgs& a, cudaStream_t s);  // returns the number of CTAs (= KL partials written)

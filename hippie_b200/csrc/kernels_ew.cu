@@ -306,7 +306,7 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(BnApply a) {
       }
       y.x = lrelu(y.x, a.slope), y.y = lrelu(y.y, a.slope), y.z = lrelu(y.z, a.slope), y.w = lrelu(y.w, a.slope);
       *reinterpret_cast<float4*>(a.out + row[u] * a.C + col) = y;
-      if (a.out_p) store_pair4(a.out_p, a.out_ps, row[u] * a.C + col, y);
+      if (a.out_p) store_pair4(a.out_p, a.out_ps, row[u] * a.C + col, y, a.flags);
       if (a.out_up) {
         *reinterpret_cast<float4*>(a.out_up + ru[u] * a.C + col) = y;
         *reinterpret_cast<float4*>(a.out_up + (ru[u] + 1) * a.C + col) = y;
@@ -703,7 +703,7 @@ __global__ void __launch_bounds__(256) dec_linear_fwd_kernel(const float* __rest
                                                              const float* __restrict__ W,
                                                              const float* __restrict__ bias, int C,
                                                              float* __restrict__ t0, uint16_t* __restrict__ t0_p,
-                                                             int64_t t0_ps) {
+                                                             int64_t t0_ps, unsigned* __restrict__ flags) {
   pdl_trigger();
   pdl_wait();
   extern __shared__ float sd[];  // [F]
@@ -720,6 +720,7 @@ __global__ void __launch_bounds__(256) dec_linear_fwd_kernel(const float* __rest
     if (t0_p) {
       uint16_t h, lo;
       pair_split<kPairF16>(s, h, lo);
+      if (flags && !(fabsf(s) < kPairF16Max)) atomicOr(flags, kFlagPairSaturated);
 #pragma unroll
       for (int l = 0; l < 4; ++l) {
         t0_p[((int64_t)b * 6 + 1 + l) * C + c] = h;
@@ -1115,8 +1116,8 @@ void launch_linear_wgrad(const float* dy, int ldy, const float* x, int ldx, int 
   launch_pdl(linear_wgrad_rows_kernel, dim3((nout * (nin + 1) + 63) / 64), dim3(256), 0, s, dy, ldy, x, ldx, B, nin, nout, dW, db);
 }
 void launch_dec_linear_fwd(const float* d, int B, int F, const float* W, const float* bias, int C, float* t0,
-                           uint16_t* t0_p, int64_t t0_ps, cudaStream_t s) {
-  launch_pdl(dec_linear_fwd_kernel, dim3(B), dim3(256), F * sizeof(float), s, d, F, W, bias, C, t0, t0_p, t0_ps);
+                           uint16_t* t0_p, int64_t t0_ps, unsigned* flags, cudaStream_t s) {
+  launch_pdl(dec_linear_fwd_kernel, dim3(B), dim3(256), F * sizeof(float), s, d, F, W, bias, C, t0, t0_p, t0_ps, flags);
 }
 void launch_dec_linear_bwd_x(const float* g_t0, const float* W, int B, int F, int C, float* gx0, float* dd,
                              cudaStream_t s) {

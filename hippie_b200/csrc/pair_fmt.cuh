@@ -27,8 +27,14 @@ __device__ __forceinline__ void pair_split(float x, uint16_t& h, uint16_t& l) {
   }
 }
 
-// 4 consecutive channels -> fp16 pair planes (hi at p, lo at p + ps), 8 bytes per plane
-__device__ __forceinline__ void store_pair4(uint16_t* p, int64_t ps, int64_t idx, float4 v) {
+constexpr float kPairF16Max = 65520.f;  // |x| >= this rounds past the largest finite fp16: cvt.satfinite clamps it
+
+// 4 consecutive channels -> fp16 pair planes (hi at p, lo at p + ps), 8 bytes per plane.  `flags` (optional): device
+// word that receives `bit` when a value saturates the hi plane (the product then silently loses its magnitude).
+__device__ __forceinline__ void store_pair4(uint16_t* p, int64_t ps, int64_t idx, float4 v, unsigned* flags = nullptr,
+                                            unsigned bit = 4u) {
+  if (flags && !(fabsf(v.x) < kPairF16Max && fabsf(v.y) < kPairF16Max && fabsf(v.z) < kPairF16Max && fabsf(v.w) < kPairF16Max))
+    atomicOr(flags, bit);  // also catches NaN / Inf
   uint16_t h0, h1, h2, h3, l0, l1, l2, l3;
   pair_split<kPairF16>(v.x, h0, l0), pair_split<kPairF16>(v.y, h1, l1);
   pair_split<kPairF16>(v.z, h2, l2), pair_split<kPairF16>(v.w, h3, l3);

@@ -191,10 +191,18 @@ class EphysBatchLoader:
             return len(self.sampler)
         return len(self.dataset) if self.indices is None else len(self.indices)
 
+    def _tail_kept(self, tail: int) -> bool:
+        """The ragged last global batch: dropped with `drop_last`; under data parallelism also when it cannot give every
+        rank at least two rows (training-mode BatchNorm needs two, and a rank that skipped the step would leave the others
+        waiting in the gradient all-reduce) -- every rank takes the same decision, so the step counts stay equal."""
+        if tail == 0 or self.drop_last:
+            return False
+        return self.world == 1 or tail >= 2 * self.world
+
     def __len__(self) -> int:
         per_step = self.batch_size * self.world
         n = self._n()
-        return n // per_step if self.drop_last else (n + per_step - 1) // per_step
+        return n // per_step + (1 if self._tail_kept(n % per_step) else 0)
 
     def _order(self):
         torch.empty((), dtype=torch.int64).random_()  # DataLoader: _base_seed of the iterator
@@ -215,14 +223,18 @@ class EphysBatchLoader:
         per_step = self.batch_size * self.world
         for lo in range(0, len(order), per_step):
             chunk = order[lo:lo + per_step]
-            if self.drop_last and len(chunk) < per_step:
-                break
-            mine = chunk[self.rank * self.batch_size:(self.rank + 1) * self.batch_size]
-            if not mine:
-                continue
+            if len(chunk) < per_step:
+                if not self._tail_kept(len(chunk)):
+                    break
+                # the tail is split evenly (contiguous shares in rank order), not by batch_size: no rank is left empty
+                base, rem = divmod(len(chunk), self.world)
+                a = self.rank * base + min(self.rank, rem)
+                mine = chunk[a:a + base + (1 if self.rank < rem else 0)]
+            else:
+                mine = chunk[self.rank * self.batch_size:(self.rank + 1) * self.batch_size]
             batch = self.dataset.batch(mine)
             if self.pin_memory and torch.cuda.is_available():
-                batch = tuple(t.pin_memory() for t in batch)
+                batch = tuple(t if t.is_cuda else t.pin_memory() for t in batch)  # DeviceTable batches are on the GPU already
             yield batch
 
 
@@ -260,3 +272,40 @@ class DeviceTable:
         if self.labels is None:
             return x1, x2
         return x1, x2, self.labels[idx]
+
+    @classmethod
+    def concat(cls, parts):
+        """torch.utils.data.ConcatDataset over device tables whose raw widths may differ (one source table each)."""
+        return DeviceTableGroup(parts)
+
+
+class DeviceTableGroup:
+    """Several `DeviceTable`s behind one global row index (the pretraining set of the reference is a ConcatDataset over the
+    source tables, scripts/train_model_with_multimodal.py:640-650).  A batch is one preprocessing launch per table that
+    contributes rows, then one gather that restores the requested order."""
+
+    def __init__(self, parts):
+        self.parts = list(parts)
+        assert self.parts, "at least one table"
+        labelled = [p.labels is not None for p in self.parts]
+        assert all(labelled) or not any(labelled), "either every table carries labels or none does"
+        self.labelled = all(labelled)
+        self.starts = np.cumsum([0] + [len(p) for p in self.parts])
+        self.device = self.parts[0].device
+
+    def __len__(self):
+        return int(self.starts[-1])
+
+    def batch(self, indices):
+        idx = np.asarray(list(indices), dtype=np.int64)
+        which = np.searchsorted(self.starts, idx, side="right") - 1
+        outs, pos = [], []
+        for t, part in enumerate(self.parts):
+            sel = np.nonzero(which == t)[0]
+            if sel.size:
+                outs.append(part.batch((idx[sel] - self.starts[t]).tolist()))
+                pos.append(sel)
+        if not outs:
+            return self.parts[0].batch([])
+        back = torch.as_tensor(np.argsort(np.concatenate(pos), kind="stable")).to(self.device)
+        return tuple(torch.cat([o[k] for o in outs])[back] for k in range(len(outs[0])))

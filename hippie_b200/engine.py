@@ -16,6 +16,9 @@ from . import _lib
 
 LAYOUT_NATIVE = 0
 LAYOUT_CONV_OKI = 1
+# hippie_cfg.multimodal (include/hippie_b200.h: HIPPIE_KIND_*)
+KIND_UNIMODAL, KIND_MULTIMODAL, KIND_ENCODER, KIND_DECODER = 0, 1, 2, 3
+FLAG_SOURCE_LABEL, FLAG_CLASS_LABEL, FLAG_PAIR_SATURATED, FLAG_WEIGHT_SATURATED = 1, 2, 4, 8
 
 
 @dataclass(frozen=True)
@@ -56,13 +59,16 @@ class Engine:
                  num_sources: int = 5, num_classes: int = 5, multimodal: bool = True, max_batch: int = 512,
                  inference_only: bool = False, conv_path: int = 0):
         self._L = _lib.lib()
+        self.kind = int(multimodal)  # bool (uni / multimodal cVAE) or KIND_ENCODER / KIND_DECODER (stand-alone backbone)
         self.cfg = _lib.HippieCfg(z_dim, class_hidden_dim, num_sources, num_classes, len_wave, len_isi,
-                                  1 if multimodal else 0, max_batch, 1 if inference_only else 0, conv_path)
+                                  self.kind, max_batch, 1 if inference_only else 0, conv_path)
         self._h = C.c_void_p()
         rc = self._L.hippie_create(C.byref(self.cfg), C.byref(self._h))
         if rc != 0:
             raise ValueError(f"hippie_create failed ({rc}): invalid configuration")
-        self.z_dim, self.multimodal, self.max_batch, self.inference_only = z_dim, multimodal, max_batch, inference_only
+        self.inference_only = bool(inference_only) or self.kind in (KIND_ENCODER, KIND_DECODER)
+        self.z_dim, self.multimodal, self.max_batch = z_dim, self.kind == KIND_MULTIMODAL, max_batch
+        self.class_hidden_dim, self.num_sources, self.num_classes = class_hidden_dim, num_sources, num_classes
         self.len_wave, self.len_isi = len_wave, len_isi
         self.param_floats = int(self._L.hippie_param_floats(self._h))
         self.bn_floats = int(self._L.hippie_bn_floats(self._h))
@@ -239,6 +245,62 @@ class Engine:
                                               -1.0 if max_norm is None else float(max_norm), grad_scale, step, step_cls,
                                               1 if has_cls_grad else 0, _ptr(scalars), self._stream()))
         return scalars
+
+    # ---- module-level forward calls (hippie/backbones.py forward(), MultiModalCVAE.encode / .decode) -------------
+    def encoder_forward(self, x, which: int = 0, train: bool = False):
+        B = x.shape[0]
+        assert x.dtype == torch.float32 and x.is_contiguous() and x.is_cuda
+        out = torch.empty(B, 2 * self.z_dim, dtype=torch.float32, device=self.device)
+        self._check(self._L.hippie_encoder_forward(self._h, which, _ptr(x), B, 1 if train else 0, _ptr(out), self._stream()))
+        return out
+
+    def decoder_forward(self, d, which: int = 0, train: bool = False):
+        B = d.shape[0]
+        assert d.dtype == torch.float32 and d.is_contiguous() and d.is_cuda and d.numel() == B * 2 * self.z_dim
+        L = self.len_isi if (self.multimodal and which == 1) else self.len_wave
+        out = torch.empty(B, 1, L, dtype=torch.float32, device=self.device)
+        self._check(self._L.hippie_decoder_forward(self._h, which, _ptr(d), B, 1 if train else 0, _ptr(out), self._stream()))
+        return out
+
+    def encode(self, x1, x2, source_emb, class_emb, train: bool = False):
+        B = x1.shape[0]
+        for t in (x1, x2, source_emb, class_emb):
+            assert t is None or (t.dtype == torch.float32 and t.is_contiguous() and t.is_cuda)
+        assert source_emb.shape == class_emb.shape == (B, self.class_hidden_dim)
+        o = {k: torch.empty(B, self.z_dim, dtype=torch.float32, device=self.device) for k in ("enc", "mu", "logvar")}
+        self._check(self._L.hippie_encode(self._h, _ptr(x1), _ptr(x2), _ptr(source_emb), _ptr(class_emb), B, 1 if train else 0,
+                                          _ptr(o["enc"]), _ptr(o["mu"]), _ptr(o["logvar"]), self._stream()))
+        return o["enc"], o["mu"], o["logvar"]
+
+    def decode(self, z, source_emb, class_emb, train: bool = False):
+        B = z.shape[0]
+        for t in (z, source_emb, class_emb):
+            assert t.dtype == torch.float32 and t.is_contiguous() and t.is_cuda
+        assert z.shape == (B, self.z_dim) and source_emb.shape == class_emb.shape == (B, self.class_hidden_dim)
+        d1 = torch.empty(B, 1, self.len_wave, dtype=torch.float32, device=self.device)
+        d2 = torch.empty(B, 1, self.len_isi, dtype=torch.float32, device=self.device) if self.multimodal else None
+        self._check(self._L.hippie_decode(self._h, _ptr(z), _ptr(source_emb), _ptr(class_emb), B, 1 if train else 0, _ptr(d1),
+                                          _ptr(d2), self._stream()))
+        return d1, d2
+
+    def device_flags(self, clear: bool = True) -> int:
+        """HIPPIE_FLAG_* word set by the kernels (bad label indices, fp16 pair-plane saturation).  Synchronises."""
+        f = C.c_uint32(0)
+        self._check(self._L.hippie_device_flags(self._h, C.byref(f), 1 if clear else 0, self._stream()))
+        return int(f.value)
+
+    def raise_on_flags(self):
+        """What the reference turns into exceptions: nn.Embedding's IndexError for a label outside the table; fp16
+        pair-plane saturation has no counterpart in the reference (fp32 operands) and raises OverflowError."""
+        f = self.device_flags()
+        if f & FLAG_SOURCE_LABEL:
+            raise IndexError(f"index out of range in self: a source label lies outside [0, {self.num_sources})")
+        if f & FLAG_CLASS_LABEL:
+            raise IndexError(f"index out of range in self: a class label lies outside [0, {self.num_classes})")
+        if f & (FLAG_PAIR_SATURATED | FLAG_WEIGHT_SATURATED):
+            what = "a parameter exceeded |w| < 255.9" if f & FLAG_WEIGHT_SATURATED else "an activation exceeded 65504"
+            raise OverflowError("hippie_b200: " + what + ": outside the range of the fp16 pair planes of the tensor-core "
+                                "GEMMs (use conv_path=1, the FP32 CUDA-core path, for such models)")
 
     def conv_path_in_use(self) -> int:
         """2 = tcgen05 implicit GEMMs over fp16 pair planes, 1 = FP32 CUDA-core GEMMs (valid after allocate())."""

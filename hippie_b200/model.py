@@ -16,154 +16,14 @@ from typing import Optional
 import torch
 import torch.nn as nn
 
-from .engine import Engine, LAYOUT_CONV_OKI
+from ._base import _EngineModule, _Node  # noqa: F401
+from . import backbones as _backbones  # noqa: F401  (registers the typed backbone containers of the module tree)
+from .engine import Engine, LAYOUT_CONV_OKI  # noqa: F401
 from .parallel import train_step_overlapped
 
 
-class _Node(nn.Module):
-    """Anonymous container used to reproduce the reference's module tree (and hence its state_dict keys)."""
-
-
-class _EngineModule(nn.Module):
-    """Base of MultiModalCVAE / hippieUnimodalCVAE: owns the Engine and the flat buffers."""
-
-    def __init__(self, *, z_dim, len_wave, len_isi, class_hidden_dim, num_sources, num_classes, multimodal,
-                 max_batch=512):
-        super().__init__()
-        self.z_dim = z_dim
-        self.class_hidden_dim = class_hidden_dim
-        self.num_sources = num_sources
-        self.num_classes = num_classes
-        self._max_batch = max_batch
-        self._cfg = dict(z_dim=z_dim, len_wave=len_wave, len_isi=len_isi, class_hidden_dim=class_hidden_dim,
-                         num_sources=num_sources, num_classes=num_classes, multimodal=multimodal)
-        object.__setattr__(self, "_engine", Engine(max_batch=max_batch, **self._cfg))
-        eng = self._engine
-        # CPU-resident flat storage until the module is moved to a CUDA device
-        self._flat = {
-            "params": torch.zeros(eng.param_floats),
-            "bn_mean": torch.zeros(eng.bn_floats),
-            "bn_var": torch.ones(eng.bn_floats),
-            "bn_count": torch.zeros(len(eng.bns), dtype=torch.int64),
-        }
-        self._param_objs = {}
-        self._build_tree()
-        self._reset_parameters()
-
-    # ---- module tree ---------------------------------------------------------------------------------
-    def _node(self, dotted: str) -> nn.Module:
-        m = self
-        for part in dotted.split("."):
-            if part not in m._modules:
-                m.add_module(part, _Node())
-            m = m._modules[part]
-        return m
-
-    def _build_tree(self):
-        eng = self._engine
-        bn_by_name = {b.name: b for b in eng.bns}
-        for p in eng.params:
-            mod_name, leaf = p.name.rsplit(".", 1)
-            node = self._node(mod_name)
-            param = nn.Parameter(Engine.view_of(self._flat["params"], p))
-            node.register_parameter(leaf, param)
-            self._param_objs[p.name] = param
-            if leaf == "bias" and mod_name in bn_by_name:  # BatchNorm: buffers follow weight, bias
-                b = bn_by_name[mod_name]
-                node.register_buffer("running_mean", self._flat["bn_mean"][b.offset:b.offset + b.channels])
-                node.register_buffer("running_var", self._flat["bn_var"][b.offset:b.offset + b.channels])
-                node.register_buffer("num_batches_tracked", self._flat["bn_count"][b.index])
-
-    def _rebind(self):
-        """Points every nn.Parameter / buffer at the current flat storage (after a device move)."""
-        eng = self._engine
-        for p in eng.params:
-            param = self._param_objs[p.name]
-            param.data = Engine.view_of(self._flat["params"], p)
-            param.grad = None
-        for b in eng.bns:
-            node = self._node(b.name)
-            node._buffers["running_mean"] = self._flat["bn_mean"][b.offset:b.offset + b.channels]
-            node._buffers["running_var"] = self._flat["bn_var"][b.offset:b.offset + b.channels]
-            node._buffers["num_batches_tracked"] = self._flat["bn_count"][b.index]
-
-    def _attach_grads(self):
-        """Exposes the engine's flat gradient buffer as `.grad` views (what loss.backward() fills in torch)."""
-        eng = self._engine
-        if eng.flat_grads is None:
-            return
-        for p in eng.params:
-            self._param_objs[p.name].grad = Engine.view_of(eng.flat_grads, p)
-
-    def _reset_parameters(self):
-        """nn.Conv1d / nn.Linear: kaiming_uniform_(a=sqrt(5)) weights, U(+-1/sqrt(fan_in)) biases;
-        nn.Embedding: N(0,1); nn.BatchNorm1d: ones / zeros -- drawn in construction order on the CPU
-        generator, as the reference does when it builds the model right after torch.manual_seed(42)."""
-        eng = self._engine
-        bn_names = {b.name for b in eng.bns}
-        fan_in_of = {}
-        with torch.no_grad():
-            for p in eng.params:
-                mod_name, leaf = p.name.rsplit(".", 1)
-                view = Engine.view_of(self._flat["params"], p)
-                if mod_name in bn_names:
-                    view.fill_(1.0 if leaf == "weight" else 0.0)
-                elif mod_name.endswith("_embedding"):
-                    view.copy_(torch.empty(p.shape).normal_())
-                elif leaf == "weight":
-                    fan_in = p.shape[1] * (p.shape[2] if len(p.shape) == 3 else 1)
-                    fan_in_of[mod_name] = fan_in
-                    gain = math.sqrt(2.0 / (1 + math.sqrt(5) ** 2))
-                    bound = math.sqrt(3.0) * gain / math.sqrt(fan_in)
-                    view.copy_(torch.empty(p.shape).uniform_(-bound, bound))
-                else:
-                    bound = 1 / math.sqrt(fan_in_of[mod_name])
-                    view.copy_(torch.empty(p.shape).uniform_(-bound, bound))
-
-    # ---- device moves ----------------------------------------------------------------------------------
-    def _apply(self, fn, recurse=True):
-        probe = fn(torch.zeros(1, dtype=torch.float32, device=self._flat["params"].device))
-        if probe.dtype != torch.float32:
-            raise TypeError("hippie_b200 models are fp32 only (the reference trains in fp32)")
-        if probe.device == self._flat["params"].device:
-            return self
-        eng = self._engine
-        if probe.device.type == "cuda":
-            old = self._flat
-            eng.allocate(probe.device)
-            eng.flat_params.copy_(old["params"])
-            eng.bn_mean.copy_(old["bn_mean"])
-            eng.bn_var.copy_(old["bn_var"])
-            eng.bn_count.copy_(old["bn_count"])
-            self._flat = {"params": eng.flat_params, "bn_mean": eng.bn_mean, "bn_var": eng.bn_var,
-                          "bn_count": eng.bn_count}
-        else:
-            self._flat = {k: v.detach().to(probe.device).clone() for k, v in self._flat.items()}
-        self._rebind()
-        return self
-
-    @property
-    def engine(self) -> Engine:
-        return self._engine
-
-    @property
-    def on_cuda(self) -> bool:
-        return self._flat["params"].is_cuda
-
-    def _require_cuda(self):
-        if not self.on_cuda:
-            raise RuntimeError("hippie_b200 has no CPU path: move the model to a CUDA device (model.to('cuda'))")
-
-    def _prep(self, data, n):
-        dev = self._flat["params"].device
-        data = data.to(dev, torch.float32, non_blocking=True).contiguous()
-        if data.shape[0] > self._max_batch:
-            raise ValueError(f"batch {data.shape[0]} exceeds max_batch={self._max_batch} this model was built with")
-        assert data.numel() == data.shape[0] * n, f"expected [B,1,{n}] input, got {tuple(data.shape)}"
-        return data
-
-    def _labels(self, t):
-        return None if t is None else t.to(self._flat["params"].device, torch.int64, non_blocking=True).contiguous()
+class _CVAEModule(_EngineModule):
+    """What the two cVAE classes share on top of the engine-backed base."""
 
     def reparameterize(self, mu, logvar):
         """reference hippie/model.py:397-400 (host-side convenience; the engine fuses this step)."""
@@ -174,10 +34,14 @@ class _EngineModule(nn.Module):
         # the reference draws randn_like(std) from the default generator of the tensor's device (hippie/model.py:399)
         return torch.randn(B, self.z_dim, device=self._flat["params"].device, dtype=torch.float32)
 
+    def _src_cls(self, source_labels, class_labels):
+        return (self._labels(source_labels, self.num_sources, "source label"),
+                self._labels(class_labels, self.num_classes, "class label"))
+
     def _forward_impl(self, x1, x2, source_labels, class_labels, eps=None):
         self._require_cuda()
         eng = self._engine
-        src, cls = self._labels(source_labels), self._labels(class_labels)
+        src, cls = self._src_cls(source_labels, class_labels)
         B = x1.shape[0]
         if eps is None:
             eps = self._draw_eps(B)
@@ -187,8 +51,14 @@ class _EngineModule(nn.Module):
             outs = eng.eval_forward(x1, x2, src, cls, eps)
         return outs
 
+    def _emb(self, t):
+        B = t.shape[0]
+        t = t.detach().to(self._flat["params"].device, torch.float32).contiguous()
+        assert t.shape == (B, self.class_hidden_dim), f"embedding rows must be [B, {self.class_hidden_dim}]"
+        return t
 
-class MultiModalCVAE(_EngineModule):
+
+class MultiModalCVAE(_CVAEModule):
     """reference hippie/model.py:350-432."""
 
     def __init__(self, z_dim, output_size_wave, output_size_isi, class_hidden_dim, num_sources, num_classes,
@@ -208,10 +78,26 @@ class MultiModalCVAE(_EngineModule):
         train_model_with_multimodal.py:22-34, without running the two decoders the reference discards)."""
         self._require_cuda()
         x1, x2 = self._prep(data1, self.output_size_wave), self._prep(data2, self.output_size_isi)
-        return self._engine.embed(x1, x2, self._labels(source_labels), self._labels(class_labels), zscore_ddof)
+        src, cls = self._src_cls(source_labels, class_labels)
+        return self._engine.embed(x1, x2, src, cls, zscore_ddof)
+
+    @torch.no_grad()
+    def encode(self, x1, x2, source_emb, class_emb):
+        """reference hippie/model.py:402-408: (h, z_mean(h), z_log_var(h)) from the two inputs and the embedding ROWS.
+        Forward only (no autograd graph): training goes through `training_step`."""
+        self._require_cuda()
+        a, b = self._prep(x1, self.output_size_wave), self._prep(x2, self.output_size_isi)
+        return self._engine.encode(a, b, self._emb(source_emb), self._emb(class_emb), train=self.training)
+
+    @torch.no_grad()
+    def decode(self, z, source_emb, class_emb):
+        """reference hippie/model.py:410-422: (recon1 [B,1,Lw], recon2 [B,1,Li]) from z and the embedding rows."""
+        self._require_cuda()
+        z = z.detach().to(self._flat["params"].device, torch.float32).contiguous()
+        return self._engine.decode(z, self._emb(source_emb), self._emb(class_emb), train=self.training)
 
 
-class hippieUnimodalCVAE(_EngineModule):
+class hippieUnimodalCVAE(_CVAEModule):
     """reference hippie/model.py:12-72."""
 
     def __init__(self, z_dim, output_size, class_hidden_dim, num_sources, num_classes, max_batch=512):
@@ -227,7 +113,22 @@ class hippieUnimodalCVAE(_EngineModule):
     def embed(self, data, source_labels, class_labels=None, zscore_ddof=-1):
         self._require_cuda()
         x = self._prep(data, self.output_size)
-        return self._engine.embed(x, None, self._labels(source_labels), self._labels(class_labels), zscore_ddof)
+        src, cls = self._src_cls(source_labels, class_labels)
+        return self._engine.embed(x, None, src, cls, zscore_ddof)
+
+    @torch.no_grad()
+    def encode(self, x, source_emb, class_emb):
+        """reference hippie/model.py:50-56 (forward only)."""
+        self._require_cuda()
+        return self._engine.encode(self._prep(x, self.output_size), None, self._emb(source_emb), self._emb(class_emb),
+                                   train=self.training)
+
+    @torch.no_grad()
+    def decode(self, z, source_emb, class_emb):
+        """reference hippie/model.py:58-61 (forward only)."""
+        self._require_cuda()
+        z = z.detach().to(self._flat["params"].device, torch.float32).contiguous()
+        return self._engine.decode(z, self._emb(source_emb), self._emb(class_emb), train=self.training)[0]
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -245,6 +146,7 @@ class FusedAdamW(torch.optim.Optimizer):
         self._step_cls = 0
         self.has_cls_grad = False
         self.last_scalars = None
+        self._surgery_seen = model._surgery_count  # a class table assigned later is not this optimizer's parameter
 
     @torch.no_grad()
     def step(self, closure=None, max_norm: Optional[float] = None, grad_scale: float = 1.0):
@@ -252,11 +154,12 @@ class FusedAdamW(torch.optim.Optimizer):
         self._model._require_cuda()
         g = self.param_groups[0]
         self._step += 1
-        if self.has_cls_grad:
+        has_cls = self.has_cls_grad and self._surgery_seen == self._model._surgery_count
+        if has_cls:
             self._step_cls += 1
         self.last_scalars = self._model.engine.clip_adamw(
             g["lr"], g["weight_decay"], self._step, max_norm=max_norm, grad_scale=grad_scale, betas=g["betas"],
-            eps=g["eps"], step_cls=max(self._step_cls, 1), has_cls_grad=self.has_cls_grad)
+            eps=g["eps"], step_cls=max(self._step_cls, 1), has_cls_grad=has_cls)
         return loss
 
     def zero_grad(self, set_to_none: bool = True):
@@ -317,6 +220,8 @@ class _TrainModuleBase(nn.Module):
         self.global_step = 0
         self._ring = None
         self._ring_pos = 0
+        self._val_sizes = []
+        self.val_loss_epoch = float("nan")
         self.world_size = 1  # set by the data-parallel trainer
         self.grad_scale = 1.0  # factor the optimizer applies to the (summed) gradients: 1 / world after an all-reduce
 
@@ -328,24 +233,36 @@ class _TrainModuleBase(nn.Module):
 
     def _scalars(self):
         dev = self.model._flat["params"].device
-        if self._ring is None or self._ring.device != dev:
+        if self._ring is None or self._ring.device != dev or self._ring_pos == self._SCALAR_RING:
+            # a fresh block: the epoch lists (train_loss / val_loss) hold views into the earlier ones, which therefore
+            # stay alive and are never overwritten, however many steps an epoch has
             self._ring = torch.zeros(self._SCALAR_RING, 8, dtype=torch.float32, device=dev)
+            self._ring_pos = 0
         s = self._ring[self._ring_pos]
-        self._ring_pos = (self._ring_pos + 1) % self._SCALAR_RING
+        self._ring_pos += 1
         return s
 
     @staticmethod
-    def _mean(vals):
+    def _mean(vals, weights=None):
         if not vals:
             return float("nan")
         if isinstance(vals[0], torch.Tensor):
-            return torch.stack([v.detach().float() for v in vals]).mean().item()  # one sync per epoch
+            v = torch.stack([x.detach().double() for x in vals])  # one sync per epoch
+            if weights:
+                w = torch.tensor(weights, dtype=torch.float64, device=v.device)
+                return ((v * w).sum() / w.sum()).item()
+            return v.mean().item()
         return sum(vals) / len(vals)
 
     def on_validation_epoch_end(self):
+        """The reference prints the plain mean of the per-batch losses (hippie/model.py:522-527); the value Lightning's
+        ModelCheckpoint / EarlyStopping monitor is the epoch aggregate of `self.log("val_loss", ...)`, which weights
+        every batch by its size.  Both are available: this returns the printed one, `val_loss_epoch` holds the other."""
         avg_loss = self._mean(self.val_loss)
+        self.val_loss_epoch = self._mean(self.val_loss, self._val_sizes) if self._val_sizes else avg_loss
         print(f"Average validation loss is {avg_loss:.2f}")
         self.val_loss = []
+        self._val_sizes = []
         return avg_loss
 
     def on_train_epoch_end(self):
@@ -353,6 +270,14 @@ class _TrainModuleBase(nn.Module):
         print(f"Average training loss is {avg_loss:.2f}")
         self.train_loss = []
         return avg_loss
+
+    def _device_labels(self, labels):
+        """(source, class | None) on the device; labels that arrive on the host are range-checked like nn.Embedding."""
+        m = self.model
+        src, cls = self._split_labels(labels)
+        src = m._labels(src, m.num_sources, "source label")
+        cls = m._labels(cls, m.num_classes, "class label")
+        return src, cls
 
     @staticmethod
     def _split_labels(labels):
@@ -380,9 +305,7 @@ class MultiModalCVAETrainModule(_TrainModuleBase):
         m._require_cuda()
         data1, data2, labels = batch
         x1, x2 = m._prep(data1, m.output_size_wave), m._prep(data2, m.output_size_isi)
-        src, cls = self._split_labels(m._labels(labels))
-        src = src.contiguous()
-        cls = cls.contiguous() if cls is not None else None
+        src, cls = self._device_labels(labels)
         if eps is None:
             eps = m._draw_eps(x1.shape[0])
         s = self._scalars()
@@ -401,15 +324,13 @@ class MultiModalCVAETrainModule(_TrainModuleBase):
         m._require_cuda()
         data1, data2, labels = batch
         x1, x2 = m._prep(data1, m.output_size_wave), m._prep(data2, m.output_size_isi)
-        src, cls = self._split_labels(m._labels(labels))
-        src = src.contiguous()
-        cls = cls.contiguous() if cls is not None else None
+        src, cls = self._device_labels(labels)
         if eps is None:
             eps = m._draw_eps(x1.shape[0])
         s = self._scalars()
         m.engine.eval_forward(x1, x2, src, cls, eps, float(self.beta), float(self.mod1_weight),
                               float(self.mod2_weight), scalars=s)
-        self.val_loss.append(s[0])
+        self.val_loss.append(s[0]), self._val_sizes.append(int(x1.shape[0]))
         self.log("val_loss", s[0]), self.log("val_mse_loss1", s[1])
         self.log("val_mse_loss2", s[2]), self.log("val_kl_loss", s[3])
         return s[0]
@@ -431,9 +352,7 @@ class hippieUnimodalEmbeddingModelCVAE(_TrainModuleBase):
         m._require_cuda()
         data, labels = batch
         x = m._prep(data, m.output_size)
-        src, cls = self._split_labels(m._labels(labels))
-        src = src.contiguous()
-        cls = cls.contiguous() if cls is not None else None
+        src, cls = self._device_labels(labels)
         if eps is None:
             eps = m._draw_eps(x.shape[0])
         s = self._scalars()
@@ -453,7 +372,7 @@ class hippieUnimodalEmbeddingModelCVAE(_TrainModuleBase):
 
     def validation_step(self, batch, batch_idx, eps=None):
         s = self._step(batch, False, eps)
-        self.val_loss.append(s[0])
+        self.val_loss.append(s[0]), self._val_sizes.append(int(batch[0].shape[0]))
         self.log("val_loss", s[0]), self.log("val_mse_loss", s[1]), self.log("val_kl_loss", s[3])
         return s[0]
 

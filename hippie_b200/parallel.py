@@ -28,6 +28,36 @@ def shard_units(n: int, rank: int, world: int):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
+def gather_rows(local: torch.Tensor, n_total: int, group=None) -> torch.Tensor:
+    """Inverse of `shard_units`: every rank passes the rows it computed for its contiguous shard of `n_total` units and
+    gets back all rows in unit order (rank order = row order of the CSV the reference writes).  The only communication of
+    the embedding path, after the compute; one all-gather of equally padded blocks."""
+    if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return local
+    world = dist.get_world_size(group)
+    sizes = [hi - lo for lo, hi in (shard_units(n_total, r, world) for r in range(world))]
+    assert local.shape[0] == sizes[dist.get_rank(group)], "rows do not match this rank's shard"
+    pad = local.new_zeros((max(sizes),) + tuple(local.shape[1:]))
+    pad[:local.shape[0]] = local
+    out = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(out, pad, group=group)
+    return torch.cat([o[:n] for o, n in zip(out, sizes)])
+
+
+def init_from_env(backend: str = "nccl"):
+    """torchrun plumbing for the command-line tools: one process per GPU (RANK / LOCAL_RANK / WORLD_SIZE / MASTER_* from
+    the environment).  Returns (rank, world); (0, 1) when not launched under torchrun."""
+    import os
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world <= 1:
+        return 0, 1
+    if backend == "nccl":
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+    if not dist.is_initialized():
+        dist.init_process_group(backend=backend)
+    return dist.get_rank(), dist.get_world_size()
+
+
 def all_reduce_gradients(flat_grads: torch.Tensor, group=None) -> float:
     """Sums the flat gradient buffer over the ranks (NCCL over NVLink on GPUs, gloo in the CPU tests) and returns
     the factor the optimizer kernel must apply (1/world)."""

@@ -127,10 +127,15 @@ class Trainer:
         self._module = None
         self.world_size = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
         self.rank = dist.get_rank() if self.world_size > 1 else 0
-        # lightning_logs/version_N like Lightning's default logger directory
+        # lightning_logs/version_N like Lightning's default logger directory; rank 0 picks it (the other ranks would race
+        # with rank 0 creating the directory) and everybody uses rank 0's choice
         n = 0
         while os.path.exists(os.path.join(default_root_dir, f"version_{n}")):
             n += 1
+        if self.world_size > 1:
+            box = [n]
+            dist.broadcast_object_list(box, src=0)
+            n = box[0]
         self.log_dir = os.path.join(default_root_dir, f"version_{n}")
 
     @property
@@ -159,16 +164,27 @@ class Trainer:
                     break
                 module.validation_step(batch, i)
                 n += 1
-        mean = module.on_validation_epoch_end() if n else float("nan")
+        rows = float(sum(getattr(module, "_val_sizes", None) or [n]))  # before the epoch-end hook clears the sizes
+        plain = module.on_validation_epoch_end() if n else float("nan")
+        # what Lightning's callbacks monitor: the epoch aggregate of self.log("val_loss"), weighted by batch size
+        mean = getattr(module, "val_loss_epoch", plain) if n else float("nan")
         if was_training:
             module.train()
+        if self.world_size > 1:  # every rank takes part, whatever it saw: (sum of loss x rows, rows)
+            ok = n > 0 and mean == mean
+            t = torch.tensor([mean * rows if ok else 0.0, rows if ok else 0.0], dtype=torch.float64,
+                             device=module.model._flat["params"].device)
+            dist.all_reduce(t)
+            n = int(float(t[1]) > 0)
+            mean = float(t[0] / t[1]) if n else float("nan")
         if sanity or not n:
             return None
-        if self.world_size > 1:
-            t = torch.tensor([mean], dtype=torch.float64, device=module.model._flat["params"].device)
-            dist.all_reduce(t)
-            mean = float(t.item()) / self.world_size
         return mean
+
+    def wait_for_checkpoint(self):
+        """Call before torch.load(ckpt.best_model_path) under data parallelism: rank 0 writes, everybody reads."""
+        if self.world_size > 1:
+            dist.barrier()
 
     def fit(self, module, train_dataloaders: Iterable, val_dataloaders: Optional[Iterable] = None):
         dev = self.device or (f"cuda:{torch.cuda.current_device()}" if torch.cuda.is_available() else None)
@@ -200,7 +216,8 @@ class Trainer:
                 if self.logger is not None and self.global_step % self.log_every_n_steps == 0 and self.is_global_zero:
                     self.logger.log_metrics({k: float(v) for k, v in module.logged.items()}, step=self.global_step)
             train_mean = module.on_train_epoch_end()
-            metrics = {"train_loss_epoch": train_mean}
+            module.model.check_device_flags()  # bad label indices / fp16 range: raised once per epoch (the epoch mean above
+            metrics = {"train_loss_epoch": train_mean}  # has synchronised already)
             if val_dataloaders is not None:
                 val_mean = self._run_validation(module, val_dataloaders, max_val, sanity=False)
                 if val_mean is not None:

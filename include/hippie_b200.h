@@ -46,12 +46,26 @@ typedef struct hippie_cfg {
   int32_t num_classes;
   int32_t len_wave;   /* output_size_wave (50); the single output_size when unimodal          */
   int32_t len_isi;    /* output_size_isi (100); ignored when unimodal                          */
-  int32_t multimodal; /* 1 = MultiModalCVAE, 0 = hippieUnimodalCVAE                             */
+  int32_t multimodal; /* 1 = MultiModalCVAE, 0 = hippieUnimodalCVAE; HIPPIE_KIND_ENCODER / _DECODER = a
+                         ResNet18Enc / ResNet18Dec on its own (hippie/backbones.py:73-141; forward-only engines:
+                         len_wave = input length / output_size, parameter names without a module prefix)       */
   int32_t max_batch;  /* largest B any call will pass; sizes the workspace                      */
   int32_t inference_only; /* 1 = no gradient tensors in the workspace (embedding engines)      */
   int32_t conv_path;  /* 0 = tcgen05 implicit GEMMs over fp16 pair planes (bind fails when TMA tensor maps are
                          unavailable), 1 = FP32 CUDA-core implicit GEMMs (the parity yardstick of the former)     */
 } hippie_cfg;
+
+enum { HIPPIE_KIND_UNIMODAL = 0, HIPPIE_KIND_MULTIMODAL = 1, HIPPIE_KIND_ENCODER = 2, HIPPIE_KIND_DECODER = 3 };
+
+/* Device-side error flags (hippie_device_flags): conditions the reference turns into exceptions or that silently lose
+ * precision here.  Sticky until cleared. */
+enum {
+  HIPPIE_FLAG_SOURCE_LABEL = 1,    /* a source label outside [0, num_sources): nn.Embedding raises IndexError; the kernels
+                                      read row 0 and skip the gradient of that sample                                    */
+  HIPPIE_FLAG_CLASS_LABEL = 2,     /* likewise for class labels and num_classes                                          */
+  HIPPIE_FLAG_PAIR_SATURATED = 4,  /* an activation fed to a GEMM exceeded the fp16 range of the pair planes (65504)     */
+  HIPPIE_FLAG_WEIGHT_SATURATED = 8 /* a parameter exceeded the range of the scaled weight planes (|w| >= 255.9)          */
+};
 
 /* Layout kinds of a parameter inside the flat buffer. */
 enum {
@@ -157,6 +171,25 @@ int hippie_train_forward(hippie_handle h, const float* x1, const float* x2, cons
  * zscore_ddof: -1 = raw `encoded`; 0 / 1 = per-row z-score with that ddof fused in. */
 int hippie_embed(hippie_handle h, const float* x1, const float* x2, const int64_t* src, const int64_t* cls,
                  int32_t B, int32_t zscore_ddof, float* out_enc, float* out_mu, float* out_logvar, void* stream);
+
+/* Module-level forward calls (eager launches, no gradients; `train` != 0: batch statistics + running-statistics update).
+ *   hippie_encoder_forward  replaces ResNet18Enc.forward (hippie/backbones.py:94-103): x [B,1,L] -> out [B,2z];
+ *   hippie_decoder_forward  replaces ResNet18Dec.forward (hippie/backbones.py:128-141): d [B,2z] -> out [B,1,output_size].
+ *     `which` selects encoder_mod1 / encoder_mod2 (decoder_mod1 / decoder_mod2) of a full model; 0 otherwise.
+ *   hippie_encode  replaces MultiModalCVAE.encode (hippie/model.py:402-408) / hippieUnimodalCVAE.encode (:50-56): the
+ *     embedding ROWS source_emb / class_emb [B, class_hidden_dim] are inputs, as in the reference;
+ *   hippie_decode  replaces .decode (hippie/model.py:410-422 / :58-61): z [B,z] is an input. */
+int hippie_encoder_forward(hippie_handle h, int32_t which, const float* x, int32_t B, int32_t train, float* out, void* stream);
+int hippie_decoder_forward(hippie_handle h, int32_t which, const float* d, int32_t B, int32_t train, float* out, void* stream);
+int hippie_encode(hippie_handle h, const float* x1, const float* x2, const float* source_emb, const float* class_emb,
+                  int32_t B, int32_t train, float* out_enc, float* out_mu, float* out_logvar, void* stream);
+int hippie_decode(hippie_handle h, const float* z, const float* source_emb, const float* class_emb, int32_t B, int32_t train,
+                  float* out_dec1, float* out_dec2, void* stream);
+
+/* Reads (and optionally clears) the HIPPIE_FLAG_* word the kernels set.  Unlike every other entry point this one waits
+ * for `stream` (one 4-byte device-to-host copy); call it at epoch boundaries or after a suspicious result.  The
+ * reference raises IndexError inside nn.Embedding for a bad label (hippie/model.py:425-426). */
+int hippie_device_flags(hippie_handle h, uint32_t* flags_out, int32_t clear, void* stream);
 
 /* Replaces EphysDataset / EphysDatasetLabeled.__getitem__ + DataLoader collation for one batch (hippie/dataloading.py:
  * 27-56, 74-101; normalize=False as every reference script passes): rows index[0..B) (NULL = rows 0..B-1) of raw,

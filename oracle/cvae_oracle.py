@@ -217,15 +217,22 @@ class _Ctx:
     """Carries mode + collects BatchNorm running-stat updates (functional: the caller's
     state is never mutated; `new_buffers` holds what the reference would have written)."""
 
-    def __init__(self, st, train: bool):
+    def __init__(self, st, train: bool, masks=None):
         self.st = st
         self.train = train
+        # test instrument (never set by the reference path): {activation name: bool [B,C,L]} forces the LeakyReLU branch
+        # of that site, so that a comparison with an implementation whose rounding put a ~0 input on the other side of
+        # zero measures arithmetic error instead of the factor-100 slope change (SURVEY.md F3 / A.7)
+        self.masks = masks
         self.new_buffers: Dict[str, torch.Tensor] = {}
         self.taps: Dict[str, torch.Tensor] = {}  # named intermediates for per-layer parity tests
 
 
-def _lrelu(x, slope):
-    return torch.where(x > 0, x, x * slope)
+def _lrelu(x, slope, cx=None, site=None):
+    pos = x > 0
+    if cx is not None and cx.masks is not None and site in cx.masks:
+        pos = cx.masks[site]
+    return torch.where(pos, x, x * slope)
 
 
 def _bn_apply(cx: _Ctx, name: str, x: torch.Tensor) -> torch.Tensor:
@@ -267,7 +274,7 @@ def _block_enc(cx: _Ctx, p: str, x, stride):
     # BasicBlockEnc.forward (backbones.py:36-41)
     out = _conv1d(cx, p + ".conv1", x, stride, 1)
     cx.taps[p + ".conv1"] = out
-    out = _lrelu(_bn_apply(cx, p + ".bn1", out), SLOPE_BACKBONE)
+    out = _lrelu(_bn_apply(cx, p + ".bn1", out), SLOPE_BACKBONE, cx, p + ".a1")
     cx.taps[p + ".a1"] = out
     out = _conv1d(cx, p + ".conv2", out, 1, 1)
     out = _bn_apply(cx, p + ".bn2", out)
@@ -275,7 +282,7 @@ def _block_enc(cx: _Ctx, p: str, x, stride):
         sc = x
     else:
         sc = _bn_apply(cx, p + ".shortcut.1", _conv1d(cx, p + ".shortcut.0", x, stride, 0))
-    out = _lrelu(out + sc, SLOPE_BACKBONE)
+    out = _lrelu(out + sc, SLOPE_BACKBONE, cx, p)
     cx.taps[p] = out
     return out
 
@@ -284,7 +291,7 @@ def _encoder(cx: _Ctx, p: str, x):
     # ResNet18Enc.forward (backbones.py:94-103)
     x = _conv1d(cx, p + ".conv1", x, 2, 1)
     cx.taps[p + ".conv1"] = x
-    x = _lrelu(_bn_apply(cx, p + ".bn1", x), SLOPE_BACKBONE)
+    x = _lrelu(_bn_apply(cx, p + ".bn1", x), SLOPE_BACKBONE, cx, p + ".stem")
     cx.taps[p + ".stem"] = x
     for li, stride in ((1, 1), (2, 2), (3, 2), (4, 2)):
         x = _block_enc(cx, f"{p}.layer{li}.0", x, stride)
@@ -296,7 +303,7 @@ def _encoder(cx: _Ctx, p: str, x):
 def _block_dec(cx: _Ctx, p: str, x, stride):
     # BasicBlockDec.forward (backbones.py:65-70); ResizeConv1d.forward (:13-16)
     out = _conv1d(cx, p + ".conv2", x, 1, 1)
-    out = _lrelu(_bn_apply(cx, p + ".bn2", out), SLOPE_BACKBONE)
+    out = _lrelu(_bn_apply(cx, p + ".bn2", out), SLOPE_BACKBONE, cx, p + ".a2")
     cx.taps[p + ".a2"] = out
     if stride == 1:
         out = _bn_apply(cx, p + ".bn1", _conv1d(cx, p + ".conv1", out, 1, 1))
@@ -304,7 +311,7 @@ def _block_dec(cx: _Ctx, p: str, x, stride):
     else:
         out = _bn_apply(cx, p + ".bn1", _conv1d(cx, p + ".conv1.conv", _up_nearest(out, stride), 1, 1))
         sc = _bn_apply(cx, p + ".shortcut.1", _conv1d(cx, p + ".shortcut.0.conv", _up_nearest(x, stride), 1, 1))
-    out = _lrelu(out + sc, SLOPE_BACKBONE)
+    out = _lrelu(out + sc, SLOPE_BACKBONE, cx, p)
     cx.taps[p] = out
     return out
 
@@ -335,14 +342,14 @@ def _decoder_fc(cx, p, z):
     return _lrelu(_bn_apply(cx, p + ".3", z), SLOPE_HEAD)
 
 
-def forward(st, cfg: CVAEConfig, x1, x2, src, cls=None, eps=None, train: bool = True):
+def forward(st, cfg: CVAEConfig, x1, x2, src, cls=None, eps=None, train: bool = True, masks=None):
     """MultiModalCVAE.forward (model.py:424-432) / hippieUnimodalCVAE.forward (:62-72).
 
     x1: [B,1,L1]; x2: [B,1,L2] (None when unimodal); src/cls: int64 [B] (cls None ->
     class embedding := zeros_like(source_emb)); eps: the N(0,1) draw of `reparameterize`
     (model.py:397-400), injected so that CPU and GPU see the same noise.
     Returns (outputs dict, new_buffers dict, taps dict)."""
-    cx = _Ctx(st, train)
+    cx = _Ctx(st, train, masks)
     source_emb = st["source_embedding.weight"][src]
     class_emb = st["class_embedding.weight"][cls] if cls is not None else torch.zeros_like(source_emb)
     if cfg.multimodal:
@@ -425,7 +432,7 @@ def new_opt_state(st, cfg):
 
 
 def train_step(st, opt, cfg: CVAEConfig, x1, x2, labels, eps, *, lr, weight_decay, beta,
-               w1=1.0, w2=1.0, max_norm: Optional[float] = 1.0, grad_hook=None):
+               w1=1.0, w2=1.0, max_norm: Optional[float] = 1.0, grad_hook=None, masks=None):
     """One Lightning-ordered optimisation step:
     training_step -> zero_grad -> backward -> clip_grad_norm_ -> AdamW.step.
     labels: int64 [B] (source only) or [B,2] = [class, source] (model.py:456-462).
@@ -437,7 +444,7 @@ def train_step(st, opt, cfg: CVAEConfig, x1, x2, labels, eps, *, lr, weight_deca
         cls, src = None, labels
     names = param_names(cfg)
     work = OrderedDict((k, (v.detach().clone().requires_grad_(True) if k in set(names) else v)) for k, v in st.items())
-    out, new_buf, _ = forward(work, cfg, x1, x2, src, cls, eps, train=True)
+    out, new_buf, _ = forward(work, cfg, x1, x2, src, cls, eps, train=True, masks=masks)
     total, mse1, mse2, klm = loss_terms(out, x1, x2, beta, w1, w2, cfg.multimodal)
     total.backward()
     grads = {n: work[n].grad for n in names if work[n].grad is not None}

@@ -3,8 +3,8 @@
 Run:  python oracle/make_golden.py            (needs /root/reference; writes tests/golden/)
 
 What it does
-  1. imports /root/reference/hippie/{backbones,model,dataloading}.py unmodified, with the
-     `pytorch_lightning` stand-in of oracle/_plstub on sys.path (Lightning is not installed);
+  1. imports /root/reference/hippie/{backbones,model,dataloading}.py unmodified (oracle/ref_loader.py: by path, so
+     that this repository's `hippie/` alias package cannot shadow them; `pytorch_lightning` stand-in of oracle/_plstub);
   2. drives the reference `MultiModalCVAETrainModule` / `hippieUnimodalEmbeddingModelCVAE`
      with the Lightning call order of SURVEY.md §3.2 (training_step -> zero_grad -> backward
      -> clip_grad_norm_(1.0) -> AdamW.step) on seeded inputs;
@@ -25,19 +25,18 @@ import torch
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(HERE, "_plstub"))
-sys.path.insert(0, "/root/reference")
 
 from oracle import cvae_oracle as O  # noqa: E402
+from oracle.ref_loader import load_reference  # noqa: E402
 
 torch.set_num_threads(8)
 NHEAD = 6  # leading elements of every tensor kept in the fixture
 
 
 def ref_modules():
-    from hippie import model as RM  # the reference
-    from hippie import dataloading as RD
-    return RM, RD
+    # loaded by path: this repository's own `hippie/` alias package would shadow the reference's namespace package
+    R = load_reference("/root/reference")
+    return R.model, R.dataloading
 
 
 def heads(d, names):

@@ -11,6 +11,11 @@ Additions: `--joint-checkpoint` embeds with a multimodal checkpoint instead of t
 `get_embeddings_multimodal` does); `--data-root`; UMAP / matplotlib are optional imports (the figures are skipped when
 they are missing); the embedding pass runs on the GPU through the encoder-only engine call (the reference's script can
 only run on CPU-only hosts because of `torch.device("gpu")`).
+
+Several GPUs (BASELINE.json config 4, "embedding inference sharded across 8 x B200"): launched under
+`torchrun --nproc-per-node N scripts/inference_from_trained_model.py ...` every rank embeds one contiguous shard of the
+units (hippie_b200.parallel.shard_units; eval-mode BatchNorm, so units are independent and nothing is exchanged during
+the compute), the rows are gathered in rank order and rank 0 writes the same CSV files a single GPU writes, bit for bit.
 """
 from __future__ import annotations
 
@@ -27,6 +32,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 
 from hippie_b200.dataloading import EphysBatchLoader, EphysTensorDataset  # noqa: E402
+from hippie_b200.parallel import gather_rows, init_from_env, shard_units  # noqa: E402
 from hippie_b200.model import (MultiModalCVAE, MultiModalCVAETrainModule, hippieUnimodalCVAE,  # noqa: E402
                                hippieUnimodalEmbeddingModelCVAE)
 from utils import get_embeddings, get_embeddings_multimodal  # noqa: E402
@@ -59,7 +65,7 @@ def load_into(module, path, num_classes):
         print(f"Warning: class embedding size mismatch in {os.path.basename(path)}; removing it from the checkpoint")
         state.pop(key)
     module.load_state_dict(state, strict=False)
-    return module.to("cuda").eval()
+    return module.to(f"cuda:{torch.cuda.current_device()}").eval()
 
 
 def umap_figure(embeddings, labels, title, path):
@@ -86,6 +92,7 @@ def main(argv=None):
     args = parse_args(argv)
     if not torch.cuda.is_available():
         raise SystemExit("hippie_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+    rank, world = init_from_env()
     os.makedirs(args.output_dir, exist_ok=True)
     torch.manual_seed(42)
     print(f"Loading dataset: {args.dataset}")
@@ -107,7 +114,8 @@ def main(argv=None):
     codes = labels.astype(np.int64) if np.issubdtype(labels.dtype, np.number) else pd.factorize(labels)[0]
     num_classes = len(np.unique(labels))
     data = EphysTensorDataset(wf, isi, codes)
-    loader = EphysBatchLoader(data, BATCH, shuffle=False)
+    lo, hi = shard_units(len(data), rank, world)  # this rank's contiguous shard of the units (all of them on one GPU)
+    loader = EphysBatchLoader(data, BATCH, shuffle=False, indices=range(lo, hi))
 
     print("Loading models from checkpoints...")
     results = {}
@@ -123,6 +131,11 @@ def main(argv=None):
         w, t, j = get_embeddings(proj("w"), proj("t"), wave, time)
         results = {"waveform": w, "isi": t, "joint": j}
 
+    if world > 1:  # rank order = unit order: rank 0 writes what a single GPU would have written
+        dev = torch.device("cuda", torch.cuda.current_device())
+        results = {k: gather_rows(torch.as_tensor(v).to(dev), len(data)).cpu().numpy() for k, v in results.items()}
+        if rank != 0:
+            return results
     print("Saving embeddings...")
     for name, emb in results.items():
         df = pd.DataFrame(emb)

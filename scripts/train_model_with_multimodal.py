@@ -302,7 +302,9 @@ def main(argv=None):
     n_train = int(args.train_val_split * len(idx))
     tr_idx, va_idx = [list(s) for s in random_split(idx, [n_train, len(idx) - n_train])]
     y_train, y_val = y[tr_idx], y[va_idx]
-    num_classes = len(np.unique(y_train))
+    # rows of the class table: every class of the label encoder, not only those that reached the training split (a
+    # class seen only in validation would index past the table; nn.Embedding raises IndexError there)
+    num_classes = len(le.classes_)
     src = all_sources[ds]
     stack = lambda yy: np.vstack((yy, src * np.ones_like(yy))).T  # [class, source] (hippie/model.py:456-460)
     d_train = EphysTensorDataset(sup_wf[tr_idx], sup_isi[tr_idx], stack(y_train))

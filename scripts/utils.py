@@ -34,6 +34,9 @@ def get_embeddings(dataloader_wave, dataloader_time, wave_model, time_model):
             st, ct = time_model._split_labels(label_time)
             e_wave.append(wave_model.model.embed(wave, sw, cw, zscore_ddof=1)["enc"])
             e_time.append(time_model.model.embed(time, st, ct, zscore_ddof=1)["enc"])
+    if not e_wave:  # an empty shard of a data-parallel inference run
+        z = np.zeros((0, wave_model.model.z_dim), dtype=np.float32)
+        return z, z, np.zeros((0, 2 * wave_model.model.z_dim), dtype=np.float32)
     w = torch.cat(e_wave).cpu().numpy()
     t = torch.cat(e_time).cpu().numpy()
     return w, t, np.concatenate([w, t], axis=1)

@@ -74,17 +74,29 @@ def to_dtype(st, dtype):
     return OrderedDict((k, v.to(dtype) if v.is_floating_point() else v) for k, v in st.items())
 
 
+def load_opt_state(eng, opt):
+    """AdamW moments of the oracle (dict name -> tensor) into the engine's flat exp_avg / exp_avg_sq buffers."""
+    for p in eng.params:
+        if p.name in opt["exp_avg"]:
+            eng.view_of(eng.exp_avg, p).copy_(opt["exp_avg"][p.name].to(torch.float32))
+            eng.view_of(eng.exp_avg_sq, p).copy_(opt["exp_avg_sq"][p.name].to(torch.float32))
+
+
 def run_train_case(cfg, B, labelled, seed=1234, beta=0.5, w1=1.0, w2=1.0, lr=1e-3, wd=0.01, clip=1.0,
-                   real_scale=False, conv_path=0, engine=None):
+                   real_scale=False, conv_path=0, engine=None, state=None, opt_state=None, inputs=None):
     """One teacher-forced optimisation step on the engine and on the oracle (fp32 and fp64).
-    Returns a dict of comparisons."""
+    `state` / `opt_state` (fp32, oracle layout) start the step from a given point of a run -- parameters, BatchNorm
+    buffers, AdamW moments and step counts -- instead of the perturbed initial state; `inputs` = (x1, x2, labels, eps)
+    replaces the synthetic batch.  Returns a dict of comparisons."""
     dev = torch.device("cuda:0")
-    x1, x2, labels, eps = case_inputs(cfg, B, labelled, seed, real_scale)
-    st = perturbed_state(cfg)
+    x1, x2, labels, eps = inputs if inputs is not None else case_inputs(cfg, B, labelled, seed, real_scale)
+    st = state if state is not None else perturbed_state(cfg)
     eng = engine or make_engine(cfg, max_batch=B, conv_path=conv_path)
     eng.load_named(st)
     if not eng.inference_only:
         eng.exp_avg.zero_(), eng.exp_avg_sq.zero_()
+        if opt_state is not None:
+            load_opt_state(eng, opt_state)
     cls, src = (labels.unbind(1) if labels.dim() == 2 else (None, labels))
     dx1, dx2 = x1.to(dev), (x2.to(dev) if x2 is not None else None)
     dsrc, dcls = src.contiguous().to(dev), (cls.contiguous().to(dev) if cls is not None else None)
@@ -102,6 +114,9 @@ def run_train_case(cfg, B, labelled, seed=1234, beta=0.5, w1=1.0, w2=1.0, lr=1e-
     for dt, tag in ((torch.float32, "f32"), (torch.float64, "f64")):
         s = to_dtype(st, dt)
         opt = O.new_opt_state(s, cfg)
+        if opt_state is not None:
+            opt = {"step": dict(opt_state["step"]), "exp_avg": to_dtype(opt_state["exp_avg"], dt),
+                   "exp_avg_sq": to_dtype(opt_state["exp_avg_sq"], dt)}
         new_st, new_opt, info = O.train_step(s, opt, cfg, x1.to(dt), x2.to(dt) if x2 is not None else None, labels,
                                              eps.to(dt), lr=lr, weight_decay=wd, beta=beta, w1=w1, w2=w2, max_norm=clip)
         with torch.no_grad():
@@ -158,6 +173,38 @@ def run_train_case(cfg, B, labelled, seed=1234, beta=0.5, w1=1.0, w2=1.0, lr=1e-
         flat_r += r * r
         flat_n += ref.norm().item() ** 2
     res["grad_err"] = gerr
+    # The same comparison with the LeakyReLU branches teacher-forced: the fp64 oracle is re-run with every backbone
+    # activation taking the branch the ENGINE took (resp. the branch the reference's fp32 run took, for the yardstick),
+    # so that inputs which rounding put on the other side of zero do not turn into factor-100 slope changes.
+    sites = [n for n, ref in taps64.items()
+             if n in tap_names and ref.dim() == 3 and not n.endswith(".conv1") and not n.endswith(".linear")]
+    m_eng = {n: (eng.tensor_view(n, B).detach().cpu() > 0) for n in sites}
+    m_f32 = {n: (taps32[n] > 0) for n in sites}
+    s64 = to_dtype(st, torch.float64)
+
+    def opt_of(dt):
+        o = O.new_opt_state(to_dtype(st, dt), cfg)
+        if opt_state is not None:
+            o = {"step": dict(opt_state["step"]), "exp_avg": to_dtype(opt_state["exp_avg"], dt),
+                 "exp_avg_sq": to_dtype(opt_state["exp_avg_sq"], dt)}
+        return o
+    x1d, x2d, epsd = x1.double(), (x2.double() if x2 is not None else None), eps.double()
+    kw = dict(lr=lr, weight_decay=wd, beta=beta, w1=w1, w2=w2, max_norm=clip)
+    _, _, i_me = O.train_step(s64, opt_of(torch.float64), cfg, x1d, x2d, labels, epsd, masks=m_eng, **kw)
+    _, _, i_m32 = O.train_step(s64, opt_of(torch.float64), cfg, x1d, x2d, labels, epsd, masks=m_f32, **kw)
+    gtf, fe, fr = {}, 0.0, 0.0
+    for n, ref in g64.items():
+        e = (grads[n].double() - i_me["grads_raw"][n]).norm().item()
+        r = (g32[n].double() - i_m32["grads_raw"][n]).norm().item()
+        gtf[n] = (e, r, ref.norm().item())
+        fe += e * e
+        fr += r * r
+    res["grad_err_tf"] = gtf
+    res["grad_flat_rel_tf"] = (fe ** 0.5) / (flat_n ** 0.5)
+    res["grad_flat_rel_f32_tf"] = (fr ** 0.5) / (flat_n ** 0.5)
+    res["loss_rel_tf"] = abs(float(s_eng[0]) - float(i_me["loss"])) / abs(float(i_me["loss"]))
+    res["unforced_sites"] = [n for n, ref in taps64.items() if ref.dim() == 3 and n not in tap_names
+                             and not n.endswith(".conv1") and not n.endswith(".linear")]
     res["grad_flat_rel"] = (flat_e ** 0.5) / (flat_n ** 0.5)
     res["grad_flat_rel_f32"] = (flat_r ** 0.5) / (flat_n ** 0.5)
     res["grad_global_norm"] = gnorm
@@ -175,7 +222,9 @@ def run_train_case(cfg, B, labelled, seed=1234, beta=0.5, w1=1.0, w2=1.0, lr=1e-
 
     # optimiser step
     has_cls = cls is not None
-    sc2 = eng.clip_adamw(lr, wd, step=1, max_norm=clip, step_cls=1, has_cls_grad=has_cls)
+    step_no = 1 + (max(opt_state["step"].values()) if opt_state is not None else 0)
+    step_cls = 1 + (opt_state["step"]["class_embedding.weight"] if opt_state is not None else 0)
+    sc2 = eng.clip_adamw(lr, wd, step=step_no, max_norm=clip, step_cls=step_cls, has_cls_grad=has_cls)
     torch.cuda.synchronize()
     res["launches_opt"] = eng.last_launch_count()
     sc2 = sc2.cpu()
@@ -223,6 +272,8 @@ def run_eval_case(cfg, B, labelled, seed=99, conv_path=0, engine=None, real_scal
     for k in ("enc", "mu", "logvar"):
         res["emb_err"][k] = (emb[k].detach().cpu().double() - o64[k]).abs().max().item()
     res["zscore_err"] = (emb_z["enc"].detach().cpu().double() - O.zscore_rows(o64["enc"], 0)).abs().max().item()
+    emb_z1 = eng.embed(dx1, dx2, dsrc, dcls, zscore_ddof=1)  # pandas' default std (inference CLI, scripts/utils.py)
+    res["zscore1_err"] = (emb_z1["enc"].detach().cpu().double() - O.zscore_rows(o64["enc"], 1)).abs().max().item()
     ref_l = torch.stack([tot, m1, m2, kl])
     res["loss_rel"] = ((scal[:4].cpu().double() - ref_l).abs() / ref_l.abs().clamp_min(1e-12)).tolist()
     return res, eng

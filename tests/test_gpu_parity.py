@@ -35,16 +35,27 @@ def _check_train(res, lr=1e-3):
         assert e <= max(10 * r, 2e-5 * max(scale, 1.0)), (k, e, r)
     for k, (e, r) in res["tap_err"].items():
         assert e <= max(10 * r, 2e-5), (k, e, r)
-    # Gradients.  A LeakyReLU input that is ~0 can take a different sign in fp32 than in fp64; that single element then
-    # scales its gradient path by 100 (slope 0.01 vs 1) and moves whole tensors by ~1/sqrt(#elements) ~ 1e-3..1e-2.
-    # The reference's own fp32 run does the same (oracle f32 column).  So: tight bound when neither side flipped,
-    # a gross-error bound (wrong layout / missing term would be O(1)) otherwise.
+    # Gradients: per tensor err(engine, fp64) <= 2 x err(reference fp32, fp64) with the 1e-6 * ||g|| floor,
+    # flat relative L2 <= 2e-3 -- with the LeakyReLU branches TEACHER-FORCED: a backbone activation whose input is ~0 can
+    # land on the other side of zero in any fp32 evaluation order (the reference's own fp32 run does, "flips" columns of
+    # profiles/r02_grad_error_table.md); that one element then scales its gradient path by 100 (slope 0.01 vs 1) and
+    # moves whole tensors by 1e-3..1e-2 whatever the arithmetic.  So the fp64 oracle is re-run with every such branch set
+    # to the one the compared implementation took (oracle `masks`), which leaves pure arithmetic error: measured worst
+    # ratio 0.9 .. 2.0 (tcgen05 pair planes) and 1.3 .. 2.8 (FP32 CUDA cores) over all cases, flat 2e-6 .. 6e-6.  The
+    # bound is 3 x (the ratio of two rounding-noise norms scatters), not the 10 x of round 1.
     gn = res["grad_global_norm"]
+    for n, (e, r, nn) in res["grad_err_tf"].items():
+        assert e <= 3.0 * r + 1e-6 * gn, (n, e, r, nn)
+    assert res["grad_flat_rel_tf"] <= min(2e-3, 3.0 * res["grad_flat_rel_f32_tf"] + 1e-6), \
+        (res["grad_flat_rel_tf"], res["grad_flat_rel_f32_tf"])
+    assert res["loss_rel_tf"] <= LOSS_RTOL
+    # ... and free-running (branches as each side took them): a gross-error bound (a wrong layout or a missing term
+    # would be O(1)); tight when neither side flipped
     clean = res["flips_eng"] == 0 and res["flips_f32"] == 0
     for n, (e, r, nn) in res["grad_err"].items():
-        bound = (10 * r + 2e-4 * nn) if clean else (10 * r + 0.05 * nn)
+        bound = (3 * r + 1e-6 * gn) if clean else (10 * r + 0.05 * nn)
         assert e <= bound + 1e-6 * gn, (n, e, r, nn, res["flips_eng"], res["flips_f32"])
-    assert res["grad_flat_rel"] <= (10 * res["grad_flat_rel_f32"] + 2e-4 if clean else 0.03), \
+    assert res["grad_flat_rel"] <= (3 * res["grad_flat_rel_f32"] + 1e-6 if clean else 0.03), \
         (res["grad_flat_rel"], res["grad_flat_rel_f32"], res["flips_eng"], res["flips_f32"])
     assert res["no_grad_params"] == []
     assert res["running_err"] <= 1e-5
@@ -131,8 +142,25 @@ def test_against_reference_golden_fixtures(golden_dir, tag):
     np.testing.assert_allclose(got[sel], ref_loss[sel], rtol=LOSS_RTOL, atol=1e-9)
     assert float(loss) == pytest.approx(float(ref_loss[0]), rel=LOSS_RTOL)
     np.testing.assert_allclose(tm.optimizer.last_scalars[4].item(), float(fx["f32_s0_grad_norm"]), rtol=3e-3)
+    # whole tensors through the fixture's checksums: per-tensor L2 norms of the reference's raw gradients
+    gnames = [str(n) for n in fx["s0_grad_names"]]
+    grads = m.engine.named_grads()
+    ref_l2 = fx["f32_s0_grad_l2"]
+    gtot = float(np.sqrt((ref_l2 ** 2).sum()))
+    for n, r in zip(gnames, ref_l2):
+        got_n = grads[n].double().norm().item()
+        assert abs(got_n - r) <= 5e-3 * r + 1e-5 * gtot, (n, got_n, r)
     names = [str(n) for n in fx["param_names"]]
     sd = m.state_dict()
+    # ... and the sums of the updated parameters (Adam's first step moves every element by ~lr: an element whose
+    # noise-level gradient has the other sign is off by 2 lr, so the bound scales with the tensor size)
+    for n, r in zip(names, fx["f32_s0_param_sum"]):
+        t = sd[n].detach().double()
+        assert abs(t.sum().item() - r) <= lr * (2.0 + 0.05 * t.numel()), (n, t.sum().item(), r)
+    run_names = [str(n) for n in fx["running_names"]]
+    run_head = np.stack([np.pad(sd[k].detach().cpu().double().flatten()[:6].numpy(), (0, max(0, 6 - sd[k].numel())))
+                         for k in run_names])
+    assert np.abs(run_head - fx["f32_s0_running_head"]).max() <= 1e-5 * max(1.0, np.abs(fx["f32_s0_running_head"]).max())
     head = np.stack([np.pad(sd[k].detach().cpu().double().flatten()[:6].numpy(), (0, max(0, 6 - sd[k].numel())))
                      for k in names])
     assert np.abs(head - fx["f32_s0_param_head"]).max() <= 2 * lr + 1e-7
@@ -192,7 +220,7 @@ def test_properties_at_benchmark_size_bs512():
     # clip invariant: after clipping the applied gradient has norm <= max_norm
     sc = eng.clip_adamw(1e-3, 0.01, 1, max_norm=1.0)
     norm, coef = sc[4].item(), sc[5].item()
-    assert abs(norm - g1.norm().item()) <= 1e-3 * norm or True
+    assert abs(norm - g1.norm().item()) <= 1e-4 * norm  # the device's norm is the norm of the gradient buffer
     assert coef == pytest.approx(min(1.0, 1.0 / (norm + 1e-6)), rel=1e-5)
     # eval-mode embedding: units are independent -> chunked == whole, bit for bit (idempotence under re-batching)
     whole = eng.embed(x1, x2, src)
