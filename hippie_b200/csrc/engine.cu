@@ -716,7 +716,8 @@ struct hippie_engine {
     } else {
       launch_conv_gemm_simt(g, br.st);
     }
-    prof_end(pe, 1, 2.0 * g.M * g.N * g.K, br);
+    // algorithmic FLOP: a stride-2 conv's output gradient is stored zero-dilated, half of the M x K products are zeros
+    prof_end(pe, 1, 2.0 * g.M * g.N * g.K / (cv.stride == 2 ? 2.0 : 1.0), br);
     ++launches;
   }
   // the weight-gradient stream of the branch waits for everything issued on the branch stream so far

@@ -116,29 +116,58 @@ class Engine:
         return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
     # ------------------------------------------------------------------------------------------
-    def allocate(self, device="cuda:0"):
+    def allocate(self, device="cuda:0", guard: int = 0):
         """Creates the flat fp32 buffers (params | grads | exp_avg | exp_avg_sq), BatchNorm buffers and the
-        workspace on `device` and hands them to the engine (hippie_bind)."""
+        workspace on `device` and hands them to the engine (hippie_bind).
+
+        `guard` > 0 (tests): every buffer is carved out of a larger allocation with `guard` canary elements on either
+        side; `check_guards()` verifies afterwards that no kernel wrote outside the buffers it was given (the pool this
+        repository is developed on does not allow compute-sanitizer, tests/test_gpu_parity2.py)."""
         device = torch.device(device)
         if device.type != "cuda" or not torch.cuda.is_available():
             raise RuntimeError("hippie_b200 runs on CUDA (sm_100a) only; there is no CPU fallback")
         self.device = device
+        self._guards = []
+
+        def buf(n, dtype, fill):
+            if not guard:
+                return torch.full((n,), fill, dtype=dtype, device=device)
+            canary = {torch.float32: float("nan"), torch.int64: -0x5A5A5A5A5A5A5A5B, torch.uint8: 0xA5}[dtype]
+            whole = torch.full((n + 2 * guard,), canary, dtype=dtype, device=device)
+            whole[guard:guard + n] = fill
+            self._guards.append((whole, guard, n))
+            return whole[guard:guard + n]
+
         with torch.cuda.device(device):
             n = self.param_floats
-            self.flat_params = torch.zeros(n, dtype=torch.float32, device=device)
+            self.flat_params = buf(n, torch.float32, 0)
             if not self.inference_only:
-                self.flat_grads = torch.zeros(n, dtype=torch.float32, device=device)
-                self.exp_avg = torch.zeros(n, dtype=torch.float32, device=device)
-                self.exp_avg_sq = torch.zeros(n, dtype=torch.float32, device=device)
-            self.bn_mean = torch.zeros(self.bn_floats, dtype=torch.float32, device=device)
-            self.bn_var = torch.ones(self.bn_floats, dtype=torch.float32, device=device)
-            self.bn_count = torch.zeros(len(self.bns), dtype=torch.int64, device=device)
-            self.workspace = torch.empty(self.workspace_bytes, dtype=torch.uint8, device=device)
+                self.flat_grads = buf(n, torch.float32, 0)
+                self.exp_avg = buf(n, torch.float32, 0)
+                self.exp_avg_sq = buf(n, torch.float32, 0)
+            self.bn_mean = buf(self.bn_floats, torch.float32, 0)
+            self.bn_var = buf(self.bn_floats, torch.float32, 1)
+            self.bn_count = buf(len(self.bns), torch.int64, 0)
+            self.workspace = buf(self.workspace_bytes, torch.uint8, 0) if guard else \
+                torch.empty(self.workspace_bytes, dtype=torch.uint8, device=device)
             self._check(self._L.hippie_bind(self._h, _ptr(self.flat_params), _ptr(self.flat_grads), _ptr(self.exp_avg),
                                             _ptr(self.exp_avg_sq), _ptr(self.bn_mean), _ptr(self.bn_var),
                                             _ptr(self.bn_count), _ptr(self.workspace), self.workspace_bytes,
                                             self._stream()))
         return self
+
+    def check_guards(self):
+        """Raises if any canary element around the bound buffers changed (see `allocate(guard=...)`)."""
+        torch.cuda.synchronize(self.device)
+        for whole, g, n in self._guards:
+            for side, part in (("before", whole[:g]), ("after", whole[g + n:])):
+                ref = torch.full_like(part, float("nan") if whole.dtype == torch.float32 else
+                                      (-0x5A5A5A5A5A5A5A5B if whole.dtype == torch.int64 else 0xA5))
+                a = part.view(torch.int32) if whole.dtype == torch.float32 else part
+                b = ref.view(torch.int32) if whole.dtype == torch.float32 else ref
+                if not torch.equal(a, b):
+                    bad = int((a != b).sum())
+                    raise AssertionError(f"{bad} canary elements {side} a {whole.dtype} buffer of {n} elements were overwritten")
 
     # ---- views ---------------------------------------------------------------------------------
     @staticmethod

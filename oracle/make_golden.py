@@ -1,6 +1,6 @@
 """Freeze golden vectors from the REFERENCE's own classes (build container only).
 
-Run:  python oracle/make_golden.py            (needs /root/reference; writes tests/golden/)
+Run:  python oracle/make_golden.py [--out DIR]   (needs /root/reference; writes tests/golden/ or DIR)
 
 What it does
   1. imports /root/reference/hippie/{backbones,model,dataloading}.py unmodified (oracle/ref_loader.py: by path, so
@@ -31,6 +31,7 @@ from oracle.ref_loader import load_reference  # noqa: E402
 
 torch.set_num_threads(8)
 NHEAD = 6  # leading elements of every tensor kept in the fixture
+OUT_DIR = os.path.join(ROOT, "tests", "golden")  # `python oracle/make_golden.py --out DIR` writes elsewhere (CI re-check)
 
 
 def ref_modules():
@@ -187,7 +188,7 @@ def run_case(tag, cfg, x1, x2, labels, eps_seeds, hyper, steps):
             fx[f"{dt}_eval_{k}"] = r.numpy()
         print(f"[{tag}/{dt}] eval-mode forward pinned")
     fx["eval_eps_seed"] = np.array(777)
-    out = os.path.join(ROOT, "tests", "golden", f"{tag}.npz")
+    out = os.path.join(OUT_DIR, f"{tag}.npz")
     np.savez_compressed(out, **fx)
     print(f"[{tag}] wrote {out} ({os.path.getsize(out) / 1024:.1f} KiB)")
 
@@ -217,7 +218,7 @@ def main():
     hyper = {"lr": 1e-3, "wd": 0.01, "beta": 0.5, "w1": 1.0, "w2": 1.0, "clip": 1.0}
     # A. real data, label-free pretrain-style batch (source id 3), z=10
     wf, isi, x1, x2 = real_batch(48)
-    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "cellexplorer_raw48.npz"), wf=wf, isi=isi,
+    np.savez_compressed(os.path.join(OUT_DIR, "cellexplorer_raw48.npz"), wf=wf, isi=isi,
                         x1=x1.numpy(), x2=x2.numpy())
     run_case("real48_z10", O.CVAEConfig(z_dim=10), x1, x2, torch.full((48,), 3, dtype=torch.long), [101, 102],
              hyper, steps=2)
@@ -238,4 +239,7 @@ def main():
 
 
 if __name__ == "__main__":
+    if "--out" in sys.argv:
+        OUT_DIR = sys.argv[sys.argv.index("--out") + 1]
+        os.makedirs(OUT_DIR, exist_ok=True)
     main()

@@ -160,3 +160,26 @@ def test_out_of_range_labels_raise_index_error():
         eng.raise_on_flags()
     assert torch.equal(eng.flat_params, before)
     assert torch.isfinite(eng.flat_grads).all()
+
+
+@pytest.mark.parametrize("B", [37, 512])
+def test_no_kernel_writes_outside_its_buffers(B):
+    """compute-sanitizer is closed on the pool this repository is built on, so the out-of-bounds check is our own:
+    every buffer handed to hippie_bind (parameters, gradients, AdamW moments, BatchNorm buffers, the workspace) sits
+    between canary bands; a full train step (ragged batch: B = 37 of max 64 leaves partial tiles everywhere), the
+    optimizer, an eval forward and an embedding pass must leave every canary element untouched."""
+    from hippie_b200.engine import Engine
+    cfg = O.CVAEConfig(z_dim=10, num_classes=4)
+    cap = 64 if B < 64 else B
+    eng = Engine(cfg.z_dim, 50, 100, 5, cfg.num_sources, cfg.num_classes, True, cap).allocate("cuda:0", guard=1 << 16)
+    eng.load_named(U.perturbed_state(cfg))
+    x1, x2, labels, eps = U.case_inputs(cfg, B, True, seed=21)
+    dev = eng.device
+    cls, src = labels.unbind(1)
+    args = (x1.to(dev), x2.to(dev), src.contiguous().to(dev), cls.contiguous().to(dev))
+    for _ in range(3):  # eager, capture, replay
+        s, _ = eng.train_fwd_bwd(*args, eps.to(dev), 0.5)
+        eng.clip_adamw(1e-3, 0.01, 1, max_norm=1.0, step_cls=1, has_cls_grad=True)
+    eng.embed(*args, zscore_ddof=1)
+    eng.check_guards()
+    assert torch.isfinite(s[:4]).all() and torch.isfinite(eng.flat_params).all()

@@ -8,6 +8,7 @@ import sys
 import numpy as np
 import pytest
 import torch
+from collections import OrderedDict
 
 from oracle import cvae_oracle as O
 
@@ -228,6 +229,26 @@ class StubEngine:  # the host logic of the overlapped exchange, without a GPU: e
         else:
             raise AssertionError("the overlapped step uses parts 0, 2, 3")
         return None
+# sharded embedding inference: contiguous shards in rank order, gathered back into unit order (ragged: 7 units on 2 ranks)
+from hippie_b200.parallel import gather_rows, shard_units
+lo, hi = shard_units(7, r, w)
+rows = torch.arange(lo, hi, dtype=torch.float32).unsqueeze(1).repeat(1, 3)
+allrows = gather_rows(rows, 7)
+assert torch.equal(allrows, torch.arange(7, dtype=torch.float32).unsqueeze(1).repeat(1, 3)), allrows
+# the loader gives every rank the same number of steps and at least two rows per step, whatever the tail
+import numpy as np
+from hippie_b200.dataloading import EphysBatchLoader, EphysTensorDataset
+for n in (64, 65, 67, 70, 95):
+    ds = EphysTensorDataset(np.zeros((n, 50)), np.ones((n, 100)), np.arange(n))
+    torch.manual_seed(5)
+    ld = EphysBatchLoader(ds, 16, shuffle=True, rank=r, world=w)
+    mine = [b[2].tolist() for b in ld]
+    assert len(mine) == len(ld) and all(len(b) >= 2 for b in mine), (n, [len(b) for b in mine])
+    both = [None, None]
+    dist.all_gather_object(both, mine)
+    assert len(both[0]) == len(both[1]), (n, len(both[0]), len(both[1]))
+    seen = sorted(i for part in both for b in part for i in b)
+    assert len(seen) == len(set(seen)) and len(seen) >= n - 3, (n, len(seen))  # a tail of < 2 * world rows is dropped
 eng = StubEngine(r)
 scale = train_step_overlapped(eng, None, None, None, None, None, 0.5)
 assert scale == 0.5 and eng.calls == [0, 2, 3]
@@ -336,3 +357,34 @@ def test_cli_flags_match_the_reference():
         assert getattr(a, k) == v, k
     b = load("inference_from_trained_model").parse_args(["--wave-checkpoint", "w.ckpt", "--time-checkpoint", "t.ckpt"])
     assert (b.z_dim, b.dataset, b.output_dir) == (64, "cellexplorer-celltype", "./embeddings")
+
+
+def test_oracle_matches_the_installed_reference_classes():
+    """The pinning recipe as a CI check: oracle/ref_loader.py imports the UNMODIFIED reference modules (baseline/_ref, the
+    offline pip install made by __graft_entry__.build(), or /root/reference) next to this repository's `hippie/` alias
+    package, and the oracle reproduces the reference's forward, loss and gradients (fp64: to rounding)."""
+    from oracle.ref_loader import load_reference, reference_root
+    if reference_root() is None:
+        pytest.skip("no reference here (neither baseline/_ref nor /root/reference)")
+    R = load_reference()
+    import hippie.model as alias  # the alias package still resolves to this repository afterwards
+    assert alias.__file__.startswith(ROOT) and not R.model.__file__.startswith(os.path.join(ROOT, "hippie"))
+    cfg = O.CVAEConfig(z_dim=10, num_classes=4)
+    torch.manual_seed(42)
+    ref = R.model.MultiModalCVAE(10, 50, 100, 5, cfg.num_sources, 4).double()
+    tm = R.model.MultiModalCVAETrainModule(ref, learning_rate=1e-3, weight_decay=0.01, beta=0.5)
+    tm.train()
+    st = OrderedDict((k, v.detach().clone()) for k, v in ref.state_dict().items())
+    x1, x2, labels, g = O.synthetic_batch(12, seed=3, labelled=True)
+    labels[:, 0] %= 4
+    eps = torch.randn(12, 10, generator=g).double()
+    ref.reparameterize = lambda mu, lv: mu + eps * torch.exp(0.5 * lv)
+    loss = tm.training_step((x1.double(), x2.double(), labels), 0)
+    loss.backward()
+    _, _, info = O.train_step(st, O.new_opt_state(st, cfg), cfg, x1.double(), x2.double(), labels, eps, lr=1e-3,
+                              weight_decay=0.01, beta=0.5, max_norm=1.0)
+    assert abs(float(loss) - float(info["loss"])) <= 1e-13 * abs(float(loss))
+    gn = float(torch.sqrt(sum((p.grad ** 2).sum() for p in ref.parameters() if p.grad is not None)))
+    for n, p in ref.named_parameters():
+        if p.grad is not None:  # (a bias in front of a BatchNorm has an analytically zero gradient: absolute floor)
+            assert (p.grad - info["grads_raw"][n]).norm() <= 1e-11 * p.grad.norm() + 1e-13 * gn, n

@@ -33,8 +33,9 @@ def test_init_bit_exact(golden_dir, tag):
     names = [str(s) for s in fx["param_names"]]
     assert names == O.param_names(cfg)
     assert np.array_equal(_heads(st, names), fx["init_head"])
-    assert np.array_equal(np.array([st[n].double().sum().item() for n in names]), fx["init_sum"])
-    assert np.array_equal(np.array([st[n].double().abs().sum().item() for n in names]), fx["init_abs"])
+    # whole-tensor checksums in float64: the order of a multi-threaded sum depends on the thread count, the values do not
+    np.testing.assert_allclose(np.array([st[n].double().sum().item() for n in names]), fx["init_sum"], rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(np.array([st[n].double().abs().sum().item() for n in names]), fx["init_abs"], rtol=1e-12)
 
 
 @pytest.mark.parametrize("tag", list(CASES))
@@ -101,3 +102,26 @@ def test_zscore_variants():
                                (e.numpy() - e.numpy().mean(1, keepdims=True)) / e.numpy().std(1, keepdims=True))
     np.testing.assert_allclose(O.zscore_rows(e, 1).numpy(),
                                ((e - e.mean(1)[:, None]) / e.std(1)[:, None]).numpy())
+
+
+def test_golden_recipe_runs_from_this_checkout(golden_dir, tmp_path):
+    """`python oracle/make_golden.py` (the pinning recipe: the reference's own classes, imported by path next to this
+    repository's `hippie/` alias package) runs from the checkout as it is and reproduces the committed fixtures.  Needs
+    /root/reference (build container); skipped on the GPU box."""
+    import subprocess
+    import sys
+    if not os.path.isfile("/root/reference/hippie/model.py"):
+        pytest.skip("/root/reference is not present here")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "oracle", "make_golden.py"), "--out", str(tmp_path)],
+                         capture_output=True, text=True, timeout=900, cwd=root)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    for tag in list(CASES) + ["cellexplorer_raw48"]:
+        new, old = np.load(tmp_path / (tag + ".npz")), np.load(os.path.join(golden_dir, tag + ".npz"))
+        assert set(new.files) == set(old.files), tag
+        for k in old.files:
+            if old[k].dtype.kind == "f":  # bit-identical on the machine that wrote them; rounding-level elsewhere
+                tol = 1e-9 if (k.startswith("f64") or old[k].dtype == np.float64 and not k.startswith("f32")) else 5e-5
+                np.testing.assert_allclose(new[k], old[k], rtol=tol, atol=tol * max(1.0, float(np.abs(old[k]).max())), err_msg=f"{tag}:{k}")
+            else:
+                assert np.array_equal(new[k], old[k]), (tag, k)
