@@ -1473,7 +1473,7 @@ int hippie_device_flags(hippie_handle h, uint32_t* flags_out, int32_t clear, voi
   return ce == cudaSuccess ? 0 : h->fail((int)ce, std::string("hippie_device_flags: ") + cudaGetErrorString(ce));
 }
 
-int hippie_clip_adamw(hippie_handle h, float lr, float beta1, float beta2, float eps, float weight_decay, float max_norm,
+int hippie_clip_adamw(hippie_handle h, double lr, double beta1, double beta2, double eps, double weight_decay, float max_norm,
                       float grad_scale, int32_t step, int32_t step_cls, int32_t has_cls_grad, float* scalars_out,
                       void* stream) {
   if (!h) return -1;

@@ -317,7 +317,8 @@ struct AdamArgs {
   float* v;
   int64_t n;
   int64_t skip_lo, skip_hi;  // class_embedding range, stepped with step_cls (or skipped when has_cls_grad = 0)
-  float lr, beta1, beta2, eps, wd, max_norm, grad_scale;
+  double lr, beta1, beta2, eps, wd;  // torch keeps the hyper-parameters as Python doubles: 1 - beta is taken in double
+  float max_norm, grad_scale;
   int step, step_cls, has_cls_grad;
   float* partials;  // >= 1024 floats
   float* scalars;   // [4] = grad norm, [5] = clip coefficient

@@ -972,12 +972,16 @@ __global__ void __launch_bounds__(256) clip_coef_kernel(const float* __restrict_
   }
 }
 
-__global__ void __launch_bounds__(256) adamw_kernel(AdamArgs a, float decay, float step_size, float bc2_sqrt,
-                                                    float step_size_cls, float bc2_sqrt_cls) {
+struct AdamCoefs {  // fp32 roundings of the double expressions torch evaluates on the host (torch/optim/adam.py)
+  float decay, step_size, bc2_sqrt, step_size_cls, bc2_sqrt_cls, omb1, omb2, beta2, eps;
+};
+__global__ void __launch_bounds__(256) adamw_kernel(AdamArgs a, AdamCoefs k) {
   pdl_trigger();
   pdl_wait();
   const float coef = a.scalars[5];
-  const float omb1 = 1.f - a.beta1, omb2 = 1.f - a.beta2;
+  const float omb1 = k.omb1, omb2 = k.omb2;
+  const float step_size = k.step_size, bc2_sqrt = k.bc2_sqrt, step_size_cls = k.step_size_cls, bc2_sqrt_cls = k.bc2_sqrt_cls;
+  const float decay = k.decay;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += (int64_t)gridDim.x * blockDim.x) {
     float ss = step_size, bs = bc2_sqrt;
     if (i >= a.skip_lo && i < a.skip_hi) {
@@ -989,9 +993,9 @@ __global__ void __launch_bounds__(256) adamw_kernel(AdamArgs a, float decay, flo
     float p = a.p[i] * decay;
     float m = a.m[i];
     m = m + omb1 * (g - m);  // lerp_(grad, 1 - beta1)
-    float v = a.v[i] * a.beta2;
+    float v = a.v[i] * k.beta2;
     v = fmaf(omb2 * g, g, v);  // addcmul_(grad, grad, value = 1 - beta2)
-    const float denom = sqrtf(v) / bs + a.eps;
+    const float denom = sqrtf(v) / bs + k.eps;
     p = p - ss * (m / denom);
     a.p[i] = p, a.m[i] = m, a.v[i] = v;
   }
@@ -1148,12 +1152,12 @@ void launch_clip_adamw(const AdamArgs& a, cudaStream_t s) {
   launch_pdl(sumsq_kernel, dim3(nblk), dim3(256), 0, s, a.g, a.n, a.grad_scale, a.partials);
   launch_pdl(clip_coef_kernel, dim3(1), dim3(256), 0, s, a.partials, nblk, a.max_norm, a.scalars);
   // scalar factors exactly as torch.optim.adam._single_tensor_adam computes them (python doubles -> fp32)
-  const double bc1 = 1.0 - pow((double)a.beta1, (double)a.step), bc2 = 1.0 - pow((double)a.beta2, (double)a.step);
+  const double bc1 = 1.0 - pow(a.beta1, (double)a.step), bc2 = 1.0 - pow(a.beta2, (double)a.step);
   const int sc = a.step_cls > 0 ? a.step_cls : 1;
-  const double bc1c = 1.0 - pow((double)a.beta1, (double)sc), bc2c = 1.0 - pow((double)a.beta2, (double)sc);
-  const float decay = (float)(1.0 - (double)a.lr * (double)a.wd);
-  launch_pdl(adamw_kernel, dim3(ew_grid(a.n)), dim3(256), 0, s, a, decay, (float)((double)a.lr / bc1), (float)sqrt(bc2),
-                                            (float)((double)a.lr / bc1c), (float)sqrt(bc2c));
+  const double bc1c = 1.0 - pow(a.beta1, (double)sc), bc2c = 1.0 - pow(a.beta2, (double)sc);
+  AdamCoefs k{(float)(1.0 - a.lr * a.wd), (float)(a.lr / bc1), (float)sqrt(bc2), (float)(a.lr / bc1c), (float)sqrt(bc2c),
+              (float)(1.0 - a.beta1), (float)(1.0 - a.beta2), (float)a.beta2, (float)a.eps};
+  launch_pdl(adamw_kernel, dim3(ew_grid(a.n)), dim3(256), 0, s, a, k);
 }
 void launch_preprocess(const double* raw, int width, const int64_t* index, int B, int size, int take_log, float* out,
                        cudaStream_t s) {

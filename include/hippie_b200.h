@@ -146,7 +146,7 @@ int hippie_grad_bounds(hippie_handle h, int64_t* bounds);
  *   ordinary parameters and of class_embedding.weight; has_cls_grad = 0 leaves class_embedding
  *   untouched (torch skips params whose grad is None).
  * scalars_out[4] = total gradient norm (after grad_scale), scalars_out[5] = clip coefficient. */
-int hippie_clip_adamw(hippie_handle h, float lr, float beta1, float beta2, float eps, float weight_decay,
+int hippie_clip_adamw(hippie_handle h, double lr, double beta1, double beta2, double eps, double weight_decay,
                       float max_norm, float grad_scale, int32_t step, int32_t step_cls, int32_t has_cls_grad,
                       float* scalars_out, void* stream);
 

@@ -69,10 +69,12 @@ def test_adamw_kernel_matches_torch_order_to_ulps(clip):
         got_m, got_v = eng.view_of(eng.exp_avg, p).cpu(), eng.view_of(eng.exp_avg_sq, p).cpu()
         scale_m = torch.maximum(m0[n].abs(), 0.1 * gc.abs())
         scale_v = torch.maximum(v0[n], 0.001 * gc * gc)
-        upd = (st[n] - pr).abs()  # decay + step: p's own rounding plus the rounding of the update term
+        upd = (st[n] - pr).abs()  # decay + step: p's own rounding plus the rounding of the update term ...
+        denom = vr.sqrt() / (1 - 0.999 ** step) ** 0.5 + 1e-8
+        carry = (lr / (1 - 0.9 ** step)) / denom * scale_m  # ... which also carries m's (cancellation-scale) rounding
         worst["m"] = max(worst["m"], ((got_m - mr).abs() / (ULP * scale_m)).max().item())
         worst["v"] = max(worst["v"], ((got_v - vr).abs() / (ULP * scale_v)).max().item())
-        worst["p"] = max(worst["p"], ((new[n] - pr).abs() / (ULP * (st[n].abs() + 4 * upd))).max().item())
+        worst["p"] = max(worst["p"], ((new[n] - pr).abs() / (ULP * (st[n].abs() + 4 * upd + 4 * carry))).max().item())
     assert worst["m"] <= 2 and worst["v"] <= 2 and worst["p"] <= 2, worst
 
 
@@ -183,3 +185,24 @@ def test_no_kernel_writes_outside_its_buffers(B):
     eng.embed(*args, zscore_ddof=1)
     eng.check_guards()
     assert torch.isfinite(s[:4]).all() and torch.isfinite(eng.flat_params).all()
+
+
+def test_free_running_epoch_inside_reference_envelope(golden_dir):
+    """BASELINE.json configs[1]/[2]: 200 free-running bs512 pretrain steps (no teacher forcing) against the curves of the
+    reference's own classes {fp32 N threads, fp32 one thread, fp64} frozen in tests/golden/free_run_bs512.npz
+    (tools/free_run_reference.py).  The reference is chaotic after step 0 (its own runs drift apart by up to ~1 % within
+    ten steps and re-converge), so the engine has to stay within a small multiple of that spread, taken over a +-5 step
+    window, and must end where the reference ends."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(golden_dir), "..", "tools"))
+    import free_run_report as FR
+    fx = np.load(os.path.join(golden_dir, "free_run_bs512.npz"))
+    got = FR.engine_curve(fx)
+    ref = fx["f64"][:, 0]
+    spread, win = FR.envelope(fx)
+    dev = np.abs(got[:, 0] - ref) / np.abs(ref)
+    assert dev[0] <= LOSS_RTOL, dev[0]                         # identical state: the per-step bound
+    assert (dev <= 6.0 * win + 3e-3).all(), (int(np.argmax(dev - 6 * win)), dev.max(), win.max())
+    tail_ref, tail_got = ref[-20:].mean(), got[-20:, 0].mean()
+    assert abs(tail_got - tail_ref) <= 5e-3 * tail_ref, (tail_got, tail_ref)
+    assert got[-1, 0] < 0.2 * got[0, 0]                        # it trains
