@@ -336,9 +336,11 @@ def main():
 
         def sup_step(i):
             sl = slice((i % n_batches) * BS, (i % n_batches) * BS + SB)
-            eng.train_fwd_bwd(x1d[sl], x2d[sl], srcd[sl], cls64, eps_all[i % 64][:SB].contiguous(), 0.5, 1.0, 1.0, scalars=scal)
-            if world > 1:
-                dist.all_reduce(eng.flat_grads)
+            if world > 1:  # the exchange overlaps the encoders' backward pass, as in the bs512 step
+                train_step_overlapped(eng, x1d[sl], x2d[sl], srcd[sl], cls64, eps_all[i % 64][:SB].contiguous(), 0.5, 1.0, 1.0,
+                                      scalars=scal)
+            else:
+                eng.train_fwd_bwd(x1d[sl], x2d[sl], srcd[sl], cls64, eps_all[i % 64][:SB].contiguous(), 0.5, 1.0, 1.0, scalars=scal)
             step_no[0] += 1
             eng.clip_adamw(1e-4, 0.01, step_no[0], max_norm=1.0, grad_scale=inv_world, step_cls=step_no[0], has_cls_grad=True,
                            scalars=scal)

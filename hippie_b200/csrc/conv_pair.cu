@@ -80,6 +80,7 @@ struct PairConv {
   int taps;        // b_mn: kernel size (3 or 1); tap of k-block kb = taps - 1 - kb / kb_per_tap
   const float* dyn_scale;  // optional device scalar multiplied into out_scale
   unsigned long long* stamps;  // tools/pair_test only: %globaltimer at the phase boundaries of CTA (0, 0)
+  int pdl_late;                // trigger the dependent launch when the main loop is issued instead of at kernel start
   EvalFold fold;               // eval-mode BatchNorm (+ residual, LeakyReLU, pair planes) applied in the epilogue
   int tma_out;                 // mapC describes the fp32 output: whole tiles leave through TMA stores
 };
@@ -132,7 +133,7 @@ __global__ void __launch_bounds__(TC_THREADS, ctas_per_sm(BN, STAGES))
   uint64_t* accum = bars + 2 * STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
 
-  pdl_trigger();
+  if (!p.pdl_late) pdl_trigger();
   if (threadIdx.x == 0) stamp(p, 0);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b0 = blockIdx.x * p.nb, n0 = blockIdx.y * BN;
@@ -228,6 +229,7 @@ __global__ void __launch_bounds__(TC_THREADS, ctas_per_sm(BN, STAGES))
     }
     if (elect_one()) umma_commit(accum);
     __syncwarp();
+    if (p.pdl_late) pdl_trigger();  // this CTA is about to enter its epilogue
   } else {
     // ===================== epilogue =====================
     const int t = threadIdx.x - 64;  // 0..127
@@ -405,6 +407,7 @@ struct PairWgrad {
   float out_scale;
   const float* dyn_scale;
   uint32_t idesc;
+  int pdl_late;
 };
 
 template <int BN, int STAGES>
@@ -420,7 +423,7 @@ __global__ void __launch_bounds__(TC_THREADS, ctas_per_sm(BN, STAGES))
   uint64_t* accum = bars + 2 * STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
 
-  pdl_trigger();
+  if (!p.pdl_late) pdl_trigger();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n0 = blockIdx.x * BN, m0 = blockIdx.y * TC_BM;
   const int r_begin = blockIdx.z * p.rows_per_split;
@@ -501,6 +504,7 @@ __global__ void __launch_bounds__(TC_THREADS, ctas_per_sm(BN, STAGES))
     }
     if (elect_one()) umma_commit(accum);
     __syncwarp();
+    if (p.pdl_late) pdl_trigger();
   } else {
     const int t = threadIdx.x - 64;
     mbar_wait(accum, 0);
@@ -594,7 +598,10 @@ static void set_smem_attrs() {
   cudaFuncSetAttribute(conv_pair_kernel<kBN, STAGES, kConvDgrad>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
   cudaFuncSetAttribute(wgrad_pair_kernel<kBN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
 }
-static int g_variant = 0, g_wgrad_variant = 1;
+static int g_variant = 0, g_wgrad_variant = 1, g_pdl_late = 0;
+static int g_wgrad_min_kb = 16;  // k-blocks (of 64 reduction rows) a weight-gradient CTA processes at least: the kernels are off
+// the critical path, so few long-lived CTAs (less prologue / fill / epilogue time per MAC) beat many short ones -- the step is
+// bound by the time CTAs occupy SM slots (bs512: 4 -> 3.134 ms, 16 -> 3.054 ms, 64 -> 3.308 ms per step)
 static int g_sm_count = 148, g_alone_max = 74;
 
 bool pair_init(std::string* err) {
@@ -612,7 +619,9 @@ bool pair_init(std::string* err) {
   set_smem_attrs<kStages>();
   set_smem_attrs<kStagesAlone>();
   if (const char* v = getenv("HIPPIE_B200_PAIR_VARIANT")) g_variant = atoi(v);  // 0 auto, 1 always shared, 2 always alone
+  if (const char* v = getenv("HIPPIE_B200_PDL_LATE")) g_pdl_late = atoi(v);
   if (const char* v = getenv("HIPPIE_B200_WGRAD_VARIANT")) g_wgrad_variant = atoi(v);  // 1 shared (two CTAs per SM), 2 alone
+  if (const char* v = getenv("HIPPIE_B200_WGRAD_MIN_KB")) g_wgrad_min_kb = atoi(v) > 0 ? atoi(v) : 16;
   int dev = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
@@ -705,7 +714,7 @@ int launch_conv_pair(const ConvGemm& g, const TcMap& mapA, const TcMap& mapB, in
   p.out_scale = o.out_scale;
   p.idesc = umma_idesc_16(bn, o.a_fmt, o.b_fmt, 0, o.b_mn ? 1 : 0);
   p.b_mn = o.b_mn, p.taps = o.taps, p.kb_per_tap = o.taps > 0 ? (g.K / o.taps) / PK : 1;
-  p.dyn_scale = o.dyn_scale, p.stamps = o.stamps;
+  p.dyn_scale = o.dyn_scale, p.stamps = o.stamps, p.pdl_late = g_pdl_late & 1;
   if (o.fold) p.fold = *o.fold;
   dim3 grid((B + p.nb - 1) / p.nb, g.N / bn);
 
@@ -725,14 +734,14 @@ void launch_wgrad_pair(const WgradGemm& g, const TcMap& mapDY, const TcMap& mapX
                        const PairOpts& o, cudaStream_t s) {
   PairWgrad p{};
   p.dW = g.dW, p.M = g.M, p.N = g.N, p.R = g.R;
-  p.out_scale = o.out_scale, p.dyn_scale = o.dyn_scale;
+  p.out_scale = o.out_scale, p.dyn_scale = o.dyn_scale, p.pdl_late = (g_pdl_late >> 1) & 1;
   bn = kBN;
   p.idesc = umma_idesc_16(bn, o.a_fmt, o.b_fmt, 1, 1);
   const int tiles = ((g.M + TC_BM - 1) / TC_BM) * (g.N / bn);
   const bool alone = g_wgrad_variant == 2;
   int splits = ((alone ? 1 : 2) * sm_count) / tiles;  // one or two CTAs per SM
   const int kblocks = (g.R + PK - 1) / PK;
-  if (splits > (kblocks + 3) / 4) splits = (kblocks + 3) / 4;  // at least 4 k-blocks (256 rows) per CTA
+  if (splits > (kblocks + g_wgrad_min_kb - 1) / g_wgrad_min_kb) splits = (kblocks + g_wgrad_min_kb - 1) / g_wgrad_min_kb;
   if (splits < 1) splits = 1;
   const int kb_per = (kblocks + splits - 1) / splits;
   p.rows_per_split = kb_per * PK;
