@@ -551,13 +551,25 @@ template <int FMT>
 __global__ void to_pair_kernel(const float* __restrict__ src, uint16_t* __restrict__ hi, uint16_t* __restrict__ lo,
                                int64_t n, float scale, unsigned* __restrict__ flags) {
   bool sat = false;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    uint16_t h, l;
-    const float x = src[i] * scale;
-    pair_split<FMT>(x, h, l);
-    if (FMT == kPairF16) sat |= !(fabsf(x) < kPairF16Max);
-    hi[i] = h, lo[i] = l;
+  const int64_t n4 = n >> 2;  // four elements per thread and iteration: one 128-bit load, two 64-bit stores
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n4; q += (int64_t)gridDim.x * blockDim.x) {
+    const float4 v = *reinterpret_cast<const float4*>(src + q * 4);
+    const float x[4] = {v.x * scale, v.y * scale, v.z * scale, v.w * scale};
+    uint16_t h[4], l[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      pair_split<FMT>(x[e], h[e], l[e]);
+      if (FMT == kPairF16) sat |= !(fabsf(x[e]) < kPairF16Max);
+    }
+    *reinterpret_cast<uint2*>(hi + q * 4) = make_uint2((uint32_t)h[0] | ((uint32_t)h[1] << 16), (uint32_t)h[2] | ((uint32_t)h[3] << 16));
+    *reinterpret_cast<uint2*>(lo + q * 4) = make_uint2((uint32_t)l[0] | ((uint32_t)l[1] << 16), (uint32_t)l[2] | ((uint32_t)l[3] << 16));
   }
+  if (blockIdx.x == 0 && threadIdx.x == 0)
+    for (int64_t i = n4 * 4; i < n; ++i) {
+      const float x = src[i] * scale;
+      pair_split<FMT>(x, hi[i], lo[i]);
+      if (FMT == kPairF16) sat |= !(fabsf(x) < kPairF16Max);
+    }
   if (flags && sat) atomicOr(flags, kFlagWeightSaturated);
 }
 
@@ -759,7 +771,7 @@ void launch_wgrad_pair(const WgradGemm& g, const TcMap& mapDY, const TcMap& mapX
 void launch_to_pair(const float* src, void* planes, int64_t plane_stride, int64_t n, float scale, int fmt,
                     cudaStream_t s, unsigned* flags) {
   uint16_t* hi = static_cast<uint16_t*>(planes);
-  int blocks = (int)((n + 255) / 256);
+  int blocks = (int)((n / 4 + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
   if (blocks < 1) blocks = 1;
   if (fmt == kPairBF16)

@@ -941,6 +941,8 @@ __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g,
     v.x *= scale, v.y *= scale, v.z *= scale, v.w *= scale;
     s += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
   }
+  if (blockIdx.x == 0 && threadIdx.x == 0)  // the n % 4 tail (the flat buffers are padded to whole groups today)
+    for (int64_t i = n4 * 4; i < n; ++i) s += (g[i] * scale) * (g[i] * scale);
   s = warp_sum(s);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
   __syncthreads();
@@ -975,29 +977,53 @@ __global__ void __launch_bounds__(256) clip_coef_kernel(const float* __restrict_
 struct AdamCoefs {  // fp32 roundings of the double expressions torch evaluates on the host (torch/optim/adam.py)
   float decay, step_size, bc2_sqrt, step_size_cls, bc2_sqrt_cls, omb1, omb2, beta2, eps;
 };
+__device__ __forceinline__ void adamw_one(float g, float& p, float& m, float& v, float coef, float gscale, float decay,
+                                          float omb1, float omb2, float beta2, float ss, float bs, float eps) {
+  g = g * gscale;
+  g *= coef;
+  p = p * decay;
+  m = m + omb1 * (g - m);  // lerp_(grad, 1 - beta1)
+  v = v * beta2;
+  v = fmaf(omb2 * g, g, v);  // addcmul_(grad, grad, value = 1 - beta2)
+  const float denom = sqrtf(v) / bs + eps;
+  p = p - ss * (m / denom);
+}
+// torch.optim.AdamW's single-tensor update (torch/optim/adam.py) over the flat buffers, four elements per thread and
+// iteration (128-bit loads / stores: the kernel moves 7 x 64 MB and is HBM-bound); the class-embedding range carries
+// its own step count (or is skipped when it has no gradient), groups that straddle its ends go element by element.
 __global__ void __launch_bounds__(256) adamw_kernel(AdamArgs a, AdamCoefs k) {
   pdl_trigger();
   pdl_wait();
   const float coef = a.scalars[5];
-  const float omb1 = k.omb1, omb2 = k.omb2;
-  const float step_size = k.step_size, bc2_sqrt = k.bc2_sqrt, step_size_cls = k.step_size_cls, bc2_sqrt_cls = k.bc2_sqrt_cls;
-  const float decay = k.decay;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += (int64_t)gridDim.x * blockDim.x) {
-    float ss = step_size, bs = bc2_sqrt;
-    if (i >= a.skip_lo && i < a.skip_hi) {
-      if (!a.has_cls_grad) continue;
-      ss = step_size_cls, bs = bc2_sqrt_cls;
+  const int64_t n4 = a.n >> 2;
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n4 + 1; q += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i0 = q * 4;
+    const int cnt = q < n4 ? 4 : (int)(a.n - i0);  // the last group holds the n % 4 tail
+    if (cnt <= 0) break;
+    const bool in0 = i0 >= a.skip_lo && i0 < a.skip_hi, in3 = i0 + 3 >= a.skip_lo && i0 + 3 < a.skip_hi;
+    if (cnt == 4 && in0 == in3 && !(i0 < a.skip_lo && i0 + 3 >= a.skip_hi)) {
+      if (in0 && !a.has_cls_grad) continue;
+      const float ss = in0 ? k.step_size_cls : k.step_size, bs = in0 ? k.bc2_sqrt_cls : k.bc2_sqrt;
+      const float4 g = *reinterpret_cast<const float4*>(a.g + i0);
+      float4 p = *reinterpret_cast<const float4*>(a.p + i0), m = *reinterpret_cast<const float4*>(a.m + i0);
+      float4 v = *reinterpret_cast<const float4*>(a.v + i0);
+      adamw_one(g.x, p.x, m.x, v.x, coef, a.grad_scale, k.decay, k.omb1, k.omb2, k.beta2, ss, bs, k.eps);
+      adamw_one(g.y, p.y, m.y, v.y, coef, a.grad_scale, k.decay, k.omb1, k.omb2, k.beta2, ss, bs, k.eps);
+      adamw_one(g.z, p.z, m.z, v.z, coef, a.grad_scale, k.decay, k.omb1, k.omb2, k.beta2, ss, bs, k.eps);
+      adamw_one(g.w, p.w, m.w, v.w, coef, a.grad_scale, k.decay, k.omb1, k.omb2, k.beta2, ss, bs, k.eps);
+      *reinterpret_cast<float4*>(a.p + i0) = p, *reinterpret_cast<float4*>(a.m + i0) = m;
+      *reinterpret_cast<float4*>(a.v + i0) = v;
+    } else {
+      for (int e = 0; e < cnt; ++e) {
+        const int64_t i = i0 + e;
+        const bool in = i >= a.skip_lo && i < a.skip_hi;
+        if (in && !a.has_cls_grad) continue;
+        float p = a.p[i], m = a.m[i], v = a.v[i];
+        adamw_one(a.g[i], p, m, v, coef, a.grad_scale, k.decay, k.omb1, k.omb2, k.beta2, in ? k.step_size_cls : k.step_size,
+                  in ? k.bc2_sqrt_cls : k.bc2_sqrt, k.eps);
+        a.p[i] = p, a.m[i] = m, a.v[i] = v;
+      }
     }
-    float g = a.g[i] * a.grad_scale;
-    g *= coef;
-    float p = a.p[i] * decay;
-    float m = a.m[i];
-    m = m + omb1 * (g - m);  // lerp_(grad, 1 - beta1)
-    float v = a.v[i] * k.beta2;
-    v = fmaf(omb2 * g, g, v);  // addcmul_(grad, grad, value = 1 - beta2)
-    const float denom = sqrtf(v) / bs + k.eps;
-    p = p - ss * (m / denom);
-    a.p[i] = p, a.m[i] = m, a.v[i] = v;
   }
 }
 
@@ -1157,7 +1183,7 @@ void launch_clip_adamw(const AdamArgs& a, cudaStream_t s) {
   const double bc1c = 1.0 - pow(a.beta1, (double)sc), bc2c = 1.0 - pow(a.beta2, (double)sc);
   AdamCoefs k{(float)(1.0 - a.lr * a.wd), (float)(a.lr / bc1), (float)sqrt(bc2), (float)(a.lr / bc1c), (float)sqrt(bc2c),
               (float)(1.0 - a.beta1), (float)(1.0 - a.beta2), (float)a.beta2, (float)a.eps};
-  launch_pdl(adamw_kernel, dim3(ew_grid(a.n)), dim3(256), 0, s, a, k);
+  launch_pdl(adamw_kernel, dim3(ew_grid(a.n / 4 + 1)), dim3(256), 0, s, a, k);
 }
 void launch_preprocess(const double* raw, int width, const int64_t* index, int B, int size, int take_log, float* out,
                        cudaStream_t s) {
