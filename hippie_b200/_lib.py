@@ -70,6 +70,7 @@ SIGNATURES = {
     "hippie_decoder_forward": (C.c_int, [_H, C.c_int32, _f32p, C.c_int32, C.c_int32, _f32p, C.c_void_p]),
     "hippie_encode": (C.c_int, [_H, _f32p, _f32p, _f32p, _f32p, C.c_int32, C.c_int32, _f32p, _f32p, _f32p, C.c_void_p]),
     "hippie_decode": (C.c_int, [_H, _f32p, _f32p, _f32p, C.c_int32, C.c_int32, _f32p, _f32p, C.c_void_p]),
+    "hippie_slice_wait": (C.c_int, [_H, C.c_int32, C.c_void_p]),
     "hippie_device_flags": (C.c_int, [_H, C.POINTER(C.c_uint32), C.c_int32, C.c_void_p]),
     "hippie_clip_adamw": (C.c_int, [_H, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, C.c_float, C.c_float,
                                     C.c_int32, C.c_int32, C.c_int32, _f32p, C.c_void_p]),

@@ -81,14 +81,21 @@ struct PairConv {
   const float* dyn_scale;  // optional device scalar multiplied into out_scale
   unsigned long long* stamps;  // tools/pair_test only: %globaltimer at the phase boundaries of CTA (0, 0)
   int pdl_late;                // trigger the dependent launch when the main loop is issued instead of at kernel start
+  int stamps_all;              // every CTA writes its stamps (8 slots per CTA, slot 7 = %smid)
   EvalFold fold;               // eval-mode BatchNorm (+ residual, LeakyReLU, pair planes) applied in the epilogue
   int tma_out;                 // mapC describes the fp32 output: whole tiles leave through TMA stores
 };
 __device__ __forceinline__ void stamp(const PairConv& p, int i) {
-  if (p.stamps && blockIdx.x == 0 && blockIdx.y == 0) {
+  if (p.stamps && (p.stamps_all || (blockIdx.x == 0 && blockIdx.y == 0))) {
     unsigned long long t;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-    p.stamps[i] = t;
+    const size_t base = p.stamps_all ? (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 8 : 0;
+    p.stamps[base + i] = t;
+    if (p.stamps_all && i == 0) {  // slot 7: the SM this CTA runs on
+      unsigned smid;
+      asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
+      p.stamps[base + 7] = smid;
+    }
   }
 }
 
@@ -726,7 +733,7 @@ int launch_conv_pair(const ConvGemm& g, const TcMap& mapA, const TcMap& mapB, in
   p.out_scale = o.out_scale;
   p.idesc = umma_idesc_16(bn, o.a_fmt, o.b_fmt, 0, o.b_mn ? 1 : 0);
   p.b_mn = o.b_mn, p.taps = o.taps, p.kb_per_tap = o.taps > 0 ? (g.K / o.taps) / PK : 1;
-  p.dyn_scale = o.dyn_scale, p.stamps = o.stamps, p.pdl_late = g_pdl_late & 1;
+  p.dyn_scale = o.dyn_scale, p.stamps = o.stamps, p.stamps_all = o.stamps_all, p.pdl_late = g_pdl_late & 1;
   if (o.fold) p.fold = *o.fold;
   dim3 grid((B + p.nb - 1) / p.nb, g.N / bn);
 

@@ -171,6 +171,14 @@ struct hippie_engine {
   bool use_graphs = true;
   static constexpr size_t kMaxGraphs = 32;  // distinct call signatures kept as instantiated graphs
   cudaStream_t cap = nullptr;  // capture stream (the caller's stream may be the legacy default stream)
+  // Data-parallel exchange without splitting the step (hippie_train_fwd_bwd_part, part 4): the whole step stays ONE
+  // graph; `xs` collects, without ever holding up the backward chain, the points at which a slice of the gradient
+  // buffer is final (chain stream + weight-gradient streams) and records ev_slice[k] -- as an EXTERNAL event-record node
+  // when the step is captured -- for the caller's exchange stream to wait on (hippie_slice_wait).
+  cudaStream_t xs = nullptr;
+  cudaEvent_t ev_slice[2] = {nullptr, nullptr};
+  bool export_ev = false, export_capturing = false;
+  std::vector<cudaEvent_t> deep_ev;
   int64_t st_x1 = 0, st_x2 = 0, st_src = 0, st_cls = 0, st_eps = 0, st_scal = 0, st_enc = 0, st_mu = 0, st_lv = 0,
           st_d1 = 0, st_d2 = 0;
   void clear_graphs() {
@@ -838,6 +846,13 @@ struct hippie_engine {
       }
       dgrad(b.c1, b.dc1, gx, true, B, br);
       wgrad(b.c1, b.dc1, b.x, B, br);
+      if (export_ev && i == 4) {  // the deep half of this encoder's gradients is final behind these two points
+        for (cudaStream_t st : {br.st, br.wst ? br.wst : br.st}) {
+          cudaEvent_t e = next_event();
+          cudaEventRecord(e, st);
+          deep_ev.push_back(e);
+        }
+      }
     }
     if (phase == 1) return;
     bn_bwd(gact.at(E.a0), false, E.a0, E.c0, E.bn0, -1, -1, E.dc0, 1, -1, 1, -1, B, br);
@@ -1002,6 +1017,14 @@ struct hippie_engine {
     Branch b0{main, ws + part_off[0], ws + bpart_off[0]}, b1{profiling ? main : side, ws + part_off[1], ws + bpart_off[1]};
     if (backward && !profiling) b0.wst = wside[0], b1.wst = wside[1];
     const float* xin[2] = {x1, x2};
+    export_ev = part == 4 && !profiling;  // whole step, slice events exported
+    if (part == 4) part = -1;
+    if (export_ev) {
+      cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+      cudaStreamIsCapturing(main, &cs);
+      export_capturing = cs != cudaStreamCaptureStatusNone;
+      deep_ev.clear();
+    }
     if (part >= 1) {  // later parts of a split step: the encoders' backward pass (1 = whole, 2 = deep half, 3 = shallow half)
       encoders_bwd(xin, B, b0, b1, main, part == 1 ? 0 : part - 1);
       if (failed) return fail(-9, err);
@@ -1051,13 +1074,39 @@ struct hippie_engine {
       launch_head_bwd(ha, main);
       prof_end(pe6, 6, 0.0, b0);
       ++launches;
-      if (part == 0)
+      if (part == 0) {
         join_wgrad(main);  // decoder + head gradients are final when part 0 completes
-      else
+      } else {
+        if (export_ev) {  // latent head + decoders: final from here on
+          if (n_dec == 2)
+            signal_slice(0, {main, wside[0], wside[1]});
+          else
+            signal_slice(0, {main, wside[0]});
+        }
         encoders_bwd(xin, B, b0, b1, main);
+        if (export_ev) {  // xs rejoins the caller's stream (a captured step must end with every forked stream joined)
+          cudaEvent_t e = next_event();
+          cudaEventRecord(e, xs);
+          cudaStreamWaitEvent(main, e, 0);
+          export_ev = false;
+        }
+      }
     }
     if (failed) return fail(-9, err);
     return check(train ? "train_fwd_bwd" : "eval_forward");
+  }
+  // slice k of the gradient buffer is final once everything enqueued so far on `streams` / recorded in `evs` is done
+  void signal_slice(int k, std::initializer_list<cudaStream_t> streams, const std::vector<cudaEvent_t>& evs = {}) {
+    for (cudaStream_t st : streams) {
+      cudaEvent_t e = next_event();
+      cudaEventRecord(e, st);
+      cudaStreamWaitEvent(xs, e, 0);
+    }
+    for (cudaEvent_t e : evs) cudaStreamWaitEvent(xs, e, 0);
+    if (export_capturing)
+      cudaEventRecordWithFlags(ev_slice[k], xs, cudaEventRecordExternal);
+    else
+      cudaEventRecord(ev_slice[k], xs);
   }
   void join_wgrad(cudaStream_t main) {  // the weight-gradient streams rejoin the caller's stream
     if (profiling) return;
@@ -1071,10 +1120,9 @@ struct hippie_engine {
     const bool two = n_enc == 2;
     if (two) fork(main);
     encoder_bwd(enc[0], xin[0], B, b0, phase);
-    if (two) {
-      encoder_bwd(enc[1], xin[1], B, b1, phase);
-      join(main);
-    }
+    if (two) encoder_bwd(enc[1], xin[1], B, b1, phase);
+    if (export_ev) signal_slice(1, {}, deep_ev);  // layer3 + layer4 + Linear of every encoder (recorded in encoder_bwd)
+    if (two) join(main);
     join_wgrad(main);
   }
 
@@ -1273,6 +1321,9 @@ void hippie_destroy(hippie_handle h) {
   h->clear_graphs();
   if (h->side) cudaStreamDestroy(h->side);
   if (h->cap) cudaStreamDestroy(h->cap);
+  if (h->xs) cudaStreamDestroy(h->xs);
+  for (int i = 0; i < 2; ++i)
+    if (h->ev_slice[i]) cudaEventDestroy(h->ev_slice[i]);
   for (auto e : h->ev_pool) cudaEventDestroy(e);
   for (int i = 0; i < 2; ++i)
     if (h->wside[i]) cudaStreamDestroy(h->wside[i]);
@@ -1349,6 +1400,8 @@ int hippie_bind(hippie_handle h, float* params, float* grads, float* exp_avg, fl
     cudaStreamCreateWithPriority(&h->cap, cudaStreamNonBlocking, prio_hi);
     cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
     for (int i = 0; i < 2; ++i) cudaStreamCreateWithPriority(&h->wside[i], cudaStreamNonBlocking, prio_lo);
+    cudaStreamCreateWithPriority(&h->xs, cudaStreamNonBlocking, prio_hi);
+    for (int i = 0; i < 2; ++i) cudaEventCreateWithFlags(&h->ev_slice[i], cudaEventDisableTiming);
     h->ev_pool.resize(512);
     for (auto& e : h->ev_pool) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming);
@@ -1388,12 +1441,20 @@ int hippie_train_fwd_bwd_part(hippie_handle h, const float* x1, const float* x2,
   if (!h) return -1;
   if (int rc = h->validate(B, x1, x2, src)) return rc;
   if (h->cfg.inference_only) return h->fail(-7, "inference-only engine");
-  if (part < 0 || part > 3) return h->fail(-3, "part must be 0..3");
+  if (part < 0 || part > 4) return h->fail(-3, "part must be 0..4");
   if (!eps) return h->fail(-4, "eps is required for training (reparameterisation noise)");
   if (B < 2) return h->fail(-3, "training-mode BatchNorm needs B >= 2");
-  hippie_engine::CallArgs a{4 + part, x1, x2, src, cls, eps, B, beta, w1, w2, -1, part == 0 ? scalars_out : nullptr,
+  hippie_engine::CallArgs a{4 + part, x1, x2, src, cls, eps, B, beta, w1, w2, -1, (part == 0 || part == 4) ? scalars_out : nullptr,
                             nullptr, nullptr, nullptr, nullptr, nullptr};
   return h->call(a, (cudaStream_t)stream);
+}
+
+int hippie_slice_wait(hippie_handle h, int32_t slice, void* stream) {
+  if (!h) return -1;
+  if (!h->bound) return h->fail(-2, "hippie_bind has not been called");
+  if (slice < 0 || slice > 1) return h->fail(-3, "slice must be 0 (latent head + decoders) or 1 (deep encoder halves)");
+  cudaError_t ce = cudaStreamWaitEvent((cudaStream_t)stream, h->ev_slice[slice], 0);
+  return ce == cudaSuccess ? 0 : h->fail((int)ce, std::string("hippie_slice_wait: ") + cudaGetErrorString(ce));
 }
 
 int64_t hippie_grad_split(hippie_handle h) { return h ? h->grad_split : -1; }

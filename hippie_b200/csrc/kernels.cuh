@@ -80,6 +80,7 @@ struct PairOpts {
   int taps;          // conv, b_mn = 1: kernel size of the layer
   const float* dyn_scale = nullptr;  // device float multiplied into out_scale (1 / scale of a gradient pair tensor)
   unsigned long long* stamps = nullptr;  // tools/pair_test: 8 device slots for %globaltimer phase stamps of CTA (0, 0)
+  int stamps_all = 0;  // tools/pair_test: every CTA writes 8 slots (slot 7 = %smid)
   const EvalFold* fold = nullptr;        // conv forward in eval mode
   const TcMap* out_map = nullptr;        // conv: fp32 output tensor map (pair_make_out_map) -> TMA stores of whole tiles
 };

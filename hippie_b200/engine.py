@@ -222,11 +222,16 @@ class Engine:
         deep / shallow halves of the encoders (`grad_bounds`) (hippie_train_fwd_bwd_part)."""
         B = x1.shape[0]
         self._io(x1, x2, src, cls, eps, B)
-        if scalars is None and part == 0:
+        if scalars is None and part in (0, 4):
             scalars = torch.zeros(8, dtype=torch.float32, device=self.device)
         self._check(self._L.hippie_train_fwd_bwd_part(self._h, _ptr(x1), _ptr(x2), _ptr(src), _ptr(cls), _ptr(eps), B, beta,
                                                       w1, w2, _ptr(scalars), part, self._stream()))
         return scalars
+
+    def slice_wait(self, k: int, stream: "torch.cuda.Stream"):
+        """Makes `stream` wait until slice k of the gradient buffer of the most recent part-4 step is final
+        (0: flat_grads[grad_split:], 1: the deep halves of `grad_bounds`); hippie_slice_wait."""
+        self._check(self._L.hippie_slice_wait(self._h, k, C.c_void_p(stream.cuda_stream)))
 
     @property
     def grad_split(self) -> int:

@@ -76,16 +76,53 @@ def broadcast_state(tensors: Sequence[torch.Tensor], src: int = 0, group=None):
             dist.broadcast(t, src=src, group=group)
 
 
+_exchange_streams = {}
+
+
+def _exchange_stream(device) -> "torch.cuda.Stream":
+    """One side stream per device on which the slice waits and the all-reduces of the overlapped exchange are issued."""
+    key = torch.device(device).index
+    if key not in _exchange_streams:
+        _exchange_streams[key] = torch.cuda.Stream(device=device, priority=-1)
+    return _exchange_streams[key]
+
+
 def train_step_overlapped(engine, x1, x2, src, cls, eps, beta, w1=1.0, w2=1.0, scalars=None, group=None) -> float:
     """One data-parallel forward + backward with the gradient exchange overlapped with the backward pass, in the order
-    the gradients become final: the latent-head + decoder half of the buffer (52 %) after part 0 -- its all-reduce runs
-    on NCCL's stream under the encoders' backward pass --, the deep half of each encoder (layer3, layer4, Linear: 45 %)
-    after part 2, under the backward pass of the wide shallow layers, and only the shallow remainder (3 %, < 2 MB) after
-    part 3 with nothing to hide under.  Returns the factor for the optimizer (1/world).  Without an initialised process
-    group this is a plain train_fwd_bwd."""
+    the gradients become final: the latent-head + decoder half of the buffer (52 %) -- its all-reduce runs on NCCL's
+    stream under the encoders' backward pass --, the deep half of each encoder (layer3, layer4, Linear: 45 %), under the
+    backward pass of the wide shallow layers, and only the shallow remainder (3 %, < 2 MB) after the step with nothing to
+    hide under.  The step itself stays ONE launch (one CUDA graph, `hippie_train_fwd_bwd_part` part 4): the engine
+    publishes the two points as events (`hippie_slice_wait`) that an exchange stream waits on, so the backward chain is
+    never cut (round 1 cut the step into three graphs at these points: every cut drained the weight-gradient streams).
+    `HIPPIE_B200_DP_PARTS=1` selects that older three-part variant.  Returns the factor for the optimizer (1/world).
+    Without an initialised process group this is a plain train_fwd_bwd."""
     if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
         engine.train_fwd_bwd(x1, x2, src, cls, eps, beta, w1, w2, scalars=scalars)
         return 1.0
+    import os
+    if os.environ.get("HIPPIE_B200_DP_PARTS", "0") == "1" or not hasattr(engine, "slice_wait"):
+        return _train_step_overlapped_parts(engine, x1, x2, src, cls, eps, beta, w1, w2, scalars, group)
+    g = engine.flat_grads
+    reduce = lambda lo, hi: dist.all_reduce(g[lo:hi], op=dist.ReduceOp.SUM, group=group, async_op=True)
+    main = torch.cuda.current_stream(g.device)
+    xs = _exchange_stream(g.device)
+    engine.train_fwd_bwd_part(4, x1, x2, src, cls, eps, beta, w1, w2, scalars=scalars)
+    bounds = engine.grad_bounds
+    with torch.cuda.stream(xs):
+        engine.slice_wait(0, xs)
+        work = [reduce(engine.grad_split, g.numel())]
+        engine.slice_wait(1, xs)
+        work += [reduce(deep, end) for _, deep, end in bounds]
+    work += [reduce(begin, deep) for begin, deep, _ in bounds]  # on the step's own stream: final when it gets there
+    for w in work:
+        w.wait()  # the current stream waits for NCCL's
+    main.wait_stream(xs)
+    return 1.0 / dist.get_world_size(group)
+
+
+def _train_step_overlapped_parts(engine, x1, x2, src, cls, eps, beta, w1=1.0, w2=1.0, scalars=None, group=None) -> float:
+    """Round-1 variant of the overlapped exchange: the step cut into three stream-ordered parts (0, 2, 3)."""
     g = engine.flat_grads
     reduce = lambda lo, hi: dist.all_reduce(g[lo:hi], op=dist.ReduceOp.SUM, group=group, async_op=True)
     engine.train_fwd_bwd_part(0, x1, x2, src, cls, eps, beta, w1, w2, scalars=scalars)

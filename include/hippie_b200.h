@@ -129,6 +129,15 @@ int hippie_train_fwd_bwd(hippie_handle h, const float* x1, const float* x2, cons
 int hippie_train_fwd_bwd_part(hippie_handle h, const float* x1, const float* x2, const int64_t* src, const int64_t* cls,
                               const float* eps, int32_t B, float beta, float w1, float w2, float* scalars_out,
                               int32_t part, void* stream);
+/* part 4 = the WHOLE step as one launch sequence (one CUDA graph) that additionally publishes, without interrupting the
+ * backward pass, the two points at which a slice of the gradient buffer becomes final:
+ *   slice 0 = grads[hippie_grad_split(h) ..)            (latent head + decoders), after the latent-head backward;
+ *   slice 1 = the deep halves [deep_e, end_e) of hippie_grad_bounds(h)   (layer3, layer4, Linear of every encoder).
+ * hippie_slice_wait(h, k, s) makes stream s wait for slice k of the most recent part-4 call (cudaStreamWaitEvent on an
+ * event the step records -- as an external event-record node when the step is replayed from its graph), so that an
+ * all-reduce issued on s overlaps the rest of the backward pass; the shallow remainder is final when the call's own
+ * stream reaches the end of the step.  hippie_b200/parallel.py:train_step_overlapped. */
+int hippie_slice_wait(hippie_handle h, int32_t slice, void* stream);
 int64_t hippie_grad_split(hippie_handle h);
 
 /* A finer split of the encoder backward for the same purpose: instead of part 1 call

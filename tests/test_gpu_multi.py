@@ -34,17 +34,24 @@ eng.load_named(st)
 broadcast_state([eng.flat_params, eng.bn_mean, eng.bn_var])
 sl = slice(rank * PB, (rank + 1) * PB)
 scal = torch.zeros(8, device=dev)
-scale = train_step_overlapped(eng, x1[sl].to(dev), x2[sl].to(dev), labels[sl].to(dev), None, eps[sl].to(dev), 0.5, 1.0, 1.0,
-                              scalars=scal)
-torch.cuda.synchronize()
-g_dp = eng.flat_grads.clone()
-sc = eng.clip_adamw(1e-3, 0.01, 1, max_norm=1.0, grad_scale=scale)
-p_dp = eng.flat_params.clone()
-# every rank holds the same gradients and parameters after the exchange
-for t in (g_dp, p_dp):
-    other = [torch.empty_like(t) for _ in range(world)]
-    dist.all_gather(other, t)
-    assert all(torch.equal(o, other[0]) for o in other), "ranks diverged"
+args = (x1[sl].to(dev), x2[sl].to(dev), labels[sl].to(dev), None, eps[sl].to(dev), 0.5, 1.0, 1.0)
+hist = []
+for it in range(5):  # eager call, graph capture, graph replays: the exchange must wait for THIS step's slices every time
+    eng.load_named(st)
+    eng.exp_avg.zero_(), eng.exp_avg_sq.zero_()
+    scale = train_step_overlapped(eng, *args, scalars=scal)
+    torch.cuda.synchronize()
+    g_dp = eng.flat_grads.clone()
+    sc = eng.clip_adamw(1e-3, 0.01, 1, max_norm=1.0, grad_scale=scale)
+    p_dp = eng.flat_params.clone()
+    hist.append(g_dp)
+    # every rank holds the same gradients and parameters after the exchange
+    for t in (g_dp, p_dp):
+        other = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(other, t)
+        assert all(torch.equal(o, other[0]) for o in other), "ranks diverged"
+for h in hist[1:]:
+    assert ((h - hist[0]).norm() / hist[0].norm()).item() <= 1e-5, "replayed steps differ from the first"
 if rank == 0:
     # single process: the shards one after the other on one engine, gradients summed
     ref = Engine(cfg.z_dim, 50, 100, 5, cfg.num_sources, cfg.num_classes, True, PB).allocate(dev)

@@ -154,6 +154,42 @@ static void test_conv(int B, int L, int Cin, int Cout, int k, int stride, bool b
            hs[1] - hs[0], hs[2] - hs[1], hs[3] - hs[2], hs[4] - hs[3], hs[5] - hs[4], hs[6] - hs[5]);
     cudaFree(ds);
   }
+  if (getenv("PT_STAMPS") && atoi(getenv("PT_STAMPS")) == 2) {  // every CTA: placement on the SMs and phase times
+    const int nb = 128 / g.Lout, gx = (B + nb - 1) / nb, gy = g.N / bn, nc = gx * gy;
+    unsigned long long* ds;
+    CK(cudaMalloc(&ds, (size_t)nc * 64));
+    CK(cudaMemset(ds, 0, (size_t)nc * 64));
+    PairOpts o2 = o;
+    o2.stamps = ds, o2.stamps_all = 1;
+    CK(cudaDeviceSynchronize());
+    launch_conv_pair(g2, ma, mw, bn, B, o2, 0);
+    CK(cudaDeviceSynchronize());
+    std::vector<unsigned long long> hs((size_t)nc * 8);
+    CK(cudaMemcpy(hs.data(), ds, (size_t)nc * 64, cudaMemcpyDeviceToHost));
+    int per_sm[256] = {0};
+    unsigned long long t_min = ~0ull, t_max = 0;
+    for (int c = 0; c < nc; ++c) {
+      per_sm[hs[c * 8 + 7] & 255]++;
+      t_min = std::min(t_min, hs[c * 8 + 0]), t_max = std::max(t_max, hs[c * 8 + 6]);
+    }
+    int sms = 0, hist[8] = {0};
+    for (int i = 0; i < 256; ++i)
+      if (per_sm[i]) ++sms, hist[std::min(per_sm[i], 7)]++;
+    double ml[8] = {0}, tot[8] = {0}, fill[8] = {0}, late[8] = {0};
+    int cnt[8] = {0};
+    for (int c = 0; c < nc; ++c) {
+      const int k = std::min(per_sm[hs[c * 8 + 7] & 255], 7);
+      ml[k] += (double)(hs[c * 8 + 3] - hs[c * 8 + 2]), tot[k] += (double)(hs[c * 8 + 6] - hs[c * 8 + 0]);
+      fill[k] += (double)(hs[c * 8 + 2] - hs[c * 8 + 1]), late[k] += (double)(hs[c * 8 + 0] - t_min), cnt[k]++;
+    }
+    printf("   all CTAs: %d CTAs on %d SMs (SMs with 1/2/3/4 CTAs: %d/%d/%d/%d), span %llu ns\n", nc, sms, hist[1], hist[2], hist[3],
+           hist[4], t_max - t_min);
+    for (int k = 1; k < 8; ++k)
+      if (cnt[k])
+        printf("     CTAs on SMs holding %d: n=%d  start +%.0f ns | first fill %.0f | main loop %.0f | CTA life %.0f ns\n", k, cnt[k],
+               late[k] / cnt[k], fill[k] / cnt[k], ml[k] / cnt[k], tot[k] / cnt[k]);
+    cudaFree(ds);
+  }
   const double fl = 2.0 * g.M * g.N * g.K;
   printf("conv  B=%4d L=%3d %3d->%3d k%d s%d bias%d a%d b%d bn%3d | rel err %.2e stats %.1e | simt %7.1f us %6.1f TF | pair %7.1f us %6.1f TF\n",
          B, L, Cin, Cout, k, stride, bias, a_fmt, b_fmt, bn, md / mr, stat_err, t1 * 1e3, fl / t1 / 1e9, t2 * 1e3, fl / t2 / 1e9);
