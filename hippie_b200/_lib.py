@@ -12,7 +12,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libhippie_b200.so")
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 
 class HippieCfg(C.Structure):
@@ -72,6 +72,7 @@ SIGNATURES = {
     "hippie_decode": (C.c_int, [_H, _f32p, _f32p, _f32p, C.c_int32, C.c_int32, _f32p, _f32p, C.c_void_p]),
     "hippie_slice_wait": (C.c_int, [_H, C.c_int32, C.c_void_p]),
     "hippie_device_flags": (C.c_int, [_H, C.POINTER(C.c_uint32), C.c_int32, C.c_void_p]),
+    "hippie_params_changed": (C.c_int, [_H]),
     "hippie_clip_adamw": (C.c_int, [_H, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, C.c_float, C.c_float,
                                     C.c_int32, C.c_int32, C.c_int32, _f32p, C.c_void_p]),
     "hippie_preprocess_batch": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, _i64p, C.c_int32, _f32p, C.c_int32,

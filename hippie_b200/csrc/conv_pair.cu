@@ -18,9 +18,13 @@
 // (TMEM -> registers -> swizzled shared staging -> ONE elected thread issues TMA tensor stores of the whole tile
 // (add-reduce when the layer accumulates into its output) while the four warps compute the BatchNorm (sum, centred M2)
 // partials from the same staging; the eval-mode fold uses per-thread stores).
-// The tensor core truncates when it adds into the fp32 accumulator; to keep that bias below the parity bound the
-// hi*hi products alternate between two accumulators and the small cross terms use a third (summed with
-// round-to-nearest in the epilogue).
+// The B planes of a stage sit next to each other in shared memory, so ONE descriptor spans [B hi | B lo] as 2 * BN
+// columns: a k-step is   A hi x [B hi | B lo]  (N = 2 BN: hi*hi and hi*lo land side by side in tensor memory)  and
+// A lo x B hi  (N = BN, added onto the hi*lo columns).  Same tensor math as three N = BN instructions, but the A hi
+// tile is read from shared memory once instead of twice: 14 KB instead of 18 KB per k-step through the 128 B/clk
+// port that bounds the main loop (tools/mma_rate2: 48 / 64 cycles per N = 64 / 128 instruction).
+// The tensor core truncates when it adds into the fp32 accumulator; to keep that bias below the parity bound
+// consecutive k-steps alternate between two accumulator sets (summed with round-to-nearest in the epilogue).
 //
 // Replaces the nn.Conv1d forward calls of hippie/backbones.py:11,24,26,31,50,55 and their autograd backward.
 #include <cuda.h>
@@ -64,6 +68,11 @@ constexpr int kBN = HP_KBN, kStages = HP_KSTAGES;  // overridable for tools/pair
 // L2 -> shared-memory ingest while other SMs idle (512->512 L=4, 128 CTAs: 21.0 -> 16.1 us, tools/pair_test).
 constexpr int kStagesAlone = HP_KSTAGES > 3 ? HP_KSTAGES : 3;
 constexpr int ctas_per_sm(int bn, int stages) { return (PK * 2 * (128 + bn) * 2 * stages <= 100 * 1024 && bn <= 64) ? 2 : 1; }
+// Register budget: the kernels are compiled as if THREE CTAs had to fit on an SM (<= 112 registers per thread).  Two fit by
+// shared memory; the registers they leave free decide whether a CTA of an elementwise kernel (BatchNorm apply / backward, on the
+// critical chains) can start on an SM that already holds two GEMM CTAs: at 154 registers nothing fits and the bs512 step is 4 %
+// slower than at 122 (gpurun_out/r02_exp32.txt).
+constexpr int reg_ctas_per_sm(int bn, int stages) { return ctas_per_sm(bn, stages) == 2 ? 3 : 1; }
 
 struct PairConv {
   float* C;
@@ -74,7 +83,10 @@ struct PairConv {
   int Lout, nb;
   int out_rows, out_off, out_lstride, accumulate;
   float out_scale;
-  uint32_t idesc;
+  uint32_t idesc;   // N = BN       (A lo x B hi)
+  uint32_t idesc2;  // N = 2 * BN   (A hi x [B hi | B lo])
+  int nmma;         // 3: all three products; 2: experiment, A lo x B hi dropped (A at 11 bits)
+  int fused;        // 1: A hi x [B hi | B lo] as one N = 2 BN instruction; 0: two N = BN instructions
   int b_mn;        // 1: B tiles are MN-major boxes of the forward weight planes [co][t][ci]
   int kb_per_tap;  // b_mn: k-blocks per tap (= Cout / 64)
   int taps;        // b_mn: kernel size (3 or 1); tap of k-block kb = taps - 1 - kb / kb_per_tap
@@ -116,7 +128,7 @@ struct PairSmem {
     return (col >> 5) * EPI_BOX_FLOATS + r * 32 + (((((col & 31) >> 2) ^ (r & 7))) << 2) + (col & 3);
   }
   static constexpr int TOTAL = RING_BYTES + 1024 + 256;
-  static constexpr int TMEM_COLS = BN == 128 ? 512 : 256;  // three accumulators of BN columns (power of two)
+  static constexpr int TMEM_COLS = 4 * BN;  // two accumulator sets of [hi*hi | cross terms], BN columns each
 };
 
 // MODE: kConvTrain = training forward (K-major weights, bias, BatchNorm partials, TMA stores), kConvEval = eval forward
@@ -127,7 +139,7 @@ constexpr int kConvTrain = 0, kConvEval = 1, kConvDgrad = 2;
 constexpr int kConvProducers = 4;   // TMA-issuing threads of conv_pair_kernel (warps 0, 2, 3, 4)
 constexpr int kWgradProducers = 5;  // of wgrad_pair_kernel (warps 0, 2, 3, 4, 5)
 template <int BN, int STAGES, int MODE>
-__global__ void __launch_bounds__(TC_THREADS, ctas_per_sm(BN, STAGES))
+__global__ void __launch_bounds__(TC_THREADS, reg_ctas_per_sm(BN, STAGES))
     conv_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                      const __grid_constant__ CUtensorMap mapC, PairConv p) {
   constexpr bool EVAL = MODE == kConvEval, B_MN = MODE == kConvDgrad;
@@ -214,21 +226,28 @@ __global__ void __launch_bounds__(TC_THREADS, ctas_per_sm(BN, STAGES))
       if (elect_one()) {
         const uint32_t st = smem_u32(ring + s * S::STAGE_BYTES);
         const uint64_t a_hi = umma_desc(st, 16, 1024, 2), a_lo = umma_desc(st + S::A_LO, 16, 1024, 2);
-        uint64_t b_hi, b_lo, badv;
+        // the B lo plane follows the B hi plane: the same descriptor read with N = 2 BN covers [B hi | B lo]
+        constexpr uint64_t blo = (uint64_t)(S::B_PLANE >> 4);  // descriptor offset of the B lo plane
+        uint64_t b_hi, badv;
         if (!B_MN) {  // K-major: 8-row groups 1024 B apart, 16 halfs = 32 B along the swizzled row per step
-          b_hi = umma_desc(st + S::B_OFF, 16, 1024, 2), b_lo = umma_desc(st + S::B_LO, 16, 1024, 2);
+          b_hi = umma_desc(st + S::B_OFF, 16, 1024, 2);
           badv = 32 >> 4;
         } else {  // MN-major: groups of 64 columns 8 KB apart (LBO), 8 k-rows 1024 B apart (SBO), 16 k-rows per step
-          b_hi = umma_desc(st + S::B_OFF, 8192, 1024, 2), b_lo = umma_desc(st + S::B_LO, 8192, 1024, 2);
+          b_hi = umma_desc(st + S::B_OFF, 8192, 1024, 2);
           badv = 2048 >> 4;
         }
 #pragma unroll
         for (int k16 = 0; k16 < PK / 16; ++k16) {
           const uint64_t aadv = (uint64_t)(k16 * 32 >> 4), bad = (uint64_t)k16 * badv;
           const int step = kb * (PK / 16) + k16;
-          umma_f16(tmem_base + 2 * BN, a_lo + aadv, b_hi + bad, p.idesc, step != 0 ? 1u : 0u);
-          umma_f16(tmem_base + 2 * BN, a_hi + aadv, b_lo + bad, p.idesc, 1u);
-          umma_f16(tmem_base + (step & 1) * BN, a_hi + aadv, b_hi + bad, p.idesc, step >= 2 ? 1u : 0u);
+          const uint32_t acc = tmem_base + (uint32_t)((step & 1) * 2 * BN);
+          if (p.fused) {
+            umma_f16(acc, a_hi + aadv, b_hi + bad, p.idesc2, step >= 2 ? 1u : 0u);  // [hi*hi | hi*lo]
+          } else {
+            umma_f16(acc, a_hi + aadv, b_hi + bad, p.idesc, step >= 2 ? 1u : 0u);
+            umma_f16(acc + BN, a_hi + aadv, b_hi + blo + bad, p.idesc, step >= 2 ? 1u : 0u);
+          }
+          if (p.nmma == 3) umma_f16(acc + BN, a_lo + aadv, b_hi + bad, p.idesc, 1u);  // + lo*hi
         }
         umma_commit(&empty[s]);
       }
@@ -249,14 +268,20 @@ __global__ void __launch_bounds__(TC_THREADS, ctas_per_sm(BN, STAGES))
     const float sc = p.dyn_scale ? p.out_scale * __ldg(p.dyn_scale) : p.out_scale;
 #pragma unroll
     for (int c = 0; c < BN / 32; ++c) {
-      uint32_t r[32], r1[32], r2[32];
+      // two live register arrays: the register footprint of these CTAs decides whether an elementwise kernel's CTA still
+      // fits on an SM that holds two of them (122 -> 154 registers cost 4 % of the bs512 step, gpurun_out/r02_exp32.txt)
+      uint32_t r[32], r1[32];
       const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32);
-      tmem_ld32(ta, r);
-      tmem_ld32(ta + BN, r1);
-      tmem_ld32(ta + 2 * BN, r2);
+      tmem_ld32(ta + BN, r);       // cross terms, even k-steps
+      tmem_ld32(ta + 3 * BN, r1);  // cross terms, odd k-steps
 #pragma unroll
-      for (int i = 0; i < 32; ++i)
-        r[i] = __float_as_uint(((__uint_as_float(r[i]) + __uint_as_float(r1[i])) + __uint_as_float(r2[i])) * sc);
+      for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) + __uint_as_float(r1[i]));
+      tmem_ld32(ta, r1);           // hi*hi, even k-steps
+#pragma unroll
+      for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) + __uint_as_float(r1[i]));
+      tmem_ld32(ta + 2 * BN, r1);  // hi*hi, odd k-steps
+#pragma unroll
+      for (int i = 0; i < 32; ++i) r[i] = __float_as_uint((__uint_as_float(r[i]) + __uint_as_float(r1[i])) * sc);
       if (!B_MN && p.bias) {  // warp-uniform addresses: broadcast loads
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -413,12 +438,13 @@ struct PairWgrad {
   int rows_per_split;  // multiple of PK
   float out_scale;
   const float* dyn_scale;
-  uint32_t idesc;
+  uint32_t idesc, idesc2;  // N = BN, N = 2 * BN (see PairConv)
+  int nmma, fused;
   int pdl_late;
 };
 
 template <int BN, int STAGES>
-__global__ void __launch_bounds__(TC_THREADS, ctas_per_sm(BN, STAGES))
+__global__ void __launch_bounds__(TC_THREADS, reg_ctas_per_sm(BN, STAGES))
     wgrad_pair_kernel(const __grid_constant__ CUtensorMap mapDY, const __grid_constant__ CUtensorMap mapX,
                       const __grid_constant__ CUtensorMap mapDW, PairWgrad p) {
   using S = PairSmem<BN, STAGES>;
@@ -496,14 +522,20 @@ __global__ void __launch_bounds__(TC_THREADS, ctas_per_sm(BN, STAGES))
       if (elect_one()) {
         const uint32_t st = smem_u32(ring + s * S::STAGE_BYTES);
         const uint64_t a_hi = umma_desc(st, 8192, 1024, 2), a_lo = umma_desc(st + S::A_LO, 8192, 1024, 2);
-        const uint64_t b_hi = umma_desc(st + S::B_OFF, 8192, 1024, 2), b_lo = umma_desc(st + S::B_LO, 8192, 1024, 2);
+        const uint64_t b_hi = umma_desc(st + S::B_OFF, 8192, 1024, 2);  // N = 2 BN: [X hi | X lo], groups 8 KB apart
+        constexpr uint64_t blo = (uint64_t)(S::B_PLANE >> 4);
 #pragma unroll
         for (int k16 = 0; k16 < PK / 16; ++k16) {
           const uint64_t adv = (uint64_t)(k16 * 2048 >> 4);  // 16 reduction rows = 16 x 128 B
           const int step = kb * (PK / 16) + k16;
-          umma_f16(tmem_base + 2 * BN, a_lo + adv, b_hi + adv, p.idesc, step != 0 ? 1u : 0u);
-          umma_f16(tmem_base + 2 * BN, a_hi + adv, b_lo + adv, p.idesc, 1u);
-          umma_f16(tmem_base + (step & 1) * BN, a_hi + adv, b_hi + adv, p.idesc, step >= 2 ? 1u : 0u);
+          const uint32_t acc = tmem_base + (uint32_t)((step & 1) * 2 * BN);
+          if (p.fused) {
+            umma_f16(acc, a_hi + adv, b_hi + adv, p.idesc2, step >= 2 ? 1u : 0u);  // [hi*hi | hi*lo]
+          } else {
+            umma_f16(acc, a_hi + adv, b_hi + adv, p.idesc, step >= 2 ? 1u : 0u);
+            umma_f16(acc + BN, a_hi + adv, b_hi + blo + adv, p.idesc, step >= 2 ? 1u : 0u);
+          }
+          if (p.nmma == 3) umma_f16(acc + BN, a_lo + adv, b_hi + adv, p.idesc, 1u);  // + lo*hi
         }
         umma_commit(&empty[s]);
       }
@@ -522,14 +554,20 @@ __global__ void __launch_bounds__(TC_THREADS, ctas_per_sm(BN, STAGES))
     const float sc = p.dyn_scale ? p.out_scale * __ldg(p.dyn_scale) : p.out_scale;
 #pragma unroll
     for (int c = 0; c < BN / 32; ++c) {
-      uint32_t r[32], r1[32], r2[32];
+      // two live register arrays: the register footprint of these CTAs decides whether an elementwise kernel's CTA still
+      // fits on an SM that holds two of them (122 -> 154 registers cost 4 % of the bs512 step, gpurun_out/r02_exp32.txt)
+      uint32_t r[32], r1[32];
       const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32);
-      tmem_ld32(ta, r);
-      tmem_ld32(ta + BN, r1);
-      tmem_ld32(ta + 2 * BN, r2);
+      tmem_ld32(ta + BN, r);       // cross terms, even k-steps
+      tmem_ld32(ta + 3 * BN, r1);  // cross terms, odd k-steps
 #pragma unroll
-      for (int i = 0; i < 32; ++i)
-        r[i] = __float_as_uint(((__uint_as_float(r[i]) + __uint_as_float(r1[i])) + __uint_as_float(r2[i])) * sc);
+      for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) + __uint_as_float(r1[i]));
+      tmem_ld32(ta, r1);           // hi*hi, even k-steps
+#pragma unroll
+      for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) + __uint_as_float(r1[i]));
+      tmem_ld32(ta + 2 * BN, r1);  // hi*hi, odd k-steps
+#pragma unroll
+      for (int i = 0; i < 32; ++i) r[i] = __float_as_uint((__uint_as_float(r[i]) + __uint_as_float(r1[i])) * sc);
 #pragma unroll
       for (int i = 0; i < 8; ++i)
         *reinterpret_cast<uint4*>(&stage[S::epi(row, c * 32 + i * 4)]) =
@@ -618,6 +656,8 @@ static void set_smem_attrs() {
   cudaFuncSetAttribute(wgrad_pair_kernel<kBN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
 }
 static int g_variant = 0, g_wgrad_variant = 1, g_pdl_late = 0;
+static int g_mma_scheme = 7;  // HIPPIE_B200_MMA_SCHEME bits: 1 forward, 2 dgrad, 4 wgrad issue A hi x [B hi | B lo] as one instruction
+static int g_bwd_nmma = 3;  // HIPPIE_B200_BWD_MMA=2: accuracy experiment, dgrad / wgrad without the (gradient lo) x (hi) product
 static int g_wgrad_min_kb = 16;  // k-blocks (of 64 reduction rows) a weight-gradient CTA processes at least: the kernels are off
 // the critical path, so few long-lived CTAs (less prologue / fill / epilogue time per MAC) beat many short ones -- the step is
 // bound by the time CTAs occupy SM slots (bs512: 4 -> 3.134 ms, 16 -> 3.054 ms, 64 -> 3.308 ms per step)
@@ -639,6 +679,8 @@ bool pair_init(std::string* err) {
   set_smem_attrs<kStagesAlone>();
   if (const char* v = getenv("HIPPIE_B200_PAIR_VARIANT")) g_variant = atoi(v);  // 0 auto, 1 always shared, 2 always alone
   if (const char* v = getenv("HIPPIE_B200_PDL_LATE")) g_pdl_late = atoi(v);
+  if (const char* v = getenv("HIPPIE_B200_MMA_SCHEME")) g_mma_scheme = atoi(v);
+  if (const char* v = getenv("HIPPIE_B200_BWD_MMA")) g_bwd_nmma = atoi(v) == 2 ? 2 : 3;
   if (const char* v = getenv("HIPPIE_B200_WGRAD_VARIANT")) g_wgrad_variant = atoi(v);  // 1 shared (two CTAs per SM), 2 alone
   if (const char* v = getenv("HIPPIE_B200_WGRAD_MIN_KB")) g_wgrad_min_kb = atoi(v) > 0 ? atoi(v) : 16;
   int dev = 0;
@@ -732,6 +774,9 @@ int launch_conv_pair(const ConvGemm& g, const TcMap& mapA, const TcMap& mapB, in
   p.out_rows = g.out_rows, p.out_off = g.out_off, p.out_lstride = g.out_lstride, p.accumulate = g.accumulate;
   p.out_scale = o.out_scale;
   p.idesc = umma_idesc_16(bn, o.a_fmt, o.b_fmt, 0, o.b_mn ? 1 : 0);
+  p.idesc2 = umma_idesc_16(2 * bn, o.a_fmt, o.b_fmt, 0, o.b_mn ? 1 : 0);
+  p.nmma = o.b_mn ? g_bwd_nmma : 3;
+  p.fused = (g_mma_scheme >> (o.b_mn ? 1 : 0)) & 1;
   p.b_mn = o.b_mn, p.taps = o.taps, p.kb_per_tap = o.taps > 0 ? (g.K / o.taps) / PK : 1;
   p.dyn_scale = o.dyn_scale, p.stamps = o.stamps, p.stamps_all = o.stamps_all, p.pdl_late = g_pdl_late & 1;
   if (o.fold) p.fold = *o.fold;
@@ -756,6 +801,9 @@ void launch_wgrad_pair(const WgradGemm& g, const TcMap& mapDY, const TcMap& mapX
   p.out_scale = o.out_scale, p.dyn_scale = o.dyn_scale, p.pdl_late = (g_pdl_late >> 1) & 1;
   bn = kBN;
   p.idesc = umma_idesc_16(bn, o.a_fmt, o.b_fmt, 1, 1);
+  p.idesc2 = umma_idesc_16(2 * bn, o.a_fmt, o.b_fmt, 1, 1);
+  p.nmma = g_bwd_nmma;
+  p.fused = (g_mma_scheme >> 2) & 1;
   const int tiles = ((g.M + TC_BM - 1) / TC_BM) * (g.N / bn);
   const bool alone = g_wgrad_variant == 2;
   int splits = ((alone ? 1 : 2) * sm_count) / tiles;  // one or two CTAs per SM

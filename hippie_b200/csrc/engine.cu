@@ -188,6 +188,8 @@ struct hippie_engine {
   }
   std::vector<ConvMaps> cmaps;
   bool tma_epilogue = true;  // conv outputs leave through TMA tensor stores (HIPPIE_B200_TMA_STORE=0: per-thread stores)
+  bool planes_fresh = false;  // the weight pair planes equal the parameter buffer (refresh_weights)
+  bool planes_keep = true;    // HIPPIE_B200_KEEP_PLANES=0: convert the whole buffer in every forward-type call (round 1)
   bool use_tc = false;  // tcgen05 implicit GEMMs over fp16 pair planes (conv_path 0); false = FP32 CUDA-core GEMMs
   std::string tc_note;
   int64_t flags_off = 0;  // device error flags (HIPPIE_FLAG_*), sticky until hippie_device_flags clears them
@@ -969,10 +971,14 @@ struct hippie_engine {
 
   // tcgen05 path: fp16 pair planes of the whole parameter buffer (scaled 2^8), used K-major by the forward convs and
   // MN-major by dgrad.  FP32 path: transposed + tap-flipped copies for dgrad.
+  // The planes stay valid between calls: hippie_clip_adamw rewrites the planes of every weight it updates, and whoever
+  // else writes the parameter buffer reports it (hippie_params_changed) -- only then is the 64 MB buffer converted again.
   void refresh_weights(bool backward, cudaStream_t main) {
     if (use_tc) {
+      if (planes_fresh && planes_keep) return;
       launch_to_pair(P, WP(), param_floats, param_floats, kWeightPairScale, kPairF16, main, flags());
       ++launches;
+      planes_fresh = true;
     } else if (backward && !wt_table.empty()) {
       launch_refresh_wt(reinterpret_cast<const WtEntry*>(ws + wt_table_off), (int)wt_table.size(), P, ws, main);
       ++launches;
@@ -1240,7 +1246,7 @@ struct hippie_engine {
     std::memset(&key, 0, sizeof(key));
     key.mode = a.mode, key.B = a.B, key.zscore = a.zscore, key.beta = a.beta, key.w1 = a.w1, key.w2 = a.w2;
     key.flags = (a.cls ? 1 : 0) | (a.eps ? 2 : 0) | (a.scalars ? 4 : 0) | (a.enc ? 8 : 0) | (a.mu ? 16 : 0) |
-                (a.lv ? 32 : 0) | (a.d1 ? 64 : 0) | (a.d2 ? 128 : 0);
+                (a.lv ? 32 : 0) | (a.d1 ? 64 : 0) | (a.d2 ? 128 : 0) | (planes_fresh && planes_keep ? 256 : 0);
     if (graphs.size() >= kMaxGraphs && !graphs.count(key)) return exec(a, main);  // e.g. a beta schedule: stay eager
     GraphEntry& e = graphs[key];
     if (e.seen <= 0) {
@@ -1281,6 +1287,8 @@ struct hippie_engine {
       e.launches = launches;
     }
     cudaGraphLaunch(e.exec, main);
+    // a graph captured from stale planes contains the conversion (later parts of a split step contain none)
+    if (use_tc && (a.mode <= 4 || a.mode == 8)) planes_fresh = true;
     IoCopy out{};
     add(out, ws + st_scal, a.scalars, a.mode == 3 ? 0 : 4);
     add(out, ws + st_enc, a.enc, (int64_t)a.B * z), add(out, ws + st_mu, a.mu, (int64_t)a.B * z);
@@ -1300,7 +1308,7 @@ struct hippie_engine {
 // ------------------------------------------------------------------------------------------------
 extern "C" {
 
-int hippie_abi_version(void) { return 2; }
+int hippie_abi_version(void) { return 3; }
 
 int hippie_create(const hippie_cfg* cfg, hippie_handle* out) {
   if (!cfg || !out) return -1;
@@ -1390,6 +1398,8 @@ int hippie_bind(hippie_handle h, float* params, float* grads, float* exp_avg, fl
   h->P = params, h->G = grads, h->M1 = exp_avg, h->M2 = exp_avg_sq;
   h->bn_mean = bn_mean, h->bn_var = bn_var, h->bn_count = bn_count, h->ws = (float*)workspace;
   h->clear_graphs();
+  h->planes_fresh = false;
+  if (const char* g = getenv("HIPPIE_B200_KEEP_PLANES")) h->planes_keep = atoi(g) != 0;
   if (const char* g = getenv("HIPPIE_B200_GRAPHS")) h->use_graphs = atoi(g) != 0;
   if (const char* g = getenv("HIPPIE_B200_TMA_STORE")) h->tma_epilogue = atoi(g) != 0;
   if (!h->side) {
@@ -1550,9 +1560,18 @@ int hippie_clip_adamw(hippie_handle h, double lr, double beta1, double beta2, do
   a.lr = lr, a.beta1 = beta1, a.beta2 = beta2, a.eps = eps, a.wd = weight_decay, a.max_norm = max_norm;
   a.grad_scale = grad_scale, a.step = step, a.step_cls = step_cls, a.has_cls_grad = has_cls_grad;
   a.partials = h->ws + h->adam_part, a.scalars = scalars_out;
+  if (h->use_tc && h->planes_fresh && h->planes_keep) {  // keep the weight pair planes current (stale planes are converted in full by the next forward)
+    a.wp_hi = h->WP(), a.wp_lo = h->WP() + h->param_floats, a.wp_scale = kWeightPairScale, a.flags = h->flags();
+  }
   launch_clip_adamw(a, (cudaStream_t)stream);
   h->launches = kClipAdamLaunches;
   return h->check("hippie_clip_adamw");
+}
+
+int hippie_params_changed(hippie_handle h) {
+  if (!h) return -1;
+  h->planes_fresh = false;
+  return 0;
 }
 
 int hippie_preprocess_batch(const double* wave_raw, int32_t wave_width, const double* isi_raw, int32_t isi_width,

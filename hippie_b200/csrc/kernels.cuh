@@ -323,6 +323,12 @@ struct AdamArgs {
   int step, step_cls, has_cls_grad;
   float* partials;  // >= 1024 floats
   float* scalars;   // [4] = grad norm, [5] = clip coefficient
+  // optional: fp16 pair planes of the parameter buffer (tensor-core GEMM operands), rewritten for every updated element
+  // while it is in a register (the separate 64 MB-read / 64 MB-write refresh pass of the next step goes away)
+  uint16_t* wp_hi;
+  uint16_t* wp_lo;
+  float wp_scale;
+  unsigned* flags;  // receives kFlagWeightSaturated when an updated weight leaves the range of the hi plane
 };
 void launch_clip_adamw(const AdamArgs& a, cudaStream_t s);
 constexpr int kClipAdamLaunches = 3;

@@ -5,6 +5,12 @@
 #include "pair_fmt.cuh"
 #include "pdl.cuh"
 
+// Launch bounds of the BatchNorm kernels (256 threads).  Capping them at 112 registers (__maxnreg__) so that one of their
+// CTAs fits next to two GEMM CTAs of 96 registers was measured slower (bs512 step 3.00 vs 2.98 ms, gpurun_out/r02_exp33.txt).
+#ifndef HP_BN_BOUNDS
+#define HP_BN_BOUNDS __launch_bounds__(256)
+#endif
+
 namespace hp {
 
 namespace {
@@ -234,7 +240,7 @@ __global__ void bn_eval_coefs_kernel(const BnEvalEntry* __restrict__ tab, const 
 // out = lrelu((c - mean)*scale + beta + residual)   reference hippie/backbones.py:37-40,66-69,95
 // grid = (C / 32, row chunks); thread = (channel quad of the slab, row lane)
 template <int RES>  // 0 none, 1 identity, 2 BatchNorm'd shortcut
-__global__ void __launch_bounds__(256) bn_apply_kernel(BnApply a) {
+__global__ void HP_BN_BOUNDS bn_apply_kernel(BnApply a) {
   __shared__ float s_sc[kSlab], s_sh[kSlab], s_mu[kSlab], r_sc[kSlab], r_sh[kSlab], r_mu[kSlab];
   __shared__ ChanAcc s_acc[8][kSlab];
   pdl_trigger();
@@ -353,7 +359,7 @@ __device__ __forceinline__ float block_max(float v, float* red) {  // 256 thread
 // part[chunk][C][3] = (S1, S2, S2s);  slot = (max|g_pre|, max|xhat|, max|gamma*invstd|, 1/scale) as atomicMax targets
 // (non-negative floats order like their bit patterns; the slots are zeroed once per step by the engine)
 template <int U>
-__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(BnBwd a, int rows_per_cta) {
+__global__ void HP_BN_BOUNDS bn_bwd_reduce_kernel(BnBwd a, int rows_per_cta) {
   __shared__ float4 red[3][256];
   __shared__ float mred[8];
   pdl_trigger();
@@ -471,7 +477,7 @@ __device__ __forceinline__ float dc_scale(const float* slot) {
 }
 
 // grid = (C / 32, row chunks); thread = (channel quad of the slab, row lane)
-__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(BnBwd a, int nchunks) {
+__global__ void HP_BN_BOUNDS bn_bwd_apply_kernel(BnBwd a, int nchunks) {
   __shared__ double s_sum[8][kSlab][3];
   __shared__ float s_m1[kSlab], s_m2[kSlab], s_m3[kSlab];
   pdl_trigger();
@@ -1013,6 +1019,10 @@ __global__ void __launch_bounds__(256) adamw_kernel(AdamArgs a, AdamCoefs k) {
       adamw_one(g.w, p.w, m.w, v.w, coef, a.grad_scale, k.decay, k.omb1, k.omb2, k.beta2, ss, bs, k.eps);
       *reinterpret_cast<float4*>(a.p + i0) = p, *reinterpret_cast<float4*>(a.m + i0) = m;
       *reinterpret_cast<float4*>(a.v + i0) = v;
+      if (a.wp_hi)
+        store_pair4(a.wp_hi, a.wp_lo - a.wp_hi, i0,
+                    make_float4(p.x * a.wp_scale, p.y * a.wp_scale, p.z * a.wp_scale, p.w * a.wp_scale), a.flags,
+                    kFlagWeightSaturated);
     } else {
       for (int e = 0; e < cnt; ++e) {
         const int64_t i = i0 + e;
@@ -1022,6 +1032,11 @@ __global__ void __launch_bounds__(256) adamw_kernel(AdamArgs a, AdamCoefs k) {
         adamw_one(a.g[i], p, m, v, coef, a.grad_scale, k.decay, k.omb1, k.omb2, k.beta2, in ? k.step_size_cls : k.step_size,
                   in ? k.bc2_sqrt_cls : k.bc2_sqrt, k.eps);
         a.p[i] = p, a.m[i] = m, a.v[i] = v;
+        if (a.wp_hi) {
+          const float x = p * a.wp_scale;
+          pair_split<kPairF16>(x, a.wp_hi[i], a.wp_lo[i]);
+          if (a.flags && !(fabsf(x) < kPairF16Max)) atomicOr(a.flags, kFlagWeightSaturated);
+        }
       }
     }
   }

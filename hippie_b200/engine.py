@@ -95,6 +95,7 @@ class Engine:
                 self.tensors.append(TensorInfo(name.value.decode(), off.value, tl.value, tc.value, tp.value))
         self.device: Optional[torch.device] = None
         self.flat_params = self.flat_grads = self.exp_avg = self.exp_avg_sq = None
+        self._pver = -1  # version counter of flat_params the engine's weight planes correspond to
         self.bn_mean = self.bn_var = self.bn_count = self.workspace = None
 
     # ------------------------------------------------------------------------------------------
@@ -189,7 +190,21 @@ class Engine:
         return t[:, ti.pad:ti.pad + ti.L, :].permute(0, 2, 1)
 
     # ---- calls ---------------------------------------------------------------------------------
+    def params_changed(self):
+        """Tells the engine that `flat_params` was written by something other than `clip_adamw` (hippie_params_changed):
+        the tensor-core path converts the whole buffer into its fp16 pair planes again at the next call.  In-place torch
+        operations on `flat_params` or on any view of it (nn.Parameter.copy_, load_state_dict, init functions, a
+        broadcast) are detected through the tensor's version counter; writes that bypass it (`param.data.<op>_()`, raw
+        pointers) need this call."""
+        self._check(self._L.hippie_params_changed(self._h))
+        self._pver = self.flat_params._version
+
+    def _sync_params(self):
+        if self.flat_params._version != self._pver:
+            self.params_changed()
+
     def _io(self, x1, x2, src, cls, eps, B):
+        self._sync_params()
         assert x1.dtype == torch.float32 and x1.is_contiguous() and x1.is_cuda
         assert src.dtype == torch.int64 and src.is_contiguous()
         if self.multimodal:
@@ -283,6 +298,7 @@ class Engine:
     # ---- module-level forward calls (hippie/backbones.py forward(), MultiModalCVAE.encode / .decode) -------------
     def encoder_forward(self, x, which: int = 0, train: bool = False):
         B = x.shape[0]
+        self._sync_params()
         assert x.dtype == torch.float32 and x.is_contiguous() and x.is_cuda
         out = torch.empty(B, 2 * self.z_dim, dtype=torch.float32, device=self.device)
         self._check(self._L.hippie_encoder_forward(self._h, which, _ptr(x), B, 1 if train else 0, _ptr(out), self._stream()))
@@ -290,6 +306,7 @@ class Engine:
 
     def decoder_forward(self, d, which: int = 0, train: bool = False):
         B = d.shape[0]
+        self._sync_params()
         assert d.dtype == torch.float32 and d.is_contiguous() and d.is_cuda and d.numel() == B * 2 * self.z_dim
         L = self.len_isi if (self.multimodal and which == 1) else self.len_wave
         out = torch.empty(B, 1, L, dtype=torch.float32, device=self.device)
@@ -298,6 +315,7 @@ class Engine:
 
     def encode(self, x1, x2, source_emb, class_emb, train: bool = False):
         B = x1.shape[0]
+        self._sync_params()
         for t in (x1, x2, source_emb, class_emb):
             assert t is None or (t.dtype == torch.float32 and t.is_contiguous() and t.is_cuda)
         assert source_emb.shape == class_emb.shape == (B, self.class_hidden_dim)
@@ -308,6 +326,7 @@ class Engine:
 
     def decode(self, z, source_emb, class_emb, train: bool = False):
         B = z.shape[0]
+        self._sync_params()
         for t in (z, source_emb, class_emb):
             assert t.dtype == torch.float32 and t.is_contiguous() and t.is_cuda
         assert z.shape == (B, self.z_dim) and source_emb.shape == class_emb.shape == (B, self.class_hidden_dim)

@@ -159,6 +159,16 @@ int hippie_clip_adamw(hippie_handle h, double lr, double beta1, double beta2, do
                       float max_norm, float grad_scale, int32_t step, int32_t step_cls, int32_t has_cls_grad,
                       float* scalars_out, void* stream);
 
+/* The tensor-core path keeps a derived copy of the parameter buffer (fp16 pair planes of every weight) in the
+ * workspace.  It is written in full by the first forward-type call after hippie_bind and kept current by
+ * hippie_clip_adamw (each updated weight is re-split while it is in a register), so that the steady-state step and the
+ * chunks of an embedding pass do not re-convert 64 MB of unchanged parameters per call.  The caller owns the
+ * parameter buffer: after writing into it by any other means (the counterpart of load_state_dict, in-place
+ * initialisation, a parameter broadcast -- hippie/model.py has no such call on the hot path) call
+ * hippie_params_changed; the next forward-type call converts the whole buffer again.  hippie_b200/engine.py does this
+ * from the version counter of the flat parameter tensor. */
+int hippie_params_changed(hippie_handle h);
+
 /* Replaces module.eval(); module(batch) (hippie/model.py:510-520): full forward with running
  * statistics.  Outputs as above (any may be NULL); scalars_out (may be NULL) gets the validation
  * loss terms of validation_step (hippie/model.py:484-508). */

@@ -206,3 +206,59 @@ def test_free_running_epoch_inside_reference_envelope(golden_dir):
     tail_ref, tail_got = ref[-20:].mean(), got[-20:, 0].mean()
     assert abs(tail_got - tail_ref) <= 5e-3 * tail_ref, (tail_got, tail_ref)
     assert got[-1, 0] < 0.2 * got[0, 0]                        # it trains
+
+
+def test_weight_planes_kept_by_adamw_equal_a_fresh_conversion():
+    """hippie_clip_adamw keeps the fp16 pair planes of the parameter buffer current (the per-step 64 MB conversion pass is
+    gone).  After some steps (eager, then graph replays) a deterministic forward pass over the kept planes must equal,
+    bit for bit, the same pass after hippie_params_changed has forced a conversion of the whole buffer."""
+    cfg = O.CVAEConfig(z_dim=10, num_classes=4)
+    st = U.perturbed_state(cfg)
+    x1, x2, labels, eps = U.case_inputs(cfg, 48, True)
+    eng = U.make_engine(cfg, 48)
+    eng.load_named(st)
+    dev = eng.device
+    lab = labels.to(dev)
+    io = (x1.to(dev), x2.to(dev), lab[:, 1].contiguous())
+    for labelled in (False, True):  # label-free steps skip class_embedding in AdamW: its planes must stay valid too
+        cls = lab[:, 0].contiguous() if labelled else None
+        for i in range(6):
+            s, _ = eng.train_fwd_bwd(io[0], io[1], io[2], cls, eps.to(dev), 0.5)
+            eng.clip_adamw(1e-3, 0.01, i + 1, max_norm=1.0, scalars=s, step_cls=i + 1 if labelled else 0,
+                           has_cls_grad=labelled)
+        kept = eng.eval_forward(io[0], io[1], io[2], lab[:, 0].contiguous(), eps.to(dev))
+        kept = {k: v.clone() for k, v in kept.items()}
+        eng.params_changed()
+        fresh = eng.eval_forward(io[0], io[1], io[2], lab[:, 0].contiguous(), eps.to(dev))
+        for k in kept:
+            assert torch.equal(kept[k], fresh[k]), (k, labelled)
+    assert eng.device_flags(clear=True) == 0
+
+
+def test_parameter_writes_behind_the_engine_are_seen():
+    """In-place torch writes to the parameter buffer (load_state_dict, init functions, a broadcast) bump its version
+    counter and the engine converts the planes again; writes through `.data` bypass the counter and need
+    Engine.params_changed() -- the documented contract of hippie_params_changed."""
+    cfg = O.CVAEConfig(z_dim=10)
+    st = U.perturbed_state(cfg)
+    x1, x2, labels, eps = U.case_inputs(cfg, 16, False)
+    eng = U.make_engine(cfg, 16)
+    eng.load_named(st)
+    dev = eng.device
+    io = (x1.to(dev), x2.to(dev), labels.to(dev), None)
+    ref0 = eng.embed(*io)["mu"].clone()
+    assert torch.equal(eng.embed(*io)["mu"], ref0)  # planes reused
+    w = eng.named_state()["encoder_mod1.layer4.1.conv2.weight"]
+    with torch.no_grad():
+        w.mul_(1.5)  # version counter moves: detected
+    ref1 = eng.embed(*io)["mu"].clone()
+    assert not torch.equal(ref1, ref0)
+    fresh = U.make_engine(cfg, 16)
+    fresh.flat_params.copy_(eng.flat_params)
+    fresh.bn_mean.copy_(eng.bn_mean), fresh.bn_var.copy_(eng.bn_var)
+    assert torch.equal(fresh.embed(*io)["mu"], ref1)
+    w.data.mul_(1.0 / 1.5)  # bypasses the counter: stale planes until reported
+    assert torch.equal(eng.embed(*io)["mu"], ref1)
+    eng.params_changed()
+    fresh.flat_params.copy_(eng.flat_params)
+    assert torch.equal(eng.embed(*io)["mu"], fresh.embed(*io)["mu"])
