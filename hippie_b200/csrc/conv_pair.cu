@@ -87,6 +87,7 @@ struct PairConv {
   uint32_t idesc2;  // N = 2 * BN   (A hi x [B hi | B lo])
   int nmma;         // 3: all three products; 2: experiment, A lo x B hi dropped (A at 11 bits)
   int fused;        // 1: A hi x [B hi | B lo] as one N = 2 BN instruction; 0: two N = BN instructions
+  int fake_reuse, fake_k;
   int b_mn;        // 1: B tiles are MN-major boxes of the forward weight planes [co][t][ci]
   int kb_per_tap;  // b_mn: k-blocks per tap (= Cout / 64)
   int taps;        // b_mn: kernel size (3 or 1); tap of k-block kb = taps - 1 - kb / kb_per_tap
@@ -156,7 +157,7 @@ __global__ void __launch_bounds__(TC_THREADS, reg_ctas_per_sm(BN, STAGES))
   if (threadIdx.x == 0) stamp(p, 0);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b0 = blockIdx.x * p.nb, n0 = blockIdx.y * BN;
-  const int nkb = p.K / PK;
+  const int nkb = p.fake_k ? min(p.fake_k, p.K / PK) : p.K / PK;  // fake_k: SPEED EXPERIMENT ONLY (main loops cut short)
   const int rows_tile = p.nb * p.Lout;
 
   if (warp == 0 && lane == 0) {
@@ -195,6 +196,10 @@ __global__ void __launch_bounds__(TC_THREADS, reg_ctas_per_sm(BN, STAGES))
       const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
       mbar_wait(&empty[s], ph ^ 1u);
       uint8_t* st = ring + s * S::STAGE_BYTES;
+      if (p.fake_reuse && pid < 2 && kb >= STAGES && kb % 3 != 0) {  // SPEED EXPERIMENT ONLY (wrong results): A fetched for one k-block in three
+        mbar_arrive(&full[s]);
+        continue;
+      }
       mbar_expect_tx(&full[s], tx_bytes);
       if (pid < 2) {
         tma_load_4d(st + pid * S::A_LO, &mapA, &full[s], kb * PK, 0, b0, pid);
@@ -439,7 +444,7 @@ struct PairWgrad {
   float out_scale;
   const float* dyn_scale;
   uint32_t idesc, idesc2;  // N = BN, N = 2 * BN (see PairConv)
-  int nmma, fused;
+  int nmma, fused, fake_k;
   int pdl_late;
 };
 
@@ -461,7 +466,8 @@ __global__ void __launch_bounds__(TC_THREADS, reg_ctas_per_sm(BN, STAGES))
   const int n0 = blockIdx.x * BN, m0 = blockIdx.y * TC_BM;
   const int r_begin = blockIdx.z * p.rows_per_split;
   const int r_end = min(p.R, r_begin + p.rows_per_split);
-  const int nkb = (r_end - r_begin + PK - 1) / PK;  // >= 1 by construction of the grid
+  const int nkb_all = (r_end - r_begin + PK - 1) / PK;  // >= 1 by construction of the grid
+  const int nkb = p.fake_k ? min(p.fake_k, nkb_all) : nkb_all;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&mapDY);
@@ -657,6 +663,7 @@ static void set_smem_attrs() {
 }
 static int g_variant = 0, g_wgrad_variant = 1, g_pdl_late = 0;
 static int g_mma_scheme = 7;  // HIPPIE_B200_MMA_SCHEME bits: 1 forward, 2 dgrad, 4 wgrad issue A hi x [B hi | B lo] as one instruction
+static int g_fake_k = 0;
 static int g_bwd_nmma = 3;  // HIPPIE_B200_BWD_MMA=2: accuracy experiment, dgrad / wgrad without the (gradient lo) x (hi) product
 static int g_wgrad_min_kb = 16;  // k-blocks (of 64 reduction rows) a weight-gradient CTA processes at least: the kernels are off
 // the critical path, so few long-lived CTAs (less prologue / fill / epilogue time per MAC) beat many short ones -- the step is
@@ -680,6 +687,7 @@ bool pair_init(std::string* err) {
   if (const char* v = getenv("HIPPIE_B200_PAIR_VARIANT")) g_variant = atoi(v);  // 0 auto, 1 always shared, 2 always alone
   if (const char* v = getenv("HIPPIE_B200_PDL_LATE")) g_pdl_late = atoi(v);
   if (const char* v = getenv("HIPPIE_B200_MMA_SCHEME")) g_mma_scheme = atoi(v);
+  if (const char* v = getenv("HIPPIE_B200_FAKE_K")) g_fake_k = atoi(v);
   if (const char* v = getenv("HIPPIE_B200_BWD_MMA")) g_bwd_nmma = atoi(v) == 2 ? 2 : 3;
   if (const char* v = getenv("HIPPIE_B200_WGRAD_VARIANT")) g_wgrad_variant = atoi(v);  // 1 shared (two CTAs per SM), 2 alone
   if (const char* v = getenv("HIPPIE_B200_WGRAD_MIN_KB")) g_wgrad_min_kb = atoi(v) > 0 ? atoi(v) : 16;
@@ -777,6 +785,8 @@ int launch_conv_pair(const ConvGemm& g, const TcMap& mapA, const TcMap& mapB, in
   p.idesc2 = umma_idesc_16(2 * bn, o.a_fmt, o.b_fmt, 0, o.b_mn ? 1 : 0);
   p.nmma = o.b_mn ? g_bwd_nmma : 3;
   p.fused = (g_mma_scheme >> (o.b_mn ? 1 : 0)) & 1;
+  p.fake_reuse = (getenv("HIPPIE_B200_FAKE_REUSE") && o.taps == 3) ? 1 : 0;
+  p.fake_k = g_fake_k;
   p.b_mn = o.b_mn, p.taps = o.taps, p.kb_per_tap = o.taps > 0 ? (g.K / o.taps) / PK : 1;
   p.dyn_scale = o.dyn_scale, p.stamps = o.stamps, p.stamps_all = o.stamps_all, p.pdl_late = g_pdl_late & 1;
   if (o.fold) p.fold = *o.fold;
@@ -804,6 +814,7 @@ void launch_wgrad_pair(const WgradGemm& g, const TcMap& mapDY, const TcMap& mapX
   p.idesc2 = umma_idesc_16(2 * bn, o.a_fmt, o.b_fmt, 1, 1);
   p.nmma = g_bwd_nmma;
   p.fused = (g_mma_scheme >> 2) & 1;
+  p.fake_k = g_fake_k;
   const int tiles = ((g.M + TC_BM - 1) / TC_BM) * (g.N / bn);
   const bool alone = g_wgrad_variant == 2;
   int splits = ((alone ? 1 : 2) * sm_count) / tiles;  // one or two CTAs per SM

@@ -100,6 +100,7 @@ struct Branch {
   float* part = nullptr;   // BatchNorm statistics / stem / tail partials
   float* bpart = nullptr;  // BatchNorm backward partials
   cudaStream_t wst = nullptr;  // weight gradients are off the critical path: they run here, behind an event
+  cudaStream_t hst = nullptr;  // helper stream of the branch: the shortcut convolution of a down / up block runs beside the main path
 };
 
 }  // namespace
@@ -137,6 +138,11 @@ struct hippie_engine {
   bool bound = false;
   cudaStream_t side = nullptr;
   cudaStream_t wside[2] = {nullptr, nullptr};
+  cudaStream_t hside[2] = {nullptr, nullptr};  // Branch::hst
+  // Batch sizes up to this run the shortcut convolutions on the helper streams.  Every fork / join costs the kernels behind
+  // it their programmatic launch edge, so it pays where kernels are short and the SMs are far from full (bs64 step
+  // 1.476 -> 1.453 ms, bs64 embedding pass 0.284 -> 0.267 ms) and loses at bs512 (3.015 -> 3.06 ms); HIPPIE_B200_SHORTCUT_STREAM
+  int helper_max_batch = 128;
   std::vector<cudaEvent_t> ev_pool;
   size_t ev_next = 0;
   cudaEvent_t next_event() { return ev_pool[ev_next++ % ev_pool.size()]; }
@@ -730,6 +736,25 @@ struct hippie_engine {
     prof_end(pe, 1, 2.0 * g.M * g.N * g.K / (cv.stride == 2 ? 2.0 : 1.0), br);
     ++launches;
   }
+  // The shortcut convolution of a down-sampling / up-sampling block (forward: 1x1 or resize conv of the block input;
+  // backward: its dgrad) depends only on the block's input (forward) or on the block's first BatchNorm backward, so it
+  // runs on the branch's helper stream beside conv -> BatchNorm -> conv of the main path and rejoins before the
+  // kernel that needs it: six fewer GEMMs per branch on each of the forward and backward critical chains.
+  Branch fork_helper(Branch& br) {
+    Branch hb = br;
+    if (!br.hst) return hb;
+    hb.st = br.hst;
+    cudaEvent_t e = next_event();
+    cudaEventRecord(e, br.st);
+    cudaStreamWaitEvent(br.hst, e, 0);
+    return hb;
+  }
+  void join_helper(Branch& br) {
+    if (!br.hst) return;
+    cudaEvent_t e = next_event();
+    cudaEventRecord(e, br.hst);
+    cudaStreamWaitEvent(br.st, e, 0);
+  }
   // the weight-gradient stream of the branch waits for everything issued on the branch stream so far
   void side_wait(Branch& br) {
     if (!br.wst || br.wst == br.st) return;
@@ -800,16 +825,24 @@ struct hippie_engine {
     for (int i = 0; i < 8; ++i) {
       EncBlock& b = E.blk[i];
       if (fold_eval(train)) {
+        if (b.down) {  // shortcut: BatchNorm, no LeakyReLU
+          Branch hb = fork_helper(br);
+          conv_fwd_folded(b.cs, b.x, b.bns, -1, b.cso, -1, 1.f, true, B, hb);
+        }
         conv_fwd_folded(b.c1, b.x, b.bn1, -1, b.a1, -1, kSlopeBackbone, false, B, br);  // a1: planes only
-        if (b.down) conv_fwd_folded(b.cs, b.x, b.bns, -1, b.cso, -1, 1.f, true, B, br);  // shortcut: BatchNorm, no LeakyReLU
+        if (b.down) join_helper(br);
         conv_fwd_folded(b.c2, b.a1, b.bn2, b.down ? b.cso : b.x, b.out, -1, kSlopeBackbone, true, B, br);
         continue;
+      }
+      if (b.down) {
+        Branch hb = fork_helper(br);
+        conv_fwd(b.cs, b.x, b.cso, b.bns, B, train, hb);
       }
       conv_fwd(b.c1, b.x, b.c1o, b.bn1, B, train, br);
       apply(b.c1o, b.bn1, -1, -1, b.a1, -1, B, train, br);
       conv_fwd(b.c2, b.a1, b.c2o, b.bn2, B, train, br);
       if (b.down) {
-        conv_fwd(b.cs, b.x, b.cso, b.bns, B, train, br);
+        join_helper(br);
         apply(b.c2o, b.bn2, b.cso, b.bns, b.out, -1, B, train, br);
       } else {
         apply(b.c2o, b.bn2, b.x, -1, b.out, -1, B, train, br);
@@ -839,13 +872,15 @@ struct hippie_engine {
       EncBlock& b = E.blk[i];
       const int gx = gact.at(b.x), gout = gact.at(b.out);
       bn_bwd(gout, false, b.out, b.c2o, b.bn2, b.down ? b.cso : -1, b.bns, b.dc2, 1, b.dcs, 2, b.down ? -1 : gx, B, br);
+      if (b.down) {  // the shortcut's dgrad (first writer of gx) beside dgrad(conv2) -> BatchNorm backward
+        Branch hb = fork_helper(br);
+        dgrad(b.cs, b.dcs, gx, false, B, hb);
+        wgrad(b.cs, b.dcs, b.x, B, br);
+      }
       dgrad(b.c2, b.dc2, b.g_a1, false, B, br);
       wgrad(b.c2, b.dc2, b.a1, B, br);
       bn_bwd(b.g_a1, false, b.a1, b.c1o, b.bn1, -1, -1, b.dc1, b.down ? 2 : 1, -1, 1, -1, B, br);
-      if (b.down) {
-        dgrad(b.cs, b.dcs, gx, false, B, br);
-        wgrad(b.cs, b.dcs, b.x, B, br);
-      }
+      if (b.down) join_helper(br);
       dgrad(b.c1, b.dc1, gx, true, B, br);
       wgrad(b.c1, b.dc1, b.x, B, br);
       if (export_ev && i == 4) {  // the deep half of this encoder's gradients is final behind these two points
@@ -874,20 +909,28 @@ struct hippie_engine {
     for (int i = 0; i < 8; ++i) {
       DecBlock& b = D.blk[i];
       if (fold_eval(train)) {
+        if (b.up) {
+          Branch hb = fork_helper(br);
+          conv_fwd_folded(b.cs, b.x_up, b.bns, -1, b.cso, -1, 1.f, true, B, hb);
+        }
         conv_fwd_folded(b.c2, b.x, b.bn2, -1, b.a2, b.a2_up, kSlopeBackbone, false, B, br);  // a2 / a2_up: planes only
         if (b.up) {
-          conv_fwd_folded(b.cs, b.x_up, b.bns, -1, b.cso, -1, 1.f, true, B, br);
+          join_helper(br);
           conv_fwd_folded(b.c1, b.a2_up, b.bn1, b.cso, b.out, b.out_up, kSlopeBackbone, true, B, br);
         } else {
           conv_fwd_folded(b.c1, b.a2, b.bn1, b.x, b.out, b.out_up, kSlopeBackbone, true, B, br);
         }
         continue;
       }
+      if (b.up) {
+        Branch hb = fork_helper(br);
+        conv_fwd(b.cs, b.x_up, b.cso, b.bns, B, train, hb);
+      }
       conv_fwd(b.c2, b.x, b.c2o, b.bn2, B, train, br);
       apply(b.c2o, b.bn2, -1, -1, b.a2, b.a2_up, B, train, br);
       if (b.up) {
         conv_fwd(b.c1, b.a2_up, b.c1o, b.bn1, B, train, br);
-        conv_fwd(b.cs, b.x_up, b.cso, b.bns, B, train, br);
+        join_helper(br);
         apply(b.c1o, b.bn1, b.cso, b.bns, b.out, b.out_up, B, train, br);
       } else {
         conv_fwd(b.c1, b.a2, b.c1o, b.bn1, B, train, br);
@@ -923,13 +966,17 @@ struct hippie_engine {
       const int gx = gact.at(b.x), gout = gact.at(b.out);
       if (b.up) {
         bn_bwd(gout, false, b.out, b.c1o, b.bn1, b.cso, b.bns, b.dc1, 1, b.dcs, 1, -1, B, br);
+        {  // the shortcut's dgrad beside dgrad(conv1) -> BatchNorm backward -> dgrad(conv2)
+          Branch hb = fork_helper(br);
+          dgrad(b.cs, b.dcs, b.g_x_up, false, B, hb);
+          wgrad(b.cs, b.dcs, b.x_up, B, br);
+        }
         dgrad(b.c1, b.dc1, b.g_a2_up, false, B, br);
         wgrad(b.c1, b.dc1, b.a2_up, B, br);
-        dgrad(b.cs, b.dcs, b.g_x_up, false, B, br);
-        wgrad(b.cs, b.dcs, b.x_up, B, br);
         bn_bwd(b.g_a2_up, true, b.a2, b.c2o, b.bn2, -1, -1, b.dc2, 1, -1, 1, -1, B, br);
         dgrad(b.c2, b.dc2, gx, false, B, br);
         wgrad(b.c2, b.dc2, b.x, B, br);
+        join_helper(br);
         cudaEvent_t pe14 = prof_begin(br);
         launch_pairsum_acc(A(b.g_x_up), A(gx), B, acts[b.x].L, acts[b.x].C, br.st);
         prof_end(pe14, 14, 0.0, br);
@@ -1022,6 +1069,7 @@ struct hippie_engine {
     launches = 0;
     Branch b0{main, ws + part_off[0], ws + bpart_off[0]}, b1{profiling ? main : side, ws + part_off[1], ws + bpart_off[1]};
     if (backward && !profiling) b0.wst = wside[0], b1.wst = wside[1];
+    if (B <= helper_max_batch && !profiling) b0.hst = hside[0], b1.hst = hside[1];
     const float* xin[2] = {x1, x2};
     export_ev = part == 4 && !profiling;  // whole step, slice events exported
     if (part == 4) part = -1;
@@ -1041,6 +1089,8 @@ struct hippie_engine {
     cudaMemsetAsync(ws + scal_off, 0, 64 * sizeof(float), main);
     if (train) cudaMemsetAsync(ws + tot_off, 0, tot_floats * sizeof(float), main);
     if (backward) {
+      // (zeroing the 64 MB gradient buffer on a weight-gradient stream under the forward pass was measured slower: the
+      // event wait it needs in front of the first gradient writer costs that kernel its programmatic launch edge)
       cudaMemsetAsync(G, 0, param_floats * sizeof(float), main);
       if (use_tc) cudaMemsetAsync(ws + slots_off, 0, 4 * kMaxSlots * sizeof(float), main);
     }
@@ -1137,6 +1187,7 @@ struct hippie_engine {
                 float* out_enc, float* out_mu, float* out_logvar, cudaStream_t main) {
     launches = 0;
     Branch b0{main, ws + part_off[0], ws + bpart_off[0]}, b1{side, ws + part_off[1], ws + bpart_off[1]};
+    if (B <= helper_max_batch) b0.hst = hside[0], b1.hst = hside[1];
     launch_bn_eval_coefs(reinterpret_cast<const BnEvalEntry*>(ws + bn_table_off), (int)bn_table.size(), P, bn_mean, bn_var,
                          ws, main);
     ++launches;
@@ -1333,8 +1384,10 @@ void hippie_destroy(hippie_handle h) {
   for (int i = 0; i < 2; ++i)
     if (h->ev_slice[i]) cudaEventDestroy(h->ev_slice[i]);
   for (auto e : h->ev_pool) cudaEventDestroy(e);
-  for (int i = 0; i < 2; ++i)
+  for (int i = 0; i < 2; ++i) {
     if (h->wside[i]) cudaStreamDestroy(h->wside[i]);
+    if (h->hside[i]) cudaStreamDestroy(h->hside[i]);
+  }
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   if (h->ev_join) cudaEventDestroy(h->ev_join);
   delete h;
@@ -1400,6 +1453,7 @@ int hippie_bind(hippie_handle h, float* params, float* grads, float* exp_avg, fl
   h->clear_graphs();
   h->planes_fresh = false;
   if (const char* g = getenv("HIPPIE_B200_KEEP_PLANES")) h->planes_keep = atoi(g) != 0;
+  if (const char* g = getenv("HIPPIE_B200_SHORTCUT_STREAM")) h->helper_max_batch = atoi(g);
   if (const char* g = getenv("HIPPIE_B200_GRAPHS")) h->use_graphs = atoi(g) != 0;
   if (const char* g = getenv("HIPPIE_B200_TMA_STORE")) h->tma_epilogue = atoi(g) != 0;
   if (!h->side) {
@@ -1410,6 +1464,7 @@ int hippie_bind(hippie_handle h, float* params, float* grads, float* exp_avg, fl
     cudaStreamCreateWithPriority(&h->cap, cudaStreamNonBlocking, prio_hi);
     cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
     for (int i = 0; i < 2; ++i) cudaStreamCreateWithPriority(&h->wside[i], cudaStreamNonBlocking, prio_lo);
+    for (int i = 0; i < 2; ++i) cudaStreamCreateWithPriority(&h->hside[i], cudaStreamNonBlocking, prio_hi);
     cudaStreamCreateWithPriority(&h->xs, cudaStreamNonBlocking, prio_hi);
     for (int i = 0; i < 2; ++i) cudaEventCreateWithFlags(&h->ev_slice[i], cudaEventDisableTiming);
     h->ev_pool.resize(512);
