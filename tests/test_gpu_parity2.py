@@ -262,3 +262,38 @@ def test_parameter_writes_behind_the_engine_are_seen():
     eng.params_changed()
     fresh.flat_params.copy_(eng.flat_params)
     assert torch.equal(eng.embed(*io)["mu"], fresh.embed(*io)["mu"])
+
+
+def test_shortcut_helper_stream_gives_the_serial_results(monkeypatch):
+    """Batches <= 128 run the shortcut convolution of every down / up block (and its dgrad) on a helper stream beside the
+    main path.  Against the same engine with the shortcuts kept on the chain (HIPPIE_B200_SHORTCUT_STREAM=0):
+    training-mode and eval-mode forward outputs bit for bit (eager and graph replay), gradients to accumulation-order
+    noise of the split-K weight gradients."""
+    cfg = O.CVAEConfig(z_dim=10, num_classes=4)
+    st = U.perturbed_state(cfg)
+    x1, x2, labels, eps = U.case_inputs(cfg, 48, True)
+    res = []
+    for limit in ("0", "128"):
+        monkeypatch.setenv("HIPPIE_B200_SHORTCUT_STREAM", limit)
+        eng = U.make_engine(cfg, 48)
+        eng.load_named(st)
+        dev = eng.device
+        lab = labels.to(dev)
+        a = (x1.to(dev), x2.to(dev), lab[:, 1].contiguous(), lab[:, 0].contiguous(), eps.to(dev))
+        outs = []
+        for _ in range(3):  # eager, eager, replay
+            ev = eng.eval_forward(*a)
+            tr = eng.train_forward(*a)
+            s, o = eng.train_fwd_bwd(*a, 0.5, outputs=True)
+            outs.append(({k: v.clone() for k, v in ev.items()}, {k: v.clone() for k, v in tr.items()}, s.clone(),
+                         {k: v.clone() for k, v in o.items()}, eng.flat_grads.clone()))
+        res.append(outs)
+        assert eng.device_flags(clear=True) == 0
+    for serial, helper in zip(res[0], res[1]):
+        for k in serial[0]:
+            assert torch.equal(serial[0][k], helper[0][k]), ("eval", k)
+            assert torch.equal(serial[1][k], helper[1][k]), ("train", k)
+        assert torch.equal(serial[2][:4], helper[2][:4])
+        for k in serial[3]:
+            assert torch.equal(serial[3][k], helper[3][k]), ("step", k)
+        assert U.rel_l2(helper[4], serial[4]) < 1e-5
