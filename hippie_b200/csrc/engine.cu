@@ -175,6 +175,7 @@ struct hippie_engine {
   };
   std::map<GraphKey, GraphEntry> graphs;
   bool use_graphs = true;
+  unsigned long long graph_flags = cudaGraphInstantiateFlagUseNodePriority;  // HIPPIE_B200_GRAPH_PRIO=0: every node at the caller's priority
   static constexpr size_t kMaxGraphs = 32;  // distinct call signatures kept as instantiated graphs
   cudaStream_t cap = nullptr;  // capture stream (the caller's stream may be the legacy default stream)
   // Data-parallel exchange without splitting the step (hippie_train_fwd_bwd_part, part 4): the whole step stays ONE
@@ -1328,7 +1329,7 @@ struct hippie_engine {
       cudaError_t ce = cudaStreamBeginCapture(cap, cudaStreamCaptureModeRelaxed);
       int rc = ce == cudaSuccess ? exec(s, cap) : (int)ce;
       if (ce == cudaSuccess) ce = cudaStreamEndCapture(cap, &g);
-      if (rc == 0 && ce == cudaSuccess && g) ce = cudaGraphInstantiate(&e.exec, g, 0);
+      if (rc == 0 && ce == cudaSuccess && g) ce = cudaGraphInstantiate(&e.exec, g, graph_flags);
       if (g) cudaGraphDestroy(g);
       if (rc != 0 || ce != cudaSuccess || !e.exec) {  // stay eager for this signature
         cudaGetLastError();
@@ -1455,17 +1456,28 @@ int hippie_bind(hippie_handle h, float* params, float* grads, float* exp_avg, fl
   if (const char* g = getenv("HIPPIE_B200_KEEP_PLANES")) h->planes_keep = atoi(g) != 0;
   if (const char* g = getenv("HIPPIE_B200_SHORTCUT_STREAM")) h->helper_max_batch = atoi(g);
   if (const char* g = getenv("HIPPIE_B200_GRAPHS")) h->use_graphs = atoi(g) != 0;
+  if (const char* g = getenv("HIPPIE_B200_GRAPH_PRIO")) h->graph_flags = atoi(g) ? cudaGraphInstantiateFlagUseNodePriority : 0;
   if (const char* g = getenv("HIPPIE_B200_TMA_STORE")) h->tma_epilogue = atoi(g) != 0;
   if (!h->side) {
-    // the branch chains are the critical path: they get the highest priority, the weight-gradient streams the lowest
-    int prio_lo = 0, prio_hi = 0;
-    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
-    cudaStreamCreateWithPriority(&h->side, cudaStreamNonBlocking, prio_hi);
-    cudaStreamCreateWithPriority(&h->cap, cudaStreamNonBlocking, prio_hi);
+    // Stream priorities, measured (gpurun_out/r02_exp39.txt, r02_exp40.txt): giving the branch chains the HIGHEST priority and
+    // the weight-gradient streams the lowest -- the obvious choice for a critical path -- starves the weight gradients until
+    // they run as an exposed tail behind the chains: eager bs512 step 3.79 ms, graph replay with per-node priorities 3.21 ms.
+    // The other way round (weight gradients take free SM slots first, the chains' few CTAs fit in between) gives 3.16 ms eager
+    // and 3.01 ms replayed; replay without node priorities (everything at the caller's priority) 3.03 ms.
+    int prio_chain = 0, prio_wgrad = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_chain, &prio_wgrad);  // (least, greatest): chains least, weight gradients greatest
+    if (const char* g = getenv("HIPPIE_B200_PRIO_INVERT"))  // 0: round-1 assignment (chains above the weight gradients)
+      if (!atoi(g)) std::swap(prio_chain, prio_wgrad);
+    int prio_side = prio_chain;
+    if (const char* g = getenv("HIPPIE_B200_PRIO"))  // experiment: "<chain 0>,<chain 1>,<weight gradients>"
+      sscanf(g, "%d,%d,%d", &prio_chain, &prio_side, &prio_wgrad);
+    cudaStreamCreateWithPriority(&h->side, cudaStreamNonBlocking, prio_side);
+    cudaStreamCreateWithPriority(&h->cap, cudaStreamNonBlocking, prio_chain);
     cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
-    for (int i = 0; i < 2; ++i) cudaStreamCreateWithPriority(&h->wside[i], cudaStreamNonBlocking, prio_lo);
-    for (int i = 0; i < 2; ++i) cudaStreamCreateWithPriority(&h->hside[i], cudaStreamNonBlocking, prio_hi);
-    cudaStreamCreateWithPriority(&h->xs, cudaStreamNonBlocking, prio_hi);
+    for (int i = 0; i < 2; ++i) cudaStreamCreateWithPriority(&h->wside[i], cudaStreamNonBlocking, prio_wgrad);
+    cudaStreamCreateWithPriority(&h->hside[0], cudaStreamNonBlocking, prio_chain);
+    cudaStreamCreateWithPriority(&h->hside[1], cudaStreamNonBlocking, prio_side);
+    cudaStreamCreateWithPriority(&h->xs, cudaStreamNonBlocking, prio_chain);
     for (int i = 0; i < 2; ++i) cudaEventCreateWithFlags(&h->ev_slice[i], cudaEventDisableTiming);
     h->ev_pool.resize(512);
     for (auto& e : h->ev_pool) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
