@@ -1,6 +1,8 @@
 // HBM-bound kernels of the cVAE step: stem conv, BatchNorm finalize / apply / backward, pooling +
 // linear tails, decoder head and tail (+ MSE), gradient clipping + AdamW.  All tensors are
 // channels-last padded rows (kernels.cuh).  Reference anchors are given per kernel.
+#include <cstdlib>
+
 #include "kernels.cuh"
 #include "pair_fmt.cuh"
 #include "pdl.cuh"
@@ -1142,9 +1144,11 @@ void launch_bn_bwd(const BnBwd& a, int sm_count, cudaStream_t s) {
   int rows = (M + kBnBwdMaxChunks - 1) / kBnBwdMaxChunks;
   if (rows < 16) rows = 16;
   const int nchunks = (M + rows - 1) / rows;
-  launch_pdl(bn_bwd_reduce_kernel<4>, dim3(nchunks), dim3(256), 0, s, a, rows);
+  // HIPPIE_B200_DEBUG_SKIP bit 1 / bit 2: knock-out experiments (wrong results): no reduce / no apply launch
+  static const int dbg_skip = getenv("HIPPIE_B200_DEBUG_SKIP") ? atoi(getenv("HIPPIE_B200_DEBUG_SKIP")) : 0;
+  if (!(dbg_skip & 2)) launch_pdl(bn_bwd_reduce_kernel<4>, dim3(nchunks), dim3(256), 0, s, a, rows);
   dim3 grid(a.C / kSlab, slab_row_chunks(M, a.C, sm_count));
-  launch_pdl(bn_bwd_apply_kernel, grid, dim3(256), 0, s, a, nchunks);
+  if (!(dbg_skip & 4)) launch_pdl(bn_bwd_apply_kernel, grid, dim3(256), 0, s, a, nchunks);
 }
 void launch_pairsum_acc(const float* src, float* dst, int B, int L, int C, cudaStream_t s) {
   launch_pdl(pairsum_acc_kernel, dim3(ew_grid((int64_t)B * L * (C / 4))), dim3(256), 0, s, src, dst, B, L, C);
