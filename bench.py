@@ -218,7 +218,8 @@ def main():
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":  # the version banner is a bare printf to stdout
             os.environ["NCCL_DEBUG"] = "WARN"
-        dist.init_process_group("nccl", device_id=dev)
+        from hippie_b200.parallel import nccl_group_options
+        dist.init_process_group("nccl", device_id=dev, **nccl_group_options("nccl"))
     from hippie_b200.model import MultiModalCVAE, MultiModalCVAETrainModule
     from hippie_b200.parallel import train_step_overlapped
 
