@@ -56,18 +56,26 @@ __global__ void __launch_bounds__(256) stem_fwd_kernel(const float* __restrict__
   const int co = threadIdx.x & 63, rg = threadIdx.x >> 6;
   const int M = B * Lout, m0 = blockIdx.x * 128;
   const float w0 = w[co * 3 + 0], w1 = w[co * 3 + 1], w2 = w[co * 3 + 2];
+  // the thread's 32 outputs stay in registers between the two passes of the centred statistics (the loads of a row are
+  // warp-uniform broadcasts; unrolled so that they are all in flight at once: 20 -> ~8 us on the ISI branch)
+  float v[32];
   float s = 0.f;
-  for (int r = rg; r < 128; r += 4) {
-    int m = m0 + r;
-    if (m >= M) break;
-    int b = m / Lout, l = m - b * Lout;
-    const float* xb = x + (int64_t)b * Lin;
-    float v = w0 * xin(xb, Lin, 2 * l - 1);
-    v = fmaf(w1, xin(xb, Lin, 2 * l), v);
-    v = fmaf(w2, xin(xb, Lin, 2 * l + 1), v);
-    c0[((int64_t)b * (Lout + 2) + 1 + l) * 64 + co] = v;
-    s += v;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    const int m = m0 + rg + 4 * j;
+    v[j] = 0.f;
+    if (m < M) {
+      const int b = m / Lout, l = m - b * Lout;
+      const float* xb = x + (int64_t)b * Lin;
+      float t = w0 * xin(xb, Lin, 2 * l - 1);
+      t = fmaf(w1, xin(xb, Lin, 2 * l), t);
+      t = fmaf(w2, xin(xb, Lin, 2 * l + 1), t);
+      c0[((int64_t)b * (Lout + 2) + 1 + l) * 64 + co] = t;
+      v[j] = t;
+    }
   }
+#pragma unroll
+  for (int j = 0; j < 32; ++j) s += v[j];  // same order as the sequential loop (invalid rows add 0)
   if (!part) return;
   red[rg][co] = s;
   __syncthreads();
@@ -77,12 +85,12 @@ __global__ void __launch_bounds__(256) stem_fwd_kernel(const float* __restrict__
   __syncthreads();
   const float mu = smean[co];
   float q = 0.f;
-  for (int r = rg; r < 128; r += 4) {
-    int m = m0 + r;
-    if (m >= M) break;
-    int b = m / Lout, l = m - b * Lout;
-    float d = c0[((int64_t)b * (Lout + 2) + 1 + l) * 64 + co] - mu;
-    q += d * d;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    if (m0 + rg + 4 * j < M) {
+      const float d = v[j] - mu;
+      q += d * d;
+    }
   }
   __syncthreads();
   red[rg][co] = q;
