@@ -331,33 +331,54 @@ __global__ void __launch_bounds__(TC_THREADS, reg_ctas_per_sm(BN, STAGES))
         fbe = *reinterpret_cast<const float4*>(fo.coef + 1 * p.N + n0 + quad * 4);
         fmu = *reinterpret_cast<const float4*>(fo.coef + 2 * p.N + n0 + quad * 4);
       }
-      for (int r = t / QUADS; r < nvalid; r += 128 / QUADS) {
-        const int bs = r / p.Lout, l = r - bs * p.Lout;
-        float4 v = *reinterpret_cast<const float4*>(&stage[S::epi(r, quad * 4)]);
-        const int64_t off = ((int64_t)(b0 + bs) * p.out_rows + p.out_off + (int64_t)l * p.out_lstride) * p.N + n0 + quad * 4;
-        float4* dst = reinterpret_cast<float4*>(p.C + off);
-        if (B_MN && p.accumulate) {
-          const float4 o = *dst;
-          v.x += o.x, v.y += o.y, v.z += o.z, v.w += o.w;
+      constexpr int RSTEP = 128 / QUADS;  // rows covered by one pass of the 128 threads
+      if (EVAL && fo.coef) {
+        // Four rows per thread and iteration, every load (staging, residual) issued before the first use: with one row per
+        // iteration the residual's L2 round trip (~0.6 us) was paid 16 times per tile in sequence and this epilogue, not the
+        // main loop, bounded the shallow layers of the embedding pass (K = 192: 1.3 us of MMAs per tile).
+        constexpr int U = 4;
+        for (int r0 = t / QUADS; r0 < nvalid; r0 += U * RSTEP) {
+          float4 v[U], rr[U];
+          int64_t off[U];
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const int r = min(r0 + u * RSTEP, nvalid - 1);  // clamped rows are loaded twice and stored never
+            const int bs = r / p.Lout, l = r - bs * p.Lout;
+            off[u] = ((int64_t)(b0 + bs) * p.out_rows + p.out_off + (int64_t)l * p.out_lstride) * p.N + n0 + quad * 4;
+            v[u] = *reinterpret_cast<const float4*>(&stage[S::epi(r, quad * 4)]);
+            rr[u] = fo.res ? __ldg(reinterpret_cast<const float4*>(fo.res + off[u])) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const int r = r0 + u * RSTEP;
+            if (r >= nvalid) break;
+            // same expressions as bn_apply_kernel: the folded result is bit-identical to conv + apply
+            float4 y;
+            y.x = fmaf(v[u].x - fmu.x, fsc.x, fbe.x), y.y = fmaf(v[u].y - fmu.y, fsc.y, fbe.y);
+            y.z = fmaf(v[u].z - fmu.z, fsc.z, fbe.z), y.w = fmaf(v[u].w - fmu.w, fsc.w, fbe.w);
+            if (fo.res) y.x += rr[u].x, y.y += rr[u].y, y.z += rr[u].z, y.w += rr[u].w;
+            y.x = y.x > 0.f ? y.x : y.x * fo.slope, y.y = y.y > 0.f ? y.y : y.y * fo.slope;
+            y.z = y.z > 0.f ? y.z : y.z * fo.slope, y.w = y.w > 0.f ? y.w : y.w * fo.slope;
+            if (fo.write_f32) *reinterpret_cast<float4*>(p.C + off[u]) = y;
+            if (fo.out_p) store_pair4(fo.out_p, fo.out_ps, off[u], y, fo.flags);
+            if (fo.up_p) {
+              const int bs = r / p.Lout, l = r - bs * p.Lout;
+              const int64_t ou = ((int64_t)(b0 + bs) * (2 * p.Lout + 2) + 1 + 2 * l) * p.N + n0 + quad * 4;
+              store_pair4(fo.up_p, fo.up_ps, ou, y);
+              store_pair4(fo.up_p, fo.up_ps, ou + p.N, y);
+            }
+          }
         }
-        if (EVAL && fo.coef) {  // same expressions as bn_apply_kernel: the folded result is bit-identical to conv + apply
-          float4 y;
-          y.x = fmaf(v.x - fmu.x, fsc.x, fbe.x), y.y = fmaf(v.y - fmu.y, fsc.y, fbe.y);
-          y.z = fmaf(v.z - fmu.z, fsc.z, fbe.z), y.w = fmaf(v.w - fmu.w, fsc.w, fbe.w);
-          if (fo.res) {
-            const float4 rr = *reinterpret_cast<const float4*>(fo.res + off);
-            y.x += rr.x, y.y += rr.y, y.z += rr.z, y.w += rr.w;
+      } else {
+        for (int r = t / QUADS; r < nvalid; r += RSTEP) {
+          const int bs = r / p.Lout, l = r - bs * p.Lout;
+          float4 v = *reinterpret_cast<const float4*>(&stage[S::epi(r, quad * 4)]);
+          const int64_t off = ((int64_t)(b0 + bs) * p.out_rows + p.out_off + (int64_t)l * p.out_lstride) * p.N + n0 + quad * 4;
+          float4* dst = reinterpret_cast<float4*>(p.C + off);
+          if (B_MN && p.accumulate) {
+            const float4 o = *dst;
+            v.x += o.x, v.y += o.y, v.z += o.z, v.w += o.w;
           }
-          y.x = y.x > 0.f ? y.x : y.x * fo.slope, y.y = y.y > 0.f ? y.y : y.y * fo.slope;
-          y.z = y.z > 0.f ? y.z : y.z * fo.slope, y.w = y.w > 0.f ? y.w : y.w * fo.slope;
-          if (fo.write_f32) *dst = y;
-          if (fo.out_p) store_pair4(fo.out_p, fo.out_ps, off, y, fo.flags);
-          if (fo.up_p) {
-            const int64_t ou = ((int64_t)(b0 + bs) * (2 * p.Lout + 2) + 1 + 2 * l) * p.N + n0 + quad * 4;
-            store_pair4(fo.up_p, fo.up_ps, ou, y);
-            store_pair4(fo.up_p, fo.up_ps, ou + p.N, y);
-          }
-        } else {
           *dst = v;
         }
       }
