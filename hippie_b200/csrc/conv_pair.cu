@@ -685,6 +685,7 @@ static void set_smem_attrs() {
 static int g_variant = 0, g_wgrad_variant = 1, g_pdl_late = 0;
 static int g_mma_scheme = 7;  // HIPPIE_B200_MMA_SCHEME bits: 1 forward, 2 dgrad, 4 wgrad issue A hi x [B hi | B lo] as one instruction
 static int g_fake_k = 0;
+static bool g_fake_reuse = false;
 static int g_bwd_nmma = 3;  // HIPPIE_B200_BWD_MMA=2: accuracy experiment, dgrad / wgrad without the (gradient lo) x (hi) product
 static int g_wgrad_min_kb = 16;  // k-blocks (of 64 reduction rows) a weight-gradient CTA processes at least: the kernels are off
 // the critical path, so few long-lived CTAs (less prologue / fill / epilogue time per MAC) beat many short ones -- the step is
@@ -708,8 +709,11 @@ bool pair_init(std::string* err) {
   if (const char* v = getenv("HIPPIE_B200_PAIR_VARIANT")) g_variant = atoi(v);  // 0 auto, 1 always shared, 2 always alone
   if (const char* v = getenv("HIPPIE_B200_PDL_LATE")) g_pdl_late = atoi(v);
   if (const char* v = getenv("HIPPIE_B200_MMA_SCHEME")) g_mma_scheme = atoi(v);
+#ifdef HP_EXPERIMENTS  // result-changing speed experiments of DESIGN 4.3: only in builds made with EXTRA=-DHP_EXPERIMENTS
   if (const char* v = getenv("HIPPIE_B200_FAKE_K")) g_fake_k = atoi(v);
   if (const char* v = getenv("HIPPIE_B200_BWD_MMA")) g_bwd_nmma = atoi(v) == 2 ? 2 : 3;
+  g_fake_reuse = getenv("HIPPIE_B200_FAKE_REUSE") != nullptr;
+#endif
   if (const char* v = getenv("HIPPIE_B200_WGRAD_VARIANT")) g_wgrad_variant = atoi(v);  // 1 shared (two CTAs per SM), 2 alone
   if (const char* v = getenv("HIPPIE_B200_WGRAD_MIN_KB")) g_wgrad_min_kb = atoi(v) > 0 ? atoi(v) : 16;
   int dev = 0;
@@ -806,7 +810,7 @@ int launch_conv_pair(const ConvGemm& g, const TcMap& mapA, const TcMap& mapB, in
   p.idesc2 = umma_idesc_16(2 * bn, o.a_fmt, o.b_fmt, 0, o.b_mn ? 1 : 0);
   p.nmma = o.b_mn ? g_bwd_nmma : 3;
   p.fused = (g_mma_scheme >> (o.b_mn ? 1 : 0)) & 1;
-  p.fake_reuse = (getenv("HIPPIE_B200_FAKE_REUSE") && o.taps == 3) ? 1 : 0;
+  p.fake_reuse = (g_fake_reuse && o.taps == 3) ? 1 : 0;
   p.fake_k = g_fake_k;
   p.b_mn = o.b_mn, p.taps = o.taps, p.kb_per_tap = o.taps > 0 ? (g.K / o.taps) / PK : 1;
   p.dyn_scale = o.dyn_scale, p.stamps = o.stamps, p.stamps_all = o.stamps_all, p.pdl_late = g_pdl_late & 1;

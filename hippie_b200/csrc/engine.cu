@@ -770,8 +770,10 @@ struct hippie_engine {
     cudaStream_t wst = br.wst ? br.wst : br.st;
     side_wait(br);  // dY is final once the stream reaches this point; everything the wgrad reads stays untouched
     cudaEvent_t pe = prof_begin(br);
+#ifdef HP_EXPERIMENTS  // knock-out runs of DESIGN 4.2 / 4.3 (wrong results): only in builds made with EXTRA=-DHP_EXPERIMENTS
     static const int dbg_skip = getenv("HIPPIE_B200_DEBUG_SKIP") ? atoi(getenv("HIPPIE_B200_DEBUG_SKIP")) : 0;
-    if (dbg_skip & 1) return;  // timing experiment only (tools/exp17.sh): no weight gradients
+    if (dbg_skip & 1) return;  // no weight gradients
+#endif
     if (use_tc) {
       ConvMaps& m = cmaps[cv.id];
       if (m.wg_B != B) {

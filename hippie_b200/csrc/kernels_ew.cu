@@ -1152,8 +1152,13 @@ void launch_bn_bwd(const BnBwd& a, int sm_count, cudaStream_t s) {
   int rows = (M + kBnBwdMaxChunks - 1) / kBnBwdMaxChunks;
   if (rows < 16) rows = 16;
   const int nchunks = (M + rows - 1) / rows;
-  // HIPPIE_B200_DEBUG_SKIP bit 1 / bit 2: knock-out experiments (wrong results): no reduce / no apply launch
+  // HIPPIE_B200_DEBUG_SKIP bits 2 / 4: knock-out experiments (wrong results: no reduce / no apply launch), only in builds
+  // made with EXTRA=-DHP_EXPERIMENTS
+#ifdef HP_EXPERIMENTS
   static const int dbg_skip = getenv("HIPPIE_B200_DEBUG_SKIP") ? atoi(getenv("HIPPIE_B200_DEBUG_SKIP")) : 0;
+#else
+  constexpr int dbg_skip = 0;
+#endif
   if (!(dbg_skip & 2)) launch_pdl(bn_bwd_reduce_kernel<4>, dim3(nchunks), dim3(256), 0, s, a, rows);
   dim3 grid(a.C / kSlab, slab_row_chunks(M, a.C, sm_count));
   if (!(dbg_skip & 4)) launch_pdl(bn_bwd_apply_kernel, grid, dim3(256), 0, s, a, nchunks);

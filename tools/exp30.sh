@@ -1,4 +1,6 @@
 #!/bin/bash
+# tools/libold.so / libB.so / lib4.so / libprev.so: libraries built from the commit before (or with the variant named in the echo lines) and copied next to this script
+# needs a library built with: make -C hippie_b200/csrc clean all EXTRA=-DHP_EXPERIMENTS
 # A/B of the concatenated-B MMA scheme: old (three N = 64 MMAs per k-step) vs new (N = 128 + N = 64)
 out=gpurun_out/r02_concat_ab.txt
 {

@@ -1,4 +1,5 @@
 #!/bin/bash
+# tools/libold.so / libB.so / lib4.so / libprev.so: libraries built from the commit before (or with the variant named in the echo lines) and copied next to this script
 # (1) old vs new library on the bs512 / bs64 step, interleaved; (2) weight-gradient CTAs limited to one per SM by a
 # shared-memory pad; (3) gradient error table with the (gradient lo) x (hi) product dropped in dgrad / wgrad
 out=gpurun_out/r02_exp31.txt

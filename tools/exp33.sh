@@ -1,4 +1,5 @@
 #!/bin/bash
+# tools/libold.so / libB.so / lib4.so / libprev.so: libraries built from the commit before (or with the variant named in the echo lines) and copied next to this script
 # register budgets: GEMM CTAs at 96 registers (A: BatchNorm kernels capped at 112 too, B: BatchNorm kernels uncapped) vs the
 # round-2 library (old: 122 registers, three N = 64 MMAs per k-step)
 out=gpurun_out/r02_exp33.txt

@@ -1,4 +1,5 @@
 #!/bin/bash
+# tools/libold.so / libB.so / lib4.so / libprev.so: libraries built from the commit before (or with the variant named in the echo lines) and copied next to this script
 # GEMM CTAs at 96 (cur) vs 80 (lib4) registers
 out=gpurun_out/r02_exp34.txt
 cp hippie_b200/libhippie_b200.so /tmp/cur.so

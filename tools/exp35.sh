@@ -1,4 +1,5 @@
 #!/bin/bash
+# needs a library built with: make -C hippie_b200/csrc clean all EXTRA=-DHP_EXPERIMENTS
 # upper bound of what re-using one A slab for the three taps of a k3 conv / dgrad would give: A fetched for one k-block in
 # three (results are wrong, speed only)
 out=gpurun_out/r02_exp35.txt

@@ -1,4 +1,5 @@
 #!/bin/bash
+# needs a library built with: make -C hippie_b200/csrc clean all EXTRA=-DHP_EXPERIMENTS
 # floor of the step without GEMM main loops: every conv / dgrad / wgrad CTA processes at most FAKE_K k-blocks (wrong results)
 out=gpurun_out/r02_exp36.txt
 {

@@ -1,4 +1,5 @@
 #!/bin/bash
+# needs a library built with: make -C hippie_b200/csrc clean all EXTRA=-DHP_EXPERIMENTS
 # knock-outs (wrong results): 1 = no weight gradients, 2 = no BatchNorm-backward reduce launches, 4 = no BatchNorm-backward apply launches
 out=gpurun_out/r02_exp42.txt
 {

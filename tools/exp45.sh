@@ -1,4 +1,5 @@
 #!/bin/bash
+# tools/libold.so / libB.so / lib4.so / libprev.so: libraries built from the commit before (or with the variant named in the echo lines) and copied next to this script
 # eval-mode epilogue: four rows per thread and iteration (cur) vs one (prev = tools/libprev.so, built from the commit before)
 out=gpurun_out/r02_exp45.txt
 cp hippie_b200/libhippie_b200.so /tmp/cur.so
