@@ -258,7 +258,8 @@ def test_parameter_writes_behind_the_engine_are_seen():
     fresh.bn_mean.copy_(eng.bn_mean), fresh.bn_var.copy_(eng.bn_var)
     assert torch.equal(fresh.embed(*io)["mu"], ref1)
     w.data.mul_(1.0 / 1.5)  # bypasses the counter: stale planes until reported
-    assert torch.equal(eng.embed(*io)["mu"], ref1)
+    if os.environ.get("HIPPIE_B200_KEEP_PLANES", "1") != "0":  # (the switch converts the planes in every call)
+        assert torch.equal(eng.embed(*io)["mu"], ref1)
     eng.params_changed()
     fresh.flat_params.copy_(eng.flat_params)
     assert torch.equal(eng.embed(*io)["mu"], fresh.embed(*io)["mu"])
