@@ -46,16 +46,15 @@ namespace {
 using namespace tc;
 
 constexpr int PK = 64;  // K elements per k-block = one 128-byte swizzle row of 16-bit values
-// Tile configuration: 128 x 64 output tile, 2-stage ring (96 KB), 192 TMEM columns -> TWO CTAs per SM, so that the
-// prologue / epilogue of one CTA (or of the next kernel, see pdl.cuh) overlaps the main loop of the other.  Measured on
-// the bs512 step: 4.77 ms (128x128 + 128x64 tiles, 1 CTA/SM) -> 4.36 ms; the step is bound by the chain of short
-// dependent kernels, not by tile efficiency.
-// Phase stamps of one CTA (tools/pair_test, PT_STAMPS=1): prologue 0.26 us, first fill 0.67 us, main loop 0.53 us per
-// k-block (ANY layer, any grid), epilogue 3.3 us with per-thread stores and 1.8 us with TMA stores (TMEM -> staging
-// 0.45, store issue 0.16, BatchNorm partials 1.2).  The k-block period is set by the TMA unit's ROW rate, not by bytes:
-// a k-block is 384 box rows of 128 B; halving the rows to 64 B (32-wide k-blocks, 64-byte swizzle, 4 stages: tried)
-// costs 0.38 us per half block, i.e. the same ~1.4 ns per row.  More MACs per fetched row (wider tiles, 2-CTA pairs)
-// is the way to a faster main loop; deeper rings are not.
+// Tile configuration: 128 x 64 output tile, 2-stage ring (96 KB), 256 TMEM columns -> TWO CTAs per SM, so that the
+// prologue / epilogue of one CTA (or of the next kernel, see pdl.cuh) overlaps the main loop of the other and the two
+// branches of the model (and the weight gradients) share every SM.  Tiles that own the SM (128 x 128, 3 stages) are
+// 13-17 % faster on the deep layers in isolation and slower in every real pass (round 1: 4.77 vs 4.36 ms per bs512 step;
+// round 2: embedding pass -1.5 % at bs4096, -9 % at bs512, profiles/r02_exp46.txt, r02_exp47.txt).
+// Phase stamps of one CTA (tools/pair_test, PT_STAMPS=1): prologue 0.26 us, first fill 0.67 us, main loop 0.42-0.46 us per
+// k-block alone and ~0.55 us when every SM holds two CTAs (the chip-wide L2 -> SM rate: 2 x 48 KB per k-block pair at
+// ~42 B/clk per SM), epilogue 1.8 us (TMEM -> staging 0.45, store issue 0.16, BatchNorm partials 1.2).
+// 32-wide k-blocks (64-byte swizzle, 4 stages: tried) cost 0.38 us per half block; deeper rings change nothing.
 #ifndef HP_KBN
 #define HP_KBN 64
 #endif
@@ -68,10 +67,10 @@ constexpr int kBN = HP_KBN, kStages = HP_KSTAGES;  // overridable for tools/pair
 // L2 -> shared-memory ingest while other SMs idle (512->512 L=4, 128 CTAs: 21.0 -> 16.1 us, tools/pair_test).
 constexpr int kStagesAlone = HP_KSTAGES > 3 ? HP_KSTAGES : 3;
 constexpr int ctas_per_sm(int bn, int stages) { return (PK * 2 * (128 + bn) * 2 * stages <= 100 * 1024 && bn <= 64) ? 2 : 1; }
-// Register budget: the kernels are compiled as if THREE CTAs had to fit on an SM (<= 112 registers per thread).  Two fit by
-// shared memory; the registers they leave free decide whether a CTA of an elementwise kernel (BatchNorm apply / backward, on the
-// critical chains) can start on an SM that already holds two GEMM CTAs: at 154 registers nothing fits and the bs512 step is 4 %
-// slower than at 122 (gpurun_out/r02_exp32.txt).
+// Register budget: the kernels are compiled as if THREE CTAs had to fit on an SM (ptxas settles on 96 registers, 4-8 bytes of
+// spill).  Two fit by shared memory; the registers they leave free decide whether a CTA of an elementwise kernel (BatchNorm
+// apply / backward, on the critical chains) can start on an SM that already holds two GEMM CTAs: 154 registers 3.06 ms per
+// bs512 step, 96 registers 2.98 ms, 80 registers (76-84 bytes of spill) 3.02 ms (profiles/r02_exp32.txt - r02_exp34.txt).
 constexpr int reg_ctas_per_sm(int bn, int stages) { return ctas_per_sm(bn, stages) == 2 ? 3 : 1; }
 
 struct PairConv {
